@@ -1,0 +1,477 @@
+/*
+ * lqcd_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  *** PARITY UNPINNED ***
+ * See lqcd_oracle.h for scope, layouts and the pinning statement.
+ *
+ * Each routine cites the reference call site it serves (paths relative to /root/reference) and the
+ * SURVEY.md appendix that restates the upstream (LatticeDiracOperators.jl 0.6.x) algorithm it follows.
+ */
+#include "lqcd_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
+/* ---- gamma matrices: upstream WilsonFermion constructor tables (recalled) ---- */
+void orc_set_gamma(orc_op *op, double r) {
+    zc g[4][4][4];
+    memset(g, 0, sizeof g);
+    /* 0-based [mu][row][col]; the 1-based table in SURVEY.md 8c */
+    g[0][0][3] = -I; g[0][1][2] = -I; g[0][2][1] =  I; g[0][3][0] =  I;
+    g[1][0][3] = -1; g[1][1][2] =  1; g[1][2][1] =  1; g[1][3][0] = -1;
+    g[2][0][2] = -I; g[2][1][3] =  I; g[2][2][0] =  I; g[2][3][1] = -I;
+    g[3][0][2] = -1; g[3][1][3] = -1; g[3][2][0] = -1; g[3][3][1] = -1;
+    for (int mu = 0; mu < 4; mu++)
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) {
+                zc id = (a == b) ? r : 0.0;
+                op->rplusg[mu][a][b]  = id + g[mu][a][b];
+                op->rminusg[mu][a][b] = id - g[mu][a][b];
+            }
+    op->r = r;
+}
+
+/* ---- geometry ---- */
+typedef struct { int64_t V; int d[4]; int64_t stride[4]; } geom;
+static geom mkgeom(const int dims[4]) {
+    geom g; g.V = 1;
+    for (int i = 0; i < 4; i++) { g.d[i] = dims[i]; g.stride[i] = g.V; g.V *= dims[i]; }
+    return g;
+}
+static inline void site_coords(const geom *g, int64_t s, int c[4]) {
+    for (int i = 0; i < 4; i++) { c[i] = (int)(s % g->d[i]); s /= g->d[i]; }
+}
+/* neighbour in +/-mu with wrap flag */
+static inline int64_t nbr(const geom *g, int64_t s, const int c[4], int mu, int sign, int *wrapped) {
+    if (sign > 0) {
+        if (c[mu] == g->d[mu] - 1) { *wrapped = 1; return s - (int64_t)(g->d[mu] - 1) * g->stride[mu]; }
+        *wrapped = 0; return s + g->stride[mu];
+    } else {
+        if (c[mu] == 0) { *wrapped = 1; return s + (int64_t)(g->d[mu] - 1) * g->stride[mu]; }
+        *wrapped = 0; return s - g->stride[mu];
+    }
+}
+
+/* ---- Wilson hopping, LinearAlgebra.mul!(y, D, x) -> upstream Wx!
+ *      served call sites: AbstractMD.jl:129 (inside calc_UdSfdU!), standardHMC.jl:69-71,
+ *      measurements/unusedfiles/measure_Pion_correlator.jl:379,399.
+ *  Per direction nu, in the reference's order of operations:
+ *      temp1 = (r - gamma_nu) [U_nu(n) x(n+nu)],  temp2 = (r + gamma_nu) [U_nu^dag(n-nu) x(n-nu)],
+ *      acc  += kappa*temp1 + kappa*temp2;   finally y = x - acc.
+ *  dagger swaps (r-gamma) <-> (r+gamma)  (upstream Wdagx!).  Boundary phase bc[nu] multiplies the shifted
+ *  spinor when the shift wraps (upstream applies it when filling the fermion "wing").                    */
+static void wilson_apply(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x) {
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V;
+    const zc (*Gf)[4][4] = dagger ? op->rplusg : op->rminusg;   /* multiplies the forward hop */
+    const zc (*Gb)[4][4] = dagger ? op->rminusg : op->rplusg;   /* multiplies the backward hop */
+    const double kappa = op->kappa;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        zc acc[4][3];
+        memset(acc, 0, sizeof acc);
+        for (int nu = 0; nu < 4; nu++) {
+            int wf, wb;
+            int64_t sf = nbr(&g, s, c, nu, +1, &wf);
+            int64_t sb = nbr(&g, s, c, nu, -1, &wb);
+            double pf = wf ? op->bc[nu] : 1.0, pb = wb ? op->bc[nu] : 1.0;
+            const zc *Uf = u[nu] + 9 * s;     /* U_nu(n)      [a + 3 b] */
+            const zc *Ub = u[nu] + 9 * sb;    /* U_nu(n - nu)           */
+            zc h[4][3], gq[4][3];
+            for (int al = 0; al < 4; al++) {
+                zc xf[3], xb[3];
+                for (int b = 0; b < 3; b++) {
+                    xf[b] = pf * x[b + 3 * (sf + V * al)];
+                    xb[b] = pb * x[b + 3 * (sb + V * al)];
+                }
+                for (int a = 0; a < 3; a++) {
+                    zc sfw = 0, sbw = 0;
+                    for (int b = 0; b < 3; b++) {
+                        sfw += Uf[a + 3 * b] * xf[b];             /* U x          */
+                        sbw += conj(Ub[b + 3 * a]) * xb[b];       /* U^dag x      */
+                    }
+                    h[al][a] = sfw; gq[al][a] = sbw;
+                }
+            }
+            for (int al = 0; al < 4; al++)
+                for (int a = 0; a < 3; a++) {
+                    zc t1 = 0, t2 = 0;
+                    for (int be = 0; be < 4; be++) {
+                        t1 += Gf[nu][al][be] * h[be][a];
+                        t2 += Gb[nu][al][be] * gq[be][a];
+                    }
+                    acc[al][a] += kappa * t1 + kappa * t2;
+                }
+        }
+        for (int al = 0; al < 4; al++)
+            for (int a = 0; a < 3; a++)
+                y[a + 3 * (s + V * al)] = x[a + 3 * (s + V * al)] - acc[al][a];
+    }
+}
+
+/* ---- staggered, mul!(y, D, x) -> upstream Dx! + mass
+ *      y = m x + sum_nu (1/2) eta_nu(n) [U_nu(n) x(n+nu) - U_nu^dag(n-nu) x(n-nu)],
+ *      eta_1 = 1, eta_2 = (-1)^x, eta_3 = (-1)^(x+y), eta_4 = (-1)^(x+y+z);  D^dag = m - hop.          */
+static void staggered_apply(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x) {
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V;
+    const double sgn = dagger ? -1.0 : 1.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        zc acc[3] = {0, 0, 0};
+        int esum = 0;
+        for (int nu = 0; nu < 4; nu++) {
+            double eta = (esum & 1) ? -1.0 : 1.0;
+            esum += c[nu];
+            int wf, wb;
+            int64_t sf = nbr(&g, s, c, nu, +1, &wf);
+            int64_t sb = nbr(&g, s, c, nu, -1, &wb);
+            double pf = wf ? op->bc[nu] : 1.0, pb = wb ? op->bc[nu] : 1.0;
+            const zc *Uf = u[nu] + 9 * s, *Ub = u[nu] + 9 * sb;
+            for (int a = 0; a < 3; a++) {
+                zc t1 = 0, t2 = 0;
+                for (int b = 0; b < 3; b++) {
+                    t1 += Uf[a + 3 * b] * (pf * x[b + 3 * sf]);
+                    t2 += conj(Ub[b + 3 * a]) * (pb * x[b + 3 * sb]);
+                }
+                acc[a] += eta * (0.5 * t1 - 0.5 * t2);
+            }
+        }
+        for (int a = 0; a < 3; a++) y[a + 3 * s] = op->mass * x[a + 3 * s] + sgn * acc[a];
+    }
+}
+
+static int64_t field_len(const orc_op *op, int kind) {
+    int64_t V = (int64_t)op->dims[0] * op->dims[1] * op->dims[2] * op->dims[3];
+    return kind == ORC_WILSON ? 12 * V : 3 * V;
+}
+
+void orc_apply(const orc_op *op, int kind, int mode, zc *y, const zc *const u[4], const zc *x, zc *scratch) {
+    if (mode == ORC_DDAGD) {   /* upstream DdagD: y = D^dag (D x) through one scratch field */
+        zc *t = scratch ? scratch : (zc *)malloc(sizeof(zc) * field_len(op, kind));
+        orc_apply(op, kind, ORC_D, t, u, x, NULL);
+        orc_apply(op, kind, ORC_DDAG, y, u, t, NULL);
+        if (!scratch) free(t);
+        return;
+    }
+    if (kind == ORC_WILSON) wilson_apply(op, mode == ORC_DDAG, y, u, x);
+    else                    staggered_apply(op, mode == ORC_DDAG, y, u, x);
+}
+
+/* ---- BLAS-1 (upstream add!, dot; standardHMC.jl:54 dot(xi,xi)) ---- */
+zc orc_dot(const zc *a, const zc *b, int64_t n) {
+    double re = 0, im = 0;
+#pragma omp parallel for reduction(+ : re, im) schedule(static)
+    for (int64_t i = 0; i < n; i++) { zc t = conj(a[i]) * b[i]; re += creal(t); im += cimag(t); }
+    return re + im * I;
+}
+static void axpy(zc *y, zc a, const zc *x, int64_t n) {        /* y += a x   (add!(y, a, x)) */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) y[i] += a * x[i];
+}
+static void xpby(zc *y, const zc *x, zc b, int64_t n) {        /* y = b y + x (add!(b, y, 1, x)) */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) y[i] = b * y[i] + x[i];
+}
+static void copyv(zc *y, const zc *x, int64_t n) { memcpy(y, x, sizeof(zc) * n); }
+
+/* ---- CG on A = D^dag D: solve_DinvX!(y, DdagD, x)
+ *      call sites: calc_UdSfdU! (AbstractMD.jl:129), evaluate_FermiAction (standardHMC.jl:69-71).      */
+int orc_cg(const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+           double eps, int maxsteps, double *resid_sq, double *hist) {
+    const int64_t n = field_len(op, kind);
+    zc *res = malloc(sizeof(zc) * n), *q = malloc(sizeof(zc) * n), *p = malloc(sizeof(zc) * n),
+       *t = malloc(sizeof(zc) * n);
+    int ret = -1;
+    orc_apply(op, kind, ORC_DDAGD, q, u, x, t);
+    copyv(res, b, n); axpy(res, -1.0, q, n);
+    copyv(p, res, n);
+    double rnorm = creal(orc_dot(res, res, n));
+    if (hist) hist[0] = rnorm;
+    if (rnorm < eps) { ret = 0; goto done; }
+    for (int i = 1; i <= maxsteps; i++) {
+        orc_apply(op, kind, ORC_DDAGD, q, u, p, t);
+        double c1 = creal(orc_dot(p, q, n));
+        double alpha = rnorm / c1;
+        axpy(x, alpha, p, n);
+        axpy(res, -alpha, q, n);
+        double c3 = creal(orc_dot(res, res, n));
+        if (hist) hist[i] = c3;
+        if (c3 < eps) { rnorm = c3; ret = i; goto done; }
+        double beta = c3 / rnorm;
+        xpby(p, res, beta, n);
+        rnorm = c3;
+    }
+done:
+    if (resid_sq) *resid_sq = rnorm;
+    free(res); free(q); free(p); free(t);
+    return ret;
+}
+
+/* ---- upstream "bicg" = CGNR on A = D: solve_DinvX!(y, D, x)
+ *      call sites: measure_Pion_correlator.jl:399, measure_chiral_condensate.jl:182 (via QCDMeasurements). */
+int orc_cgnr(const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+             double eps, int maxsteps, double *resid_sq, double *hist) {
+    const int64_t n = field_len(op, kind);
+    zc *res = malloc(sizeof(zc) * n), *q = malloc(sizeof(zc) * n), *p = malloc(sizeof(zc) * n);
+    int ret = -1;
+    orc_apply(op, kind, ORC_D, q, u, x, NULL);
+    copyv(res, b, n); axpy(res, -1.0, q, n);
+    double rnorm = creal(orc_dot(res, res, n));
+    if (hist) hist[0] = rnorm;
+    if (rnorm < eps) { ret = 0; goto done; }
+    orc_apply(op, kind, ORC_DDAG, q, u, res, NULL);
+    copyv(p, q, n);
+    double c1 = creal(orc_dot(q, q, n));
+    for (int i = 1; i <= maxsteps; i++) {
+        orc_apply(op, kind, ORC_D, q, u, p, NULL);
+        double c2 = creal(orc_dot(q, q, n));
+        double alpha = c1 / c2;
+        axpy(res, -alpha, q, n);
+        axpy(x, alpha, p, n);
+        rnorm = creal(orc_dot(res, res, n));
+        if (hist) hist[i] = rnorm;
+        if (rnorm < eps) { ret = i; goto done; }
+        orc_apply(op, kind, ORC_DDAG, q, u, res, NULL);
+        double c3 = creal(orc_dot(q, q, n));
+        double beta = c3 / c1;
+        c1 = c3;
+        xpby(p, q, beta, n);
+    }
+done:
+    if (resid_sq) *resid_sq = rnorm;
+    free(res); free(q); free(p);
+    return ret;
+}
+
+/* ---- BiCGStab on A = D (params["method_CG"]="bicgstab", SURVEY.md App. C.4 last line).
+ *      Textbook van der Vorst recurrences with shadow residual r0~ = r0; same stopping rule.           */
+int orc_bicgstab(const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+                 double eps, int maxsteps, double *resid_sq, double *hist) {
+    const int64_t n = field_len(op, kind);
+    zc *r = malloc(sizeof(zc) * n), *r0 = malloc(sizeof(zc) * n), *p = malloc(sizeof(zc) * n),
+       *v = malloc(sizeof(zc) * n), *s = malloc(sizeof(zc) * n), *t = malloc(sizeof(zc) * n);
+    int ret = -1;
+    orc_apply(op, kind, ORC_D, v, u, x, NULL);
+    copyv(r, b, n); axpy(r, -1.0, v, n);
+    copyv(r0, r, n); copyv(p, r, n);
+    double rnorm = creal(orc_dot(r, r, n));
+    if (hist) hist[0] = rnorm;
+    if (rnorm < eps) { ret = 0; goto done; }
+    zc rho = orc_dot(r0, r, n);
+    for (int i = 1; i <= maxsteps; i++) {
+        orc_apply(op, kind, ORC_D, v, u, p, NULL);
+        zc alpha = rho / orc_dot(r0, v, n);
+        copyv(s, r, n); axpy(s, -alpha, v, n);
+        orc_apply(op, kind, ORC_D, t, u, s, NULL);
+        zc omega = orc_dot(t, s, n) / creal(orc_dot(t, t, n));
+        axpy(x, alpha, p, n); axpy(x, omega, s, n);
+        copyv(r, s, n); axpy(r, -omega, t, n);
+        rnorm = creal(orc_dot(r, r, n));
+        if (hist) hist[i] = rnorm;
+        if (rnorm < eps) { ret = i; goto done; }
+        zc rho_new = orc_dot(r0, r, n);
+        zc beta = (rho_new / rho) * (alpha / omega);
+        rho = rho_new;
+        /* p = r + beta (p - omega v) */
+        axpy(p, -omega, v, n);
+        xpby(p, r, beta, n);
+    }
+done:
+    if (resid_sq) *resid_sq = rnorm;
+    free(r); free(r0); free(p); free(v); free(s); free(t);
+    return ret;
+}
+
+/* ---- multi-shift CG (upstream shiftedcg): (D^dag D + sigma_j) x_j = b.
+ *      Used by RHMC (test/test_Nf2.toml, universe.jl:106-110).  Zero initial guess; zeta recurrences
+ *      (Jegerlehner hep-lat/9612014); convergence tested on the residual of shifts[0].                  */
+int orc_mscg(const orc_op *op, int kind, zc *const xs[], const zc *const u[4], const zc *b,
+             const double *shifts, int nshift, double eps, int maxsteps, double *resid_sq) {
+    const int64_t n = field_len(op, kind);
+    zc *r = malloc(sizeof(zc) * n), *q = malloc(sizeof(zc) * n), *t = malloc(sizeof(zc) * n);
+    zc **ps = malloc(sizeof(zc *) * nshift);
+    double *zeta = malloc(sizeof(double) * nshift), *zeta_old = malloc(sizeof(double) * nshift),
+           *beta_s = malloc(sizeof(double) * nshift);
+    for (int j = 0; j < nshift; j++) {
+        ps[j] = malloc(sizeof(zc) * n);
+        copyv(ps[j], b, n);
+        memset(xs[j], 0, sizeof(zc) * n);
+        zeta[j] = zeta_old[j] = 1.0;
+    }
+    copyv(r, b, n);
+    int ret = -1;
+    double rr = creal(orc_dot(r, r, n));
+    double alpha_old = 1.0, beta_old = 0.0;   /* CG scalars of the base system in "x += alpha p" form */
+    if (rr < eps) { ret = 0; goto done; }
+    const double s0 = shifts[0];
+    for (int i = 1; i <= maxsteps; i++) {
+        /* base system A0 = D^dag D + s0 */
+        orc_apply(op, kind, ORC_DDAGD, q, u, ps[0], t);
+        axpy(q, s0, ps[0], n);
+        double pq = creal(orc_dot(ps[0], q, n));
+        double alpha = rr / pq;
+        /* shifted coefficients (relative shift ds = sigma_j - s0) */
+        for (int j = 1; j < nshift; j++) {
+            double ds = shifts[j] - s0;
+            double znew = zeta[j] * zeta_old[j] * alpha_old /
+                          (alpha * beta_old * (zeta_old[j] - zeta[j]) + zeta_old[j] * alpha_old * (1.0 + ds * alpha));
+            double alpha_j = alpha * znew / zeta[j];
+            axpy(xs[j], alpha_j, ps[j], n);
+            zeta_old[j] = zeta[j]; zeta[j] = znew;
+            beta_s[j] = alpha_j;   /* stash alpha_j for the beta_j update */
+        }
+        axpy(xs[0], alpha, ps[0], n);
+        axpy(r, -alpha, q, n);
+        double rr_new = creal(orc_dot(r, r, n));
+        if (rr_new < eps) { rr = rr_new; ret = i; goto done; }
+        double beta = rr_new / rr;
+        xpby(ps[0], r, beta, n);
+        for (int j = 1; j < nshift; j++) {
+            /* beta_j = beta * (zeta_new/zeta_old_iter)^2 ; p_j = zeta_new r + beta_j p_j */
+            double ratio = zeta[j] / zeta_old[j];
+            double beta_j = beta * ratio * ratio;
+            zc *pj = ps[j];
+            const double zj = zeta[j];
+#pragma omp parallel for schedule(static)
+            for (int64_t k = 0; k < n; k++) pj[k] = beta_j * pj[k] + zj * r[k];
+        }
+        alpha_old = alpha; beta_old = beta; rr = rr_new;
+    }
+done:
+    if (resid_sq) *resid_sq = rr;
+    for (int j = 0; j < nshift; j++) free(ps[j]);
+    free(ps); free(zeta); free(zeta_old); free(beta_s); free(r); free(q); free(t);
+    return ret;
+}
+
+/* ---- plaquette (pins the fixture loader + link layout; SURVEY.md section 4 values) ---- */
+static void mm(zc *c, const zc *a, const zc *b) {          /* c = a b, [row + 3 col] */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        zc s = 0; for (int k = 0; k < 3; k++) s += a[i + 3 * k] * b[k + 3 * j];
+        c[i + 3 * j] = s;
+    }
+}
+static void mmd(zc *c, const zc *a, const zc *b) {         /* c = a b^dag */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        zc s = 0; for (int k = 0; k < 3; k++) s += a[i + 3 * k] * conj(b[j + 3 * k]);
+        c[i + 3 * j] = s;
+    }
+}
+double orc_plaquette(const int dims[4], const zc *const u[4]) {
+    geom g = mkgeom(dims);
+    double sum = 0;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+    for (int64_t s = 0; s < g.V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        for (int mu = 0; mu < 4; mu++)
+            for (int nu = mu + 1; nu < 4; nu++) {
+                int w;
+                int64_t smu = nbr(&g, s, c, mu, +1, &w), snu = nbr(&g, s, c, nu, +1, &w);
+                zc a[9], b[9], d[9];
+                mm(a, u[mu] + 9 * s, u[nu] + 9 * smu);      /* U_mu(n) U_nu(n+mu) */
+                mmd(b, a, u[mu] + 9 * snu);                  /* ... U_mu(n+nu)^dag */
+                mmd(d, b, u[nu] + 9 * s);                    /* ... U_nu(n)^dag    */
+                sum += creal(d[0] + d[4] + d[8]);
+            }
+    }
+    return sum / (6.0 * 3.0 * (double)g.V);
+}
+
+/* ---- Wilson pseudofermion force, calc_UdSfdU! (AbstractMD.jl:129) ----
+ *  UdSfdU_mu(n)[a][b] = -kappa * sum_spin [ ((r-gamma_mu) U_mu(n) X(n+mu))_a  conj(Y(n)_b) ]
+ *                       +kappa * sum_spin [ X(n)_a  conj( ((r+gamma_mu) U_mu(n) Y(n+mu)) )_b ... ]
+ *  written so that dS_f/d eps = -2 Re tr[A * UdSfdU_mu(n)] for U_mu(n) -> exp(eps A) U_mu(n)
+ *  (S_f = phi^dag (D^dag D)^-1 phi).  Derivation in DESIGN.md; verified by finite differences in tests. */
+void orc_wilson_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y) {
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V;
+    const double kappa = op->kappa;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        for (int mu = 0; mu < 4; mu++) {
+            int wf; int64_t sf = nbr(&g, s, c, mu, +1, &wf);
+            double pf = wf ? op->bc[mu] : 1.0;
+            const zc *U = u[mu] + 9 * s;
+            /* hX = U X(n+mu), hY = U Y(n+mu) (phase included), per spin */
+            zc hX[4][3], hY[4][3];
+            for (int al = 0; al < 4; al++)
+                for (int a = 0; a < 3; a++) {
+                    zc sx = 0, sy = 0;
+                    for (int b = 0; b < 3; b++) {
+                        sx += U[a + 3 * b] * (pf * X[b + 3 * (sf + V * al)]);
+                        sy += U[a + 3 * b] * (pf * Y[b + 3 * (sf + V * al)]);
+                    }
+                    hX[al][a] = sx; hY[al][a] = sy;
+                }
+            /* delta D = -kappa [ (r-g) dU X(n+mu) at n  +  (r+g) dU^dag X(n) at n+mu ]
+             * dS = -2 Re( Y^dag dD X ).  With dU = A U :
+             *   term1: Y(n)^dag (r-g) A U X(n+mu)         -> tr A * [ (r-g) hX ] Y(n)^dag
+             *   term2: Y(n+mu)^dag (r+g) U^dag A^dag X(n) = -[ (U (r+g) Y(n+mu))^dag A X(n) ] -> tr A * X(n) [(r+g) hY]^dag (sign -)
+             * => dS = -2 Re tr A * { -kappa (r-g)hX Y(n)^dag + kappa X(n) ((r+g) hY)^dag }                */
+            zc pX[4][3], pY[4][3];
+            for (int al = 0; al < 4; al++)
+                for (int a = 0; a < 3; a++) {
+                    zc t1 = 0, t2 = 0;
+                    for (int be = 0; be < 4; be++) {
+                        t1 += op->rminusg[mu][al][be] * hX[be][a];
+                        t2 += op->rplusg[mu][al][be] * hY[be][a];
+                    }
+                    pX[al][a] = t1; pY[al][a] = t2;
+                }
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    zc m = 0;
+                    for (int al = 0; al < 4; al++) {
+                        m += -kappa * pX[al][a] * conj(Y[b + 3 * (s + V * al)]);
+                        m +=  kappa * X[a + 3 * (s + V * al)] * conj(pY[al][b]);
+                    }
+                    out[mu][a + 3 * (b + 3 * s)] = m;
+                }
+        }
+    }
+}
+
+/* staggered analogue: delta D = (1/2) eta [ dU X(n+mu) at n - dU^dag X(n) at n+mu ] */
+void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y) {
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        int esum = 0;
+        for (int mu = 0; mu < 4; mu++) {
+            double eta = (esum & 1) ? -1.0 : 1.0;
+            esum += c[mu];
+            int wf; int64_t sf = nbr(&g, s, c, mu, +1, &wf);
+            double pf = wf ? op->bc[mu] : 1.0;
+            const zc *U = u[mu] + 9 * s;
+            zc hX[3], hY[3];
+            for (int a = 0; a < 3; a++) {
+                zc sx = 0, sy = 0;
+                for (int b = 0; b < 3; b++) {
+                    sx += U[a + 3 * b] * (pf * X[b + 3 * sf]);
+                    sy += U[a + 3 * b] * (pf * Y[b + 3 * sf]);
+                }
+                hX[a] = sx; hY[a] = sy;
+            }
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++)
+                    out[mu][a + 3 * (b + 3 * s)] =
+                        0.5 * eta * (hX[a] * conj(Y[b + 3 * s]) + X[a + 3 * s] * conj(hY[b]));
+        }
+    }
+}

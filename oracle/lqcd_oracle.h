@@ -1,0 +1,86 @@
+/*
+ * lqcd_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Plain-C fp64 restatement of the Dirac-operator solve path that LatticeQCD.jl drives through
+ * LatticeDiracOperators.jl (compat "0.6.1", /root/reference/Project.toml:11,27) on link fields owned by
+ * Gaugefields.jl (compat "0.4-0.7", Project.toml:8,24).  Neither package's source is under /root/reference
+ * and no Julia runtime exists in the build container, so every algorithm below is restated from the
+ * reference's call sites and the published (recalled) upstream algorithms, see SURVEY.md App. C.
+ *
+ *      *** PARITY UNPINNED ***  
+ * The reference's tests only pin a plaquette to 10 % (test/runtests.jl:15,97).  This oracle is pinned
+ * instead by basis-independent known-answer tests (tests/test_oracle_*.py): fixture plaquettes, free-field
+ * plane waves, gamma5-hermiticity, gauge covariance, dense-matrix numpy cross-check, CG true residuals.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * Host ("Julia") layouts used at this boundary, column-major, x fastest:
+ *   links    U[mu] : ComplexF64[NC,NC,NX,NY,NZ,NT]   -> u[mu][ a + 3*(b + 3*site) ]      (row a, col b)
+ *   Wilson   psi   : ComplexF64[NC,NX,NY,NZ,NT,4]    -> f[ c + 3*(site + V*alpha) ]
+ *   stagger. chi   : ComplexF64[NC,NX,NY,NZ,NT,1]    -> f[ c + 3*site ]
+ *   site = x + NX*(y + NY*(z + NZ*t)), 0-based.
+ */
+#ifndef LQCD_ORACLE_H
+#define LQCD_ORACLE_H
+#include <complex.h>
+#include <stdint.h>
+
+typedef double _Complex zc;
+
+typedef struct {
+    int dims[4];            /* NX NY NZ NT */
+    double bc[4];           /* fermion boundary phase per direction, reference default [1,1,1,-1]
+                               (src/system/parameter_structs.jl:133, forwarded at universe.jl:135) */
+    /* Wilson */
+    double kappa;           /* "hop", universe.jl:114 */
+    double r;               /* universe.jl:115 */
+    zc rplusg[4][4][4];     /* r*1 + gamma_mu  (upstream WilsonFermion "rplusγ"), [mu][row][col] */
+    zc rminusg[4][4][4];    /* r*1 - gamma_mu  ("rminusγ") */
+    /* staggered */
+    double mass;            /* universe.jl:109 */
+    /* Wilson clover (new capability, unpinned): csw = 0 disables */
+    double csw;
+} orc_op;
+
+enum { ORC_WILSON = 0, ORC_STAGGERED = 1 };
+enum { ORC_D = 0, ORC_DDAG = 1, ORC_DDAGD = 2 };
+
+/* fill gamma tables (LTK / upstream basis) for a given r */
+void orc_set_gamma(orc_op *op, double r);
+
+int  orc_set_threads(int n);   /* OpenMP threads; returns the count in effect */
+
+/* y = D x (mode ORC_D), D^dag x, or D^dag D x.  kind selects Wilson / staggered. */
+void orc_apply(const orc_op *op, int kind, int mode, zc *y, const zc *const u[4], const zc *x, zc *scratch);
+
+/* inner product <a,b> = sum conj(a) b over n complex numbers */
+zc   orc_dot(const zc *a, const zc *b, int64_t n);
+
+/* Solvers.  x is initial guess and result.  eps is compared with the ABSOLUTE
+ * SQUARED residual norm.  Return: iterations (>=0) on convergence, -1 if maxsteps exceeded.
+ * resid_sq receives the last recursive |r|^2; hist (nullable, length maxsteps+1) the per-step |r|^2. */
+int orc_cg   (const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+              double eps, int maxsteps, double *resid_sq, double *hist);          /* A = D^dag D */
+int orc_cgnr (const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+              double eps, int maxsteps, double *resid_sq, double *hist);          /* A = D, upstream "bicg" */
+int orc_bicgstab(const orc_op *op, int kind, zc *x, const zc *const u[4], const zc *b,
+              double eps, int maxsteps, double *resid_sq, double *hist);          /* A = D */
+/* multi-shift CG on (D^dag D + sigma_j) x_j = b, zero initial guess, stop on base (j=0 after sorting
+ * by the caller: shifts[0] must be the smallest) residual */
+int orc_mscg (const orc_op *op, int kind, zc *const xs[], const zc *const u[4], const zc *b,
+              const double *shifts, int nshift, double eps, int maxsteps, double *resid_sq);
+
+/* average plaquette  (1/(6 V NC)) sum Re tr U_mu(n) U_nu(n+mu) U_mu(n+nu)^dag U_nu(n)^dag */
+double orc_plaquette(const int dims[4], const zc *const u[4]);
+
+/* Wilson pseudofermion force: given X=(D^dag D)^-1 phi and Y = D X,
+ * out[mu][a + 3*(b+3*site)] = U_mu dS_f/dU_mu colour matrix before Traceless_antihermitian. */
+void orc_wilson_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y);
+/* staggered analogue */
+void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y);
+
+/* clover term support (Wilson-clover, new capability): builds the 4 V (6x6 hermitian x2) packed as
+ * full 12x12 block-diagonal-in-chirality matrices: clov[site*72*... ] -- see lqcd_oracle.c */
+void orc_clover_build(const orc_op *op, zc *clov /* V*2*36 */, const zc *const u[4]);
+
+#endif
