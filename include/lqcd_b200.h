@@ -1,0 +1,152 @@
+/*
+ * lqcd_b200.h -- flat C ABI of liblqcd_b200.so: the B200-native (sm_100a) Dirac-operator solve path that
+ * LatticeQCD.jl reaches through LatticeDiracOperators.jl / Gaugefields.jl.
+ *
+ * Nothing like this boundary exists in the reference (it is pure Julia dispatch); each
+ * entry point below names the Julia generic function + reference call site (paths relative to
+ * /root/reference) whose arithmetic it replaces.  The Julia-side ccall shim is in
+ * latticeqcd.jl_b200/julia/LQCDB200.jl and INTEGRATION.md; a ctypes mirror used by the tests and bench.py
+ * is in latticeqcd.jl_b200/lqcd_b200/.
+ *
+ * Conventions
+ *   - every function returns an int status (LQCD_OK == 0); never throws, never exits.  On error the
+ *     message is retrievable with lqcd_last_error(ctx) (ctx may be NULL for creation failures).
+ *     The Julia shim turns non-zero into error(...), matching the reference's convention
+ *     (src/system/universe.jl:73-75,130).  Non-convergence after MaxCGstep is an error (LQCD_ERR_NOCONV).
+ *   - host arrays are the caller's (Julia GC-owned); they are only read/written during the call.
+ *     Device memory belongs to the library behind opaque handles.
+ *   - host layouts are the Julia column-major arrays, ComplexF64 = 2 doubles:
+ *       links    U[mu]  : [NC, NC, NX+2w, NY+2w, NZ+2w, NT+2w]      (w = ndw, wing width)
+ *       Wilson   psi    : [NC, NX+2w, NY+2w, NZ+2w, NT+2w, 4]
+ *       stagg.   chi    : [NC, NX+2w, NY+2w, NZ+2w, NT+2w, 1]
+ *     with LOCAL extents when the context is one rank of a process grid.
+ *   - all exported calls are blocking-on-return unless named *_async.
+ *   - one context per process and GPU; multi-GPU = one process per GPU (lqcd_comm_*).
+ */
+#ifndef LQCD_B200_H
+#define LQCD_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQCD_ABI_VERSION 1
+
+enum {
+    LQCD_OK = 0,
+    LQCD_ERR_ARG = 1,        /* bad argument / unsupported parameter */
+    LQCD_ERR_CUDA = 2,       /* CUDA runtime error */
+    LQCD_ERR_COMM = 3,       /* inter-GPU communication error / timeout */
+    LQCD_ERR_NOCONV = 4,     /* solver hit maxsteps (upstream: error("The CG is not converged!")) */
+    LQCD_ERR_NOGPU = 5,      /* no usable CUDA device: there is NO CPU fallback */
+    LQCD_ERR_STATE = 6       /* call out of order (e.g. dslash before gauge upload) */
+};
+
+enum { LQCD_WILSON = 0, LQCD_STAGGERED = 1 };                 /* params["Dirac_operator"], universe.jl:106-113 */
+enum { LQCD_OP_D = 0, LQCD_OP_DDAG = 1, LQCD_OP_DDAGD = 2 };  /* D, D', DdagD (measure_Pion_correlator.jl:379) */
+enum {
+    LQCD_SOLVER_CG = 0,        /* Hermitian A (DdagD): upstream cg           */
+    LQCD_SOLVER_CGNR = 1,      /* A = D: upstream "bicg" (really CGNR)      (App. C.4)            */
+    LQCD_SOLVER_BICGSTAB = 2   /* A = D: params["method_CG"] = "bicgstab"                          */
+};
+
+typedef struct lqcd_ctx lqcd_ctx;
+typedef struct lqcd_fermion lqcd_fermion;
+
+/* Operator descriptor = the params Dict of Dirac_operator(U, x, params), universe.jl:103-137 */
+typedef struct {
+    int kind;          /* LQCD_WILSON | LQCD_STAGGERED                          params["Dirac_operator"] */
+    double kappa;      /* Wilson hopping parameter                              params["κ"]  (universe.jl:114) */
+    double r;          /* Wilson parameter; only r == 1 has a kernel            params["r"]  (universe.jl:115) */
+    double mass;       /* staggered mass                                        params["mass"] (universe.jl:109) */
+    double csw;        /* clover coefficient (0 = none; Clover is not reachable from run_LQCD) */
+    double bc[4];      /* fermion boundary phases, +-1                          params["boundarycondition"] (universe.jl:135) */
+} lqcd_op;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* global_dims = (NX,NY,NZ,NT); procgrid = ranks per direction (product = nranks; mirrors the reference's
+ * PEs[4], src/mpi/mpimodule.jl:9-13); device = CUDA ordinal for this rank.  Replaces the geometry part of
+ * Initialize_Gaugefields (universe.jl:41-49). */
+int lqcd_ctx_create(const int global_dims[4], const int procgrid[4], int rank, int device, lqcd_ctx **out);
+int lqcd_ctx_destroy(lqcd_ctx *ctx);
+const char *lqcd_last_error(const lqcd_ctx *ctx);
+int lqcd_abi_version(void);
+int lqcd_local_dims(const lqcd_ctx *ctx, int local_dims[4], int origin[4]);
+int lqcd_synchronize(lqcd_ctx *ctx);
+/* pin / unpin a caller-owned host buffer so uploads run at PCIe speed (optional) */
+int lqcd_host_register(lqcd_ctx *ctx, void *ptr, size_t bytes);
+int lqcd_host_unregister(lqcd_ctx *ctx, void *ptr);
+
+/* ---- link field (Gaugefields.jl container -> device mirror) ------------------------------------ */
+/* Upload the 4 link arrays; the natural call point is Dirac_operator(U,x,params) (universe.jl:137) and the
+ * rebinding D(U) (measure_Pion_correlator.jl:338) because U mutates every MD step (AbstractMD.jl:89-93). */
+int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int nc, int ndw);
+int lqcd_gauge_download(lqcd_ctx *ctx, double *const U_mu[4], int nc, int ndw);
+/* synthetic inputs generated on the device: warm_eps < 0 -> hot (Haar) links,
+ * warm_eps >= 0 -> exp(i eps H).  counter-based: identical fields for any process grid. */
+int lqcd_gauge_random(lqcd_ctx *ctx, uint64_t seed, double warm_eps);
+/* average plaquette of the device links (QCDMeasurements Plaquette; used to pin the loader/layout) */
+int lqcd_gauge_plaquette(lqcd_ctx *ctx, double *plaq);
+
+/* ---- pseudofermion fields: Initialize_pseudofermion_fields (universe.jl:107,112) ---------------- */
+int lqcd_fermion_alloc(lqcd_ctx *ctx, int kind, lqcd_fermion **out);
+int lqcd_fermion_free(lqcd_ctx *ctx, lqcd_fermion *f);
+int lqcd_fermion_upload(lqcd_ctx *ctx, lqcd_fermion *f, const double *host, int ndw);
+int lqcd_fermion_download(lqcd_ctx *ctx, const lqcd_fermion *f, double *host, int ndw);
+int lqcd_fermion_zero(lqcd_ctx *ctx, lqcd_fermion *f);                               /* clear_fermion! */
+int lqcd_fermion_copy(lqcd_ctx *ctx, lqcd_fermion *dst, const lqcd_fermion *src);    /* substitute_fermion! */
+int lqcd_fermion_gaussian(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t seed);            /* gauss_distribution_fermion!, sigma^2=1/2 */
+int lqcd_fermion_point_source(lqcd_ctx *ctx, lqcd_fermion *f, const int site[4], int color, int spin);
+                                                                                     /* setindex_global! (measure_Pion_correlator.jl:376) */
+
+/* ---- BLAS-1 on fermion fields ------------------------------------------- */
+int lqcd_blas_axpy(lqcd_ctx *ctx, double a_re, double a_im, const lqcd_fermion *x, lqcd_fermion *y);   /* add!(y, a, x)      */
+int lqcd_blas_xpby(lqcd_ctx *ctx, const lqcd_fermion *x, double b_re, double b_im, lqcd_fermion *y);   /* add!(b, y, 1, x)   */
+int lqcd_blas_scale(lqcd_ctx *ctx, double a_re, double a_im, lqcd_fermion *x);
+int lqcd_blas_dot(lqcd_ctx *ctx, const lqcd_fermion *a, const lqcd_fermion *b, double out[2]);         /* dot(a,b)=sum conj(a) b (standardHMC.jl:54) */
+int lqcd_blas_norm2(lqcd_ctx *ctx, const lqcd_fermion *a, double *out);
+
+/* ---- operator application: LinearAlgebra.mul!(y, D, x), mul!(y, D', x), mul!(y, DdagD, x) -------- */
+int lqcd_dslash(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode);
+
+/* ---- solvers: solve_DinvX!(y, A, x) (measure_Pion_correlator.jl:399, measure_chiral_condensate.jl:182;
+ *      inside calc_UdSfdU! AbstractMD.jl:129 and evaluate_FermiAction standardHMC.jl:69-71) ---------
+ * y is initial guess and result.  eps is compared with the ABSOLUTE SQUARED residual (params["eps_CG"],
+ * universe.jl:132, default 1e-19 parameter_structs.jl:174); maxsteps = params["MaxCGstep"] (universe.jl:134).
+ * method/target: CG needs target LQCD_OP_DDAGD; CGNR and BICGSTAB need LQCD_OP_D or LQCD_OP_DDAG.
+ * hist (nullable, maxsteps+1 doubles) receives |r|^2 per step (verbose_level 3 prints it upstream). */
+int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int method, int target,
+               double eps, int maxsteps, int *iters, double *resid_sq, double *hist);
+/* multi-shift CG: (DdagD + shifts[j]) ys[j] = x, zero initial guess, shifts[0] smallest (RHMC, App. C.5) */
+int lqcd_multishift_cg(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *x,
+                       const double *shifts, int nshift, double eps, int maxsteps, int *iters, double *resid_sq);
+
+/* ---- fermion force: calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129) ---------------
+ * Given eta: X = (DdagD)^-1 eta by CG, Y = D X, then the 4 link-shaped outer-product fields are written
+ * to the host arrays out_mu (same layout as links, ndw = 0).  x_inout (nullable) is X (initial guess / result). */
+int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
+                       double eps, int maxsteps, double *const out_mu[4], int *iters, double *action);
+
+/* ---- multi-GPU plumbing (one process per GPU; handles are exchanged by the host: MPI.jl Allgather in
+ *      Julia, torch.distributed.all_gather in the Python mirror) ---------------------------------- */
+#define LQCD_IPC_HANDLE_BYTES 256
+int lqcd_comm_export(lqcd_ctx *ctx, void *handle_out /* LQCD_IPC_HANDLE_BYTES */);
+int lqcd_comm_connect(lqcd_ctx *ctx, const void *all_handles /* nranks * LQCD_IPC_HANDLE_BYTES, rank order */);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* number of kernels this library launched since context creation (bench.py's gpu_launches) */
+int lqcd_launch_count(const lqcd_ctx *ctx, uint64_t *count);
+/* time `reps` back-to-back applications of one operator with CUDA events on the library's stream;
+ * flush_l2 != 0 writes a >L2 scratch buffer between applications (outside the event brackets).
+ * Returns the mean per-application milliseconds of the dslash kernels only. */
+int lqcd_time_dslash(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
+                     int reps, int flush_l2, double *ms_mean, double *ms_min);
+/* expose the CUDA stream (cudaStream_t as void*) so the host can bracket work with its own events */
+int lqcd_stream(lqcd_ctx *ctx, void **stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQCD_B200_H */

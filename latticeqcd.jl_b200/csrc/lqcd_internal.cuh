@@ -1,0 +1,190 @@
+// lqcd_internal.cuh -- shared definitions of liblqcd_b200 (sm_100a only).
+//
+// Device field layout ("AoSoA-32"): sites are numbered lexicographically, x fastest
+// (site = x + X*(y + Y*(z + Z*t)) over the LOCAL lattice) and grouped in blocks of 32 consecutive sites
+// (one warp).  Inside a block the complex components are stored component-major:
+//
+//     spinor (ncomp = 12 Wilson, k = 3*alpha + c;  ncomp = 3 staggered, k = c)
+//         f[(blk*ncomp + k)*32 + lane]                       double2 = (re, im)
+//     links  (4 directions x 9 matrix elements, e = 3*a + b, row a, column b)
+//         g[((blk*4 + mu)*9 + e)*32 + lane]                  double2
+//
+// so that (i) every warp-wide load of one component is one contiguous, 512-byte, 128-bit-per-lane request,
+// (ii) all data of a 32-site block is one contiguous record (6 KB spinor, 18 KB links) that a single
+// cp.async.bulk can move, and (iii) a block's HBM pages stay together (DRAM page / TLB locality).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/lqcd_b200.h"
+
+#define LQCD_SB 32                 // sites per block (= warp size)
+#define LQCD_MAX_RED 8             // doubles reduced per kernel
+#define LQCD_MAX_SHIFTS 32
+
+typedef double2 cplx;
+
+struct Geom {
+    int X, Y, Z, T;            // local extents
+    int V;                     // local volume
+    int nblk;                  // V / 32
+    // CTA tiling of the block lattice (regular case) -- see make_tiling()
+    int regular;               // 1: blocks form a regular 4-d lattice
+    int s[4];                  // block shape in sites  (product 32)
+    int nb[4];                 // block-lattice extents
+    int c[4];                  // CTA tile in blocks     (product = warps per CTA)
+    int nt[4];                 // tiles per direction
+    int wpc;                   // warps per CTA
+    int part[4];               // 1 if direction is partitioned across ranks (neighbour off-rank)
+    int gX, gY, gZ, gT;        // global extents
+    int o[4];                  // origin of the local lattice in the global one
+};
+
+// Solver scalars living in device memory: kernels read alpha/beta from here so that the Krylov loop runs
+// without host round trips; `done` turns every later kernel of the loop into a no-op.
+struct SolverState {
+    double rr;        // current |r|^2
+    double pq;        // <p, A p> (or |q|^2 for CGNR)
+    double c1;        // CGNR: |A^dag r|^2
+    double alpha, beta;
+    double eps;
+    double are, aim, bre, bim, cre, cim;   // generic complex scalars (BiCGStab)
+    double rho_re, rho_im, omega_re, omega_im, alpha_re, alpha_im;
+    int done;         // 1 once converged
+    int iters;        // iteration at which convergence was detected
+    int it;           // running iteration counter
+    int maxit;
+    int nshift;
+    double shift[LQCD_MAX_SHIFTS];
+    double zeta[LQCD_MAX_SHIFTS], zeta_old[LQCD_MAX_SHIFTS], alpha_s[LQCD_MAX_SHIFTS], beta_s[LQCD_MAX_SHIFTS];
+    double alpha_old, beta_old;
+    double red[LQCD_MAX_RED];   // raw reduction results of the last reducing kernel
+};
+
+// deterministic grid reduction workspace
+struct Reduce {
+    double *partials;          // [grid * LQCD_MAX_RED]
+    unsigned int *ticket;      // last-block-done counter (self-resetting)
+    SolverState *st;           // where results / derived scalars go
+    double *hist;              // optional per-iteration |r|^2 history (device)
+};
+
+enum FinishOp {
+    FIN_STORE = 0,        // st->red[j] = sum_j
+    FIN_CG_PQ,            // red0 = Re<p,q>        -> pq, alpha = rr/pq
+    FIN_CG_RR,            // red0 = |r_new|^2      -> convergence test, beta, rr, it++
+    FIN_CG_INIT,          // red0 = |r0|^2         -> rr, convergence test at step 0
+    FIN_NR_C2,            // red0 = |q|^2          -> alpha = c1/c2
+    FIN_NR_RR,            // red0 = |res|^2        -> convergence test, it++
+    FIN_NR_C3,            // red0 = |s|^2          -> beta = c3/c1, c1 = c3
+    FIN_NR_C1,            // red0 = |q0|^2         -> c1
+    FIN_BI_INIT,          // red0 = |r0|^2         -> rr, rho = (rr,0), convergence test at step 0
+    FIN_BI_ALPHA,         // red0,1 = <r0,v>       -> alpha = rho / <r0,v>
+    FIN_BI_OMEGA,         // red0,1 = <t,s>, red2 = |t|^2 -> omega
+    FIN_BI_RR,            // red0 = |r|^2, red1,2 = <r0,r> -> convergence, beta, rho
+    FIN_MS_PQ,            // multishift: pq -> alpha, zeta recurrences, alpha_j
+    FIN_MS_RR             // multishift: rr_new -> convergence, beta, beta_j
+};
+
+struct MSPtrs { cplx *x[LQCD_MAX_SHIFTS]; cplx *p[LQCD_MAX_SHIFTS]; };
+
+struct lqcd_fermion {
+    int kind;          // LQCD_WILSON / LQCD_STAGGERED
+    int ncomp;         // 12 / 3
+    cplx *d;           // device AoSoA-32 data, nblk*ncomp*32 complex
+    size_t bytes;
+    lqcd_ctx *owner;
+};
+
+struct lqcd_ctx {
+    int device;
+    int rank, nranks;
+    int procgrid[4], pcoord[4];
+    Geom g;
+    cudaStream_t stream, stream2;
+    cudaEvent_t ev0, ev1, ev_pack, ev_int, ev_poll[2];
+    cplx *gauge;               // AoSoA-32 links
+    bool gauge_valid;
+    // staging
+    void *stage; size_t stage_bytes;
+    // reductions
+    Reduce red;
+    SolverState *st_host;      // pinned: [0] init image / blocking reads, [1],[2] async polling slots
+    double *hist_dev; int hist_cap;
+    // scratch fermions for solvers (allocated lazily per kind)
+    std::vector<lqcd_fermion *> scratch[2];
+    // L2 flush buffer
+    void *flush; size_t flush_bytes;
+    uint64_t launches;
+    int num_sms;
+    mutable std::string err;
+    // comm (multi-GPU) -- see comm.cu
+    struct CommState *comm;
+};
+
+int lqcd_fail(const lqcd_ctx *ctx, int code, const char *fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return lqcd_fail(ctx, LQCD_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,           \
+                             cudaGetErrorString(_e));                                                   \
+    } while (0)
+
+#define LQCD_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        int _s = (expr);                                                                                \
+        if (_s != LQCD_OK) return _s;                                                                   \
+    } while (0)
+
+static inline int ncomp_of(int kind) { return kind == LQCD_WILSON ? 12 : 3; }
+
+// ---- complex helpers (device) ------------------------------------------------------------------
+__device__ __forceinline__ cplx cmake(double r, double i) { return make_double2(r, i); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {   // conj(a) * b
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ void cfma(cplx &acc, cplx a, cplx b) {        // acc += a*b
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(cplx &acc, cplx a, cplx b) {       // acc += conj(a)*b
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ cplx cscale(double s, cplx a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ cplx cmuli(cplx a) { return make_double2(-a.y, a.x); }    // i*a
+__device__ __forceinline__ cplx cmulmi(cplx a) { return make_double2(a.y, -a.x); }   // -i*a
+
+__device__ __forceinline__ cplx ldg128(const cplx *p) { return __ldg(p); }
+
+// ---- kernels' host-side entry points (one per .cu) ----------------------------------------------
+struct DslashFuse {
+    // optional fused epilogue: dot_with != nullptr -> reduce  red0/1 = <dot_with, y>, red2 = |y|^2
+    const cplx *dot_with;
+    int want_norm;             // reduce |y|^2 in red2 even without dot_with
+    int finish;                // FinishOp applied to the reduction
+    int use_state;             // kernels early-exit when st->done
+    double shift;              // y += shift * x  (multi-shift base system: (DdagD + s) )
+    const cplx *shift_src;     // field multiplied by `shift` (the input of the first hop of DdagD)
+};
+
+int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
+                         const DslashFuse *fuse, cudaStream_t s);
+int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
+                            const DslashFuse *fuse, cudaStream_t s);
+int apply_op(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
+             lqcd_fermion *tmp, const DslashFuse *fuse_last);
+
+// blas.cu
+int blas_zero(lqcd_ctx *ctx, cplx *x, size_t n);
+int blas_copy(lqcd_ctx *ctx, cplx *dst, const cplx *src, size_t n);
+int get_scratch(lqcd_ctx *ctx, int kind, int idx, lqcd_fermion **out);
+int reduce_grid(const lqcd_ctx *ctx);

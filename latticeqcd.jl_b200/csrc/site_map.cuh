@@ -1,0 +1,29 @@
+// site_map.cuh -- CTA/warp -> 32-site block mapping and site coordinates.
+//
+// A CTA of `wpc` warps owns a small 4-d TILE of the block lattice (c[0..3] blocks per direction) so that
+// the +-y/z/t neighbours of most of its sites are read by the same SM (L1 reuse); tiles are numbered with
+// t slowest so the set of CTAs in flight sweeps the lattice in t and the neighbour slices stay in the
+// 126 MB L2 (each spinor/link record is then fetched from HBM once per application).
+#pragma once
+#include "lqcd_internal.cuh"
+
+__device__ __forceinline__ int block_of_warp(const Geom &g, int cta, int warp) {
+    if (!g.regular) return cta * g.wpc + warp;
+    int t0 = cta % g.nt[0]; cta /= g.nt[0];
+    int t1 = cta % g.nt[1]; cta /= g.nt[1];
+    int t2 = cta % g.nt[2];
+    int t3 = cta / g.nt[2];
+    int w0 = warp % g.c[0]; warp /= g.c[0];
+    int w1 = warp % g.c[1]; warp /= g.c[1];
+    int w2 = warp % g.c[2];
+    int w3 = warp / g.c[2];
+    int b0 = t0 * g.c[0] + w0, b1 = t1 * g.c[1] + w1, b2 = t2 * g.c[2] + w2, b3 = t3 * g.c[3] + w3;
+    return b0 + g.nb[0] * (b1 + g.nb[1] * (b2 + g.nb[2] * b3));
+}
+
+__device__ __forceinline__ void site_coords(const Geom &g, int s, int &x, int &y, int &z, int &t) {
+    x = s % g.X; s /= g.X;
+    y = s % g.Y; s /= g.Y;
+    z = s % g.Z;
+    t = s / g.Z;
+}

@@ -1,0 +1,115 @@
+// staggered_dslash.cu -- staggered (Kogut-Susskind) Dslash, fp64, sm_100a.
+//
+// Replaces LinearAlgebra.mul!(y, D::Staggered_Dirac_operator, x) / mul!(y, D', x) of
+// LatticeDiracOperators.jl (upstream Dx! + mass), reached from
+// src/system/universe.jl:106-110 ("Staggered") through the same call sites as the Wilson operator:
+//
+//     y(n) = m x(n) +- sum_mu (1/2) eta_mu(n) [ U_mu(n) x(n+mu) - U_mu^dag(n-mu) x(n-mu) ]       (+: D, -: D^dag)
+//     eta_1 = 1, eta_2 = (-1)^x, eta_3 = (-1)^(x+y), eta_4 = (-1)^(x+y+z)   (GLOBAL coordinates)
+//
+// Same mapping as the Wilson kernel: one thread per site, one warp per AoSoA-32 block, 128-bit coalesced
+// loads.  672 B/site compulsory (576 B of links), 582 flop/site: purely HBM-bound.
+#include "lqcd_internal.cuh"
+#include "reduce.cuh"
+#include "site_map.cuh"
+
+struct StagArgs {
+    cplx *out;
+    const cplx *in;
+    const cplx *gauge;
+    Geom g;
+    double mass;
+    double sign;      // +1 D, -1 D^dag
+    double bc[4];
+    DslashFuse fuse;
+    Reduce red;
+};
+
+template <int MU, int FWD>
+__device__ __forceinline__ void shop(cplx (&acc)[3], const cplx *__restrict__ in, const cplx *__restrict__ gauge,
+                                     int ns, int ls, double coef) {
+    const cplx *sp = in + (size_t)(ns >> 5) * (3 * 32) + (ns & 31);
+    cplx v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = cscale(coef, ldg128(sp + c * 32));
+    const cplx *lk = gauge + ((size_t)(ls >> 5) * 4 + MU) * (9 * 32) + (ls & 31);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            if (FWD) cfma(acc[a], ldg128(lk + (a * 3 + b) * 32), v[b]);
+            else     cfmac(acc[a], ldg128(lk + (b * 3 + a) * 32), v[b]);
+        }
+    }
+}
+
+template <int MU>
+__device__ __forceinline__ void shop_pair(cplx (&acc)[3], const StagArgs &A, int s, int coord, int dim, int stride, double eta) {
+    {
+        bool w = (coord == dim - 1);
+        int ns = w ? s - (dim - 1) * stride : s + stride;
+        double coef = 0.5 * eta * (w ? A.bc[MU] : 1.0);
+        if (!(w && A.g.part[MU])) shop<MU, 1>(acc, A.in, A.gauge, ns, s, coef);
+    }
+    {
+        bool w = (coord == 0);
+        int ns = w ? s + (dim - 1) * stride : s - stride;
+        double coef = -0.5 * eta * (w ? A.bc[MU] : 1.0);
+        if (!(w && A.g.part[MU])) shop<MU, 0>(acc, A.in, A.gauge, ns, ns, coef);
+    }
+}
+
+__global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A) {
+    if (A.fuse.use_state && A.red.st->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = block_of_warp(A.g, blockIdx.x, warp);
+    const bool active = blk < A.g.nblk;
+    double red[3] = {0.0, 0.0, 0.0};
+    if (active) {
+        const int s = blk * 32 + lane;
+        int x, y, z, t;
+        site_coords(A.g, s, x, y, z, t);
+        const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
+        cplx acc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc[k] = cmake(0.0, 0.0);
+        shop_pair<0>(acc, A, s, x, A.g.X, 1, 1.0);
+        shop_pair<1>(acc, A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0);
+        shop_pair<2>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0);
+        shop_pair<3>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0);
+        const size_t base = (size_t)blk * (3 * 32) + lane;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            cplx xi = ldg128(A.in + base + k * 32);
+            cplx yk = cmake(fma(A.sign, acc[k].x, A.mass * xi.x), fma(A.sign, acc[k].y, A.mass * xi.y));
+            if (A.fuse.shift_src) {
+                cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
+                yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
+            }
+            if (A.fuse.dot_with) {
+                cplx w = ldg128(A.fuse.dot_with + base + k * 32);
+                red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
+                red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
+            }
+            red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
+            A.out[base + k * 32] = yk;
+        }
+    }
+    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
+}
+
+int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
+                            const DslashFuse *fuse, cudaStream_t s) {
+    if (x == y) return lqcd_fail(ctx, LQCD_ERR_ARG, "dslash: in-place application is not allowed");
+    StagArgs A;
+    A.out = y; A.in = x; A.gauge = ctx->gauge; A.g = ctx->g; A.mass = op->mass; A.sign = dagger ? -1.0 : 1.0;
+    for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
+    if (fuse) A.fuse = *fuse; else A.fuse = DslashFuse();
+    A.red = ctx->red;
+    const int bs = 32 * ctx->g.wpc;
+    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
+    staggered_dslash_kernel<<<grid, bs, 0, s>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return LQCD_OK;
+}

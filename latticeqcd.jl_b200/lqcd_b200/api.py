@@ -1,0 +1,364 @@
+"""
+Host-side mirror of the reference's operator interface for the Dirac-solve path, above the C ABI.
+
+The reference reaches this path through Julia generic functions defined by LatticeDiracOperators.jl /
+Gaugefields.jl.  No Julia runtime exists in the build image, so this module is the Python
+twin of latticeqcd.jl_b200/julia/LQCDB200.jl: same function names (Julia's ``f!`` is spelled ``f_``), same
+argument order and meaning, same error behaviour, so the parity tests read like the reference's call sites:
+
+    U  = Initialize_Gaugefields(3, 0, NX, NY, NZ, NT, condition="cold")          # universe.jl:41-49
+    x  = Initialize_pseudofermion_fields(U[0], "Wilson", nowing=True)            # universe.jl:112
+    D  = Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": 0.141139, ...})  # universe.jl:113-137
+    mul_(y, D, x); mul_(y, adjoint(D), x); mul_(y, DdagD(D), x)                  # measure_Pion_correlator.jl:379
+    solve_DinvX_(y, D, b)                                                        # measure_Pion_correlator.jl:399
+    fa = FermiAction(D, {"Nf": 2}); calc_UdSfdU_(UdSfdU, fa, U, eta)              # universe.jl:138, AbstractMD.jl:129
+
+Link fields stay host numpy arrays in the Julia memory layout (the gauge sector keeps using them on the
+CPU, SURVEY.md 8b "Selection" option 1); they are mirrored to the device when an operator is built or
+re-bound with ``D(U)``.  Pseudofermion fields are device-resident handles with explicit
+``to_host()`` / ``from_host()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+_CTX = {}     # (dims, procgrid, rank, device) -> Context
+
+
+class Context:
+    """One per process and GPU (lqcd_ctx_create)."""
+
+    def __init__(self, dims, procgrid=(1, 1, 1, 1), rank=0, device=0):
+        self.lib = L.load()
+        self.dims = tuple(int(d) for d in dims)
+        self.procgrid = tuple(int(p) for p in procgrid)
+        self.rank, self.device = int(rank), int(device)
+        h = C.c_void_p()
+        d = (C.c_int * 4)(*self.dims)
+        p = (C.c_int * 4)(*self.procgrid)
+        L.check(None, self.lib.lqcd_ctx_create(d, p, self.rank, self.device, C.byref(h)))
+        self.h = h
+        ld, og = (C.c_int * 4)(), (C.c_int * 4)()
+        self.call("lqcd_local_dims", ld, og)
+        self.local_dims, self.origin = tuple(ld), tuple(og)
+        self.gauge_epoch = None
+        self._fin = weakref.finalize(self, self.lib.lqcd_ctx_destroy, h)
+
+    def call(self, name, *args):
+        L.check(self.h, getattr(self.lib, name)(self.h, *args))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self.call("lqcd_launch_count", C.byref(n))
+        return n.value
+
+    def synchronize(self):
+        self.call("lqcd_synchronize")
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self.call("lqcd_stream", C.byref(s))
+        return s.value
+
+
+def get_context(dims, procgrid=(1, 1, 1, 1), rank=0, device=0) -> Context:
+    key = (tuple(dims), tuple(procgrid), rank, device)
+    if key not in _CTX:
+        _CTX[key] = Context(dims, procgrid, rank, device)
+    return _CTX[key]
+
+
+# ---------------------------------------------------------------------------------------------------
+# link fields (Gaugefields.jl container; host-resident, Julia layout)
+# ---------------------------------------------------------------------------------------------------
+class GaugeField:
+    """U[mu]: AbstractGaugefields{NC,4}.  ``.U`` is ComplexF64[NC,NC,NX,NY,NZ,NT] in Julia order, i.e. the
+    C-order numpy array [NT,NZ,NY,NX,b,a].  Fields used by the reference: .NC .NV .NX .NY .NZ .NT, size()."""
+
+    def __init__(self, arr, NC, dims, parent):
+        self.U, self.NC = arr, NC
+        self.NX, self.NY, self.NZ, self.NT = dims
+        self.NV = int(np.prod(dims))
+        self.parent = parent
+
+    def size(self):
+        return (self.NC, self.NC, self.NX, self.NY, self.NZ, self.NT)
+
+
+class Gaugefields(list):
+    """Vector{<:AbstractGaugefields} of length 4 sharing one [4,NT,NZ,NY,NX,3,3] array."""
+
+    def __init__(self, data, dims, ctx_args=None):
+        self.data = np.ascontiguousarray(data, dtype=np.complex128)
+        self.dims = tuple(dims)
+        self.ctx_args = ctx_args or {}
+        super().__init__(GaugeField(self.data[mu], 3, self.dims, self) for mu in range(4))
+
+    def context(self) -> Context:
+        return get_context(self.dims, **self.ctx_args)
+
+
+def Initialize_Gaugefields(NC, Nwing, NX, NY, NZ, NT, condition="cold", seed=111, **ctx_args) -> Gaugefields:
+    """src/system/universe.jl:41-49.  cold = identity, hot = random SU(3) (numpy Haar, seeded)."""
+    if NC != 3:
+        raise ValueError("the B200 path implements NC = 3")
+    dims = (NX, NY, NZ, NT)
+    data = np.zeros((4, NT, NZ, NY, NX, 3, 3), dtype=np.complex128)
+    if condition == "cold":
+        for a in range(3):
+            data[..., a, a] = 1.0
+    elif condition == "hot":
+        rng = np.random.default_rng(seed)
+        a = rng.standard_normal(data.shape) + 1j * rng.standard_normal(data.shape)
+        q, r = np.linalg.qr(a)
+        dg = np.diagonal(r, axis1=-2, axis2=-1)
+        q = q * (dg / np.abs(dg))[..., None, :]
+        q = q / (np.linalg.det(q) ** (1.0 / 3.0))[..., None, None]
+        data[:] = np.swapaxes(q, -1, -2)
+    else:
+        raise ValueError(f"condition {condition!r} not supported")
+    return Gaugefields(data, dims, ctx_args)
+
+
+def gaugefields_from_array(arr, **ctx_args) -> Gaugefields:
+    """Wrap links given as [4,NT,NZ,NY,NX,3(b),3(a)] (what load_BridgeText!/ILDG produce, universe.jl:62-68)."""
+    _, NT, NZ, NY, NX, _, _ = arr.shape
+    return Gaugefields(arr, (NX, NY, NZ, NT), ctx_args)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pseudofermion fields (device resident)
+# ---------------------------------------------------------------------------------------------------
+class FermionField:
+    def __init__(self, ctx: Context, kind: int):
+        self.ctx, self.kind = ctx, kind
+        h = C.c_void_p()
+        ctx.call("lqcd_fermion_alloc", kind, C.byref(h))
+        self.h = h
+        self._fin = weakref.finalize(self, ctx.lib.lqcd_fermion_free, ctx.h, h)
+
+    @property
+    def host_shape(self):
+        NX, NY, NZ, NT = self.ctx.local_dims
+        return (4, NT, NZ, NY, NX, 3) if self.kind == L.WILSON else (NT, NZ, NY, NX, 3)
+
+    def from_host(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        assert a.shape == self.host_shape, (a.shape, self.host_shape)
+        self.ctx.call("lqcd_fermion_upload", self.h, a.ctypes.data, 0)
+        return self
+
+    def to_host(self):
+        out = np.empty(self.host_shape, dtype=np.complex128)
+        self.ctx.call("lqcd_fermion_download", self.h, out.ctypes.data, 0)
+        return out
+
+    # Julia-style indexing psi[ic, ix, iy, iz, it, ialpha] (1-based), measure_Pion_correlator.jl:244
+    def __getitem__(self, idx):
+        ic, ix, iy, iz, it, ia = idx
+        h = self.to_host()
+        return h[ia - 1, it - 1, iz - 1, iy - 1, ix - 1, ic - 1] if self.kind == L.WILSON else h[it - 1, iz - 1, iy - 1, ix - 1, ic - 1]
+
+
+def Initialize_pseudofermion_fields(U1: GaugeField, kind: str, nowing=True, L5=None) -> FermionField:
+    """src/system/universe.jl:107,112."""
+    k = {"Wilson": L.WILSON, "staggered": L.STAGGERED, "Staggered": L.STAGGERED}.get(kind)
+    if k is None:
+        raise ValueError(f"fermion kind {kind!r} is not on the B200 path (Wilson, staggered)")
+    return FermionField(U1.parent.context(), k)
+
+
+def similar(x: FermionField) -> FermionField:                       # standardMD.jl:50-51
+    return FermionField(x.ctx, x.kind)
+
+
+def clear_fermion_(x: FermionField):                                # measure_Pion_correlator.jl:370
+    x.ctx.call("lqcd_fermion_zero", x.h)
+
+
+def substitute_fermion_(dst: FermionField, src: FermionField):
+    dst.ctx.call("lqcd_fermion_copy", dst.h, src.h)
+
+
+def setindex_global_(b: FermionField, v, ic, ix, iy, iz, it, ialpha):   # measure_Pion_correlator.jl:376
+    if v != 1:
+        raise ValueError("only unit point sources are supported")
+    site = (C.c_int * 4)(ix - 1, iy - 1, iz - 1, it - 1)
+    b.ctx.call("lqcd_fermion_point_source", b.h, site, ic - 1, ialpha - 1)
+
+
+def gauss_distribution_fermion_(x: FermionField, seed=112):
+    x.ctx.call("lqcd_fermion_gaussian", x.h, int(seed))
+
+
+def dot(a: FermionField, b: FermionField) -> complex:               # standardHMC.jl:54
+    out = (C.c_double * 2)()
+    a.ctx.call("lqcd_blas_dot", a.h, b.h, out)
+    return complex(out[0], out[1])
+
+
+def add_(y: FermionField, a, x: FermionField):                      # add!(y, a, x): y += a x
+    a = complex(a)
+    y.ctx.call("lqcd_blas_axpy", a.real, a.imag, x.h, y.h)
+
+
+def add_xpby_(b, y: FermionField, x: FermionField):                 # add!(b, y, 1, x): y = b y + x
+    b = complex(b)
+    y.ctx.call("lqcd_blas_xpby", x.h, b.real, b.imag, y.h)
+
+
+# ---------------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------------
+class DiracOperator:
+    """Dirac_operator(U, x, params) (universe.jl:137).  Callable: D(U) re-binds (and re-uploads) the links
+    (measure_Pion_correlator.jl:338)."""
+
+    mode = L.OP_D
+
+    def __init__(self, U: Gaugefields, x: FermionField, params: dict):
+        self.params = dict(params)
+        name = params["Dirac_operator"]
+        self.op = L.LqcdOp()
+        if name == "Wilson":
+            self.op.kind = L.WILSON
+            self.op.kappa = float(params["κ"])
+            self.op.r = float(params.get("r", 1.0))
+        elif name in ("staggered", "Staggered"):
+            self.op.kind = L.STAGGERED
+            self.op.mass = float(params["mass"])
+        else:
+            raise ValueError(f"Dirac_operator {name!r} not supported")      # universe.jl:130 error("not supported")
+        bc = params.get("boundarycondition", [1, 1, 1, -1])                  # parameter_structs.jl:133
+        for i in range(4):
+            self.op.bc[i] = float(bc[i])
+        self.eps = float(params.get("eps_CG", 1e-19))                        # parameter_structs.jl:174
+        self.maxsteps = int(params.get("MaxCGstep", 3000))                   # parameter_structs.jl:175
+        self.verbose = int(params.get("verbose_level", 1))
+        self.method = params.get("method_CG", "bicg")
+        self.ctx = x.ctx
+        self.kind = self.op.kind
+        self.last = {}
+        self._bind(U)
+
+    def _bind(self, U: Gaugefields):
+        self.U = U
+        ptrs = (C.c_void_p * 4)(*[U.data[mu].ctypes.data for mu in range(4)])
+        self.ctx.call("lqcd_gauge_upload", ptrs, 3, 0)
+
+    def __call__(self, U: Gaugefields):
+        self._bind(U)
+        return self
+
+
+class _Derived:
+    def __init__(self, D: DiracOperator, mode):
+        self.D, self.mode = D, mode
+
+
+def adjoint(D: DiracOperator):            # D'
+    return _Derived(D, L.OP_DDAG)
+
+
+def DdagD(D: DiracOperator):              # DdagD_operator
+    return _Derived(D, L.OP_DDAGD)
+
+
+def Dirac_operator(U, x, params) -> DiracOperator:
+    return DiracOperator(U, x, params)
+
+
+def _base(A):
+    return (A, A.mode) if isinstance(A, DiracOperator) else (A.D, A.mode)
+
+
+def mul_(y: FermionField, A, x: FermionField):
+    """LinearAlgebra.mul!(y, A, x)."""
+    D, mode = _base(A)
+    D.ctx.call("lqcd_dslash", C.byref(D.op), y.h, x.h, mode)
+
+
+_METHODS = {"bicg": L.SOLVER_CGNR, "bicgstab": L.SOLVER_BICGSTAB, "preconditiond_bicgstab": L.SOLVER_BICGSTAB}
+
+
+def solve_DinvX_(y: FermionField, A, x: FermionField, history=False):
+    """solve_DinvX!(y, A, x): A y = x, y is the initial guess.  A::Dirac_operator (or its adjoint) -> the
+    routine upstream calls 'bicg' (CGNR) unless params["method_CG"] says otherwise; A::DdagD -> CG."""
+    D, mode = _base(A)
+    method = L.SOLVER_CG if mode == L.OP_DDAGD else _METHODS[D.method]
+    it, rs = C.c_int(0), C.c_double(0.0)
+    hist = np.full(D.maxsteps + 1, np.nan) if (history or D.verbose >= 3) else None
+    hp = hist.ctypes.data_as(L.pdbl) if hist is not None else None
+    try:
+        D.ctx.call("lqcd_solve", C.byref(D.op), y.h, x.h, method, mode, D.eps, D.maxsteps, C.byref(it), C.byref(rs), hp)
+    finally:
+        D.last = {"iters": it.value, "resid_sq": rs.value,
+                  "hist": None if hist is None else hist[: it.value + 1]}
+    if D.verbose >= 3 and hist is not None:
+        for i, v in enumerate(D.last["hist"]):
+            print(f"{i}-th eps: {v}")                                         # upstream println_verbose_level3
+    return D.last
+
+
+def shiftedcg_(ys, D: DiracOperator, x: FermionField, shifts, eps=None, maxsteps=None):
+    """upstream shiftedcg: (DdagD + shifts[j]) ys[j] = x."""
+    sh = np.ascontiguousarray(shifts, dtype=np.float64)
+    hs = (C.c_void_p * len(ys))(*[y.h.value for y in ys])
+    it, rs = C.c_int(0), C.c_double(0.0)
+    D.ctx.call("lqcd_multishift_cg", C.byref(D.op), hs, x.h, sh.ctypes.data_as(L.pdbl), len(ys),
+               D.eps if eps is None else eps, D.maxsteps if maxsteps is None else maxsteps, C.byref(it), C.byref(rs))
+    return {"iters": it.value, "resid_sq": rs.value}
+
+
+# ---------------------------------------------------------------------------------------------------
+# fermion action (Wilson 2-flavour / staggered Nf = 8 form: S_f = eta^dag (D^dag D)^-1 eta)
+# ---------------------------------------------------------------------------------------------------
+class FermiActionB200:
+    """FermiAction(D, parameters_action) (universe.jl:138)."""
+
+    def __init__(self, D: DiracOperator, parameters_action: dict):
+        self.D = D
+        self.Nf = parameters_action.get("Nf", None)
+        self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]   # standardMD.jl:50
+        self.last = {}
+
+
+def FermiAction(D, parameters_action) -> FermiActionB200:
+    return FermiActionB200(D, parameters_action)
+
+
+def gauss_sampling_in_action_(xi: FermionField, U, fa: FermiActionB200, seed=112):     # standardMD.jl:95
+    gauss_distribution_fermion_(xi, seed)
+
+
+def sample_pseudofermions_(eta: FermionField, U, fa: FermiActionB200, xi: FermionField):   # standardMD.jl:96
+    """Wilson / staggered: eta = D^dag xi  (SURVEY.md App. C.6)."""
+    fa.D(U)
+    mul_(eta, adjoint(fa.D), xi)
+
+
+def evaluate_FermiAction(fa: FermiActionB200, U, eta: FermionField) -> float:           # standardHMC.jl:69-71
+    """S_f = eta^dag (D^dag D)^-1 eta: one CG solve."""
+    D = fa.D(U)
+    X = fa._temporary_fermionfields[0]
+    clear_fermion_(X)
+    fa.last = solve_DinvX_(X, DdagD(D), eta)
+    return dot(eta, X).real
+
+
+def calc_UdSfdU_(UdSfdU: np.ndarray, fa: FermiActionB200, U, eta: FermionField):         # AbstractMD.jl:129
+    """Fermion MD force: X = (D^dag D)^-1 eta (CG), Y = D X, per-mu colour outer products.
+    UdSfdU: complex128[4,NT,NZ,NY,NX,3,3] in the link layout, overwritten."""
+    D = fa.D(U)
+    X = fa._temporary_fermionfields[0]
+    clear_fermion_(X)
+    out = (C.c_void_p * 4)(*[UdSfdU[mu].ctypes.data for mu in range(4)])
+    it, act = C.c_int(0), C.c_double(0.0)
+    D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, C.byref(it), C.byref(act))
+    fa.last = {"iters": it.value, "action": act.value}
+    return fa.last
