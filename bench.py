@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200-native Dirac-solve path (contract: see the task prompt).
+
+Metric (BASELINE.json): Wilson Dslash GFLOP/s (+ CG iterations/s) at 32^4, fp64, 1/2/4/8 B200 vs CPU ref.
+A "step" is ONE application y = D x of the Wilson operator (LinearAlgebra.mul!(y, D, x)) on the full
+32^4 lattice (configs[3] volume; 16^4 of configs[1] is L2-resident and is a parity-test size, not a bench line),
+synthetic hot SU(3) links generated on the device (seed 111) and a Gaussian source (seed 112).
+
+  value      whole-job Dslash GFLOP/s = 1368 flop/site x V / (mean CUDA-event time of the K timed
+             applications, max over ranks); inputs resident in HBM; L2 flushed between applications
+             (512 MB memset outside the event brackets).
+  roofline   HBM: achieved = 960 B/site x V / t  against MEASURED_PEAKS.json:hbm_gbs.
+  e2e        the same metric through the reference-facing call with HOST buffers: per step the source is
+             copied host->device (pinned), mul_(y, D, x) runs, and the result is copied back.
+  cg         CG iterations/s of solve_DinvX_(y, DdagD, b) (device resident and through host buffers).
+  cpu_baseline / --impl reference: the CPU oracle (oracle/lqcd_oracle.c, a restatement of the reference's
+             Julia CPU path; the reference itself is Julia and cannot run here) on all host threads.
+
+N > 1 (torchrun): strong scaling -- the 32^4 lattice is split along T (then Z) over the ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT), str(ROOT / "latticeqcd.jl_b200")]
+
+FLOP_PER_SITE = 1368          # 1320 hopping + 48 xpay
+BYTES_PER_SITE = 960          # 576 links + 192 in + 192 out
+CG_BYTES_PER_SITE = 4224      # un-fused algorithmic figure (2 mul! + 12 vector passes), SURVEY.md 8d
+KAPPA = 0.12
+BC = [1, 1, 1, -1]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lattice", default="32x32x32x32")
+    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json:hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (oracle).  Used for cpu_baseline (rank 0, N=1) and for --impl reference.
+# ---------------------------------------------------------------------------------------------------
+def cpu_dslash(dims, steps, warmup, threads):
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.set_threads(threads)
+    op = orc.make_op(dims, kappa=KAPPA)
+    NX, NY, NZ, NT = dims
+    V = NX * NY * NZ * NT
+    # synthetic links: a 4^4 Haar block tiled over the lattice (content does not affect CPU timing)
+    small = orc.random_su3((4, 4, 4, 4), seed=111)
+    reps = (1, NT // 4, NZ // 4, NY // 4, NX // 4, 1, 1)
+    U = np.ascontiguousarray(np.tile(small, reps))
+    rng = np.random.default_rng(112)
+    x = np.ascontiguousarray(rng.standard_normal((4, NT, NZ, NY, NX, 3)) + 1j * rng.standard_normal((4, NT, NZ, NY, NX, 3)))
+    for _ in range(warmup):
+        orc.apply(op, orc.WILSON, orc.D, U, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.apply(op, orc.WILSON, orc.D, U, x)
+    dt = (time.perf_counter() - t0) / steps
+    return {"gflops": FLOP_PER_SITE * V / dt / 1e9, "ms": dt * 1e3, "threads": threads}
+
+
+def run_reference(args, dims):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    thr = host_threads()
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    r = cpu_dslash(dims, steps, warm, thr)
+    V = dims[0] * dims[1] * dims[2] * dims[3]
+    line = {
+        "impl": "reference", "metric": "Wilson Dslash GFLOP/s at 32^4 fp64", "value": r["gflops"], "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Wilson Dslash mul!(y,D,x), {args.lattice}, kappa={KAPPA}, bc={BC}, CPU oracle port of the reference's Julia path"},
+        "cpu_baseline": {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{steps} full-lattice applications at {args.lattice} (requested {args.steps})"},
+        "e2e": {"value": r["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# small cudart wrapper: events on the library's own stream
+# ---------------------------------------------------------------------------------------------------
+class Cudart:
+    def __init__(self):
+        self.rt = None
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                self.rt = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if self.rt is None:
+            raise RuntimeError("libcudart not found")
+        self.rt.cudaEventCreate.argtypes = [C.POINTER(C.c_void_p)]
+        self.rt.cudaEventRecord.argtypes = [C.c_void_p, C.c_void_p]
+        self.rt.cudaEventSynchronize.argtypes = [C.c_void_p]
+        self.rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+
+    def event(self):
+        e = C.c_void_p()
+        assert self.rt.cudaEventCreate(C.byref(e)) == 0
+        return e
+
+    def record(self, e, stream):
+        assert self.rt.cudaEventRecord(e, C.c_void_p(stream)) == 0
+
+    def elapsed_ms(self, e0, e1):
+        assert self.rt.cudaEventSynchronize(e1) == 0
+        ms = C.c_float()
+        assert self.rt.cudaEventElapsedTime(C.byref(ms), e0, e1) == 0
+        return ms.value
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(int(r[1]) for r in rows if len(r) >= 9 and r[1].isdigit())
+        reasons = set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(r[2]) for r in rows if len(r) >= 9 and r[2].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def choose_procgrid(n):
+    # T first, then Z (north_star): keep T_local >= 8 where possible
+    return {1: (1, 1, 1, 1), 2: (1, 1, 1, 2), 4: (1, 1, 1, 4), 8: (1, 1, 2, 4)}[n]
+
+
+def run_b200(args, dims):
+    import numpy as np
+    import torch
+    import lqcd_b200 as q
+    from lqcd_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pg = choose_procgrid(world)
+    ctx = q.get_context(dims, procgrid=pg, rank=rank, device=local_rank)
+    if world > 1:
+        q.connect_ranks(ctx, dist)
+    ctx.call("lqcd_gauge_random", 111, -1.0)
+    Vloc = int(np.prod(ctx.local_dims))
+    V = int(np.prod(dims))
+    op = L.LqcdOp()
+    op.kind, op.kappa, op.r = L.WILSON, KAPPA, 1.0
+    for i, b in enumerate(BC):
+        op.bc[i] = b
+    x, y = q.FermionField(ctx, L.WILSON), q.FermionField(ctx, L.WILSON)
+    q.gauss_distribution_fermion_(x, 112)
+    rt = Cudart()
+    stream = ctx.stream()
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident Dslash: K timed applications, L2 flushed between ----------------
+    mean, mn = C.c_double(), C.c_double()
+    ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, max(args.warmup, 3), 1, C.byref(mean), C.byref(mn))
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launch_count()
+    t_wall0 = time.perf_counter()
+    ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, args.steps, 1, C.byref(mean), C.byref(mn))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - l0
+    ms = max_over_ranks(mean.value)
+    ms_min = max_over_ranks(mn.value)
+    gflops = FLOP_PER_SITE * V / (ms * 1e-3) / 1e9
+    gbs = BYTES_PER_SITE * V / (ms * 1e-3) / 1e9
+
+    # ---------------- device-resident CG: iterations/s of solve_DinvX!(y, DdagD, b) ------------------
+    ctx.call("lqcd_gauge_random", 111, 0.3)                         # warm field: realistic conditioning
+    sol = q.FermionField(ctx, L.WILSON)
+    it, rs = C.c_int(0), C.c_double(0.0)
+
+    def cg_run(maxit):
+        q.clear_fermion_(sol)
+        st = ctx.lib.lqcd_solve(ctx.h, C.byref(op), sol.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 0.0, maxit, C.byref(it), C.byref(rs), None)
+        assert st in (L.LQCD_OK, L.ERR_NOCONV), ctx.lib.lqcd_last_error(ctx.h)
+        return it.value
+
+    cg_run(10)
+    barrier()
+    e0, e1 = rt.event(), rt.event()
+    rt.record(e0, stream)
+    n_it = cg_run(args.cg_iters)
+    rt.record(e1, stream)
+    cg_ms = max_over_ranks(rt.elapsed_ms(e0, e1))
+    cg_ips = n_it / (cg_ms * 1e-3)
+    # converged solve for the residual report
+    it_conv, rs_conv = None, None
+    st = ctx.lib.lqcd_solve(ctx.h, C.byref(op), sol.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 1e-10, 3000, C.byref(it), C.byref(rs), None)
+    if st == L.LQCD_OK:
+        it_conv, rs_conv = it.value, rs.value
+    ctx.call("lqcd_gauge_random", 111, -1.0)
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- e2e: host buffers through the public API ----------------------------------------
+    e2e = None
+    e2e_cg = None
+    if world == 1:
+        shape = x.host_shape
+        hx = torch.empty(shape, dtype=torch.complex128).pin_memory()
+        hy = torch.empty(shape, dtype=torch.complex128).pin_memory()
+        hx.copy_(torch.from_numpy(x.to_host()))
+        U = None
+        D = q.DiracOperator.__new__(q.DiracOperator)                  # operator bound to the links already on the device
+        D.op, D.ctx, D.kind, D.mode = op, ctx, L.WILSON, L.OP_D
+        D.eps, D.maxsteps, D.verbose, D.method, D.last = 0.0, args.cg_iters, 1, "bicg", {}
+        hxn, hyn = hx.numpy(), hy.numpy()
+
+        def e2e_step():
+            ctx.call("lqcd_fermion_upload", x.h, hxn.ctypes.data, 0)
+            q.mul_(y, D, x)
+            ctx.call("lqcd_fermion_download", y.h, hyn.ctypes.data, 0)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        k = min(args.steps, 20)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / k
+        nbytes = hx.numel() * 16
+        e2e = {"value": FLOP_PER_SITE * V / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": dt * 1e3, "call": "x.from_host(h); mul_(y, D, x); y.to_host()  [lqcd_fermion_upload + lqcd_dslash + lqcd_fermion_download]"}
+        # CG through host buffers: upload source, solve, download solution
+        ctx.call("lqcd_gauge_random", 111, 0.3)
+        t0 = time.perf_counter()
+        ctx.call("lqcd_fermion_upload", x.h, hxn.ctypes.data, 0)
+        n2 = cg_run(args.cg_iters)
+        ctx.call("lqcd_fermion_download", sol.h, hyn.ctypes.data, 0)
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e_cg = {"value": n2 / dt, "unit": "CG iterations/s", "iters": n2, "h2d_bytes": nbytes, "d2h_bytes": nbytes}
+
+    # ---------------- CPU baseline (oracle port, bounded sample) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        thr = host_threads()
+        r = cpu_dslash(dims, 3, 1, thr)
+        cpu = {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["threads"], "kind": "port",
+               "sample": f"3 full-lattice Wilson applications at {args.lattice} ({r['ms']:.0f} ms each), oracle/lqcd_oracle.c with OpenMP"}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    traffic = None
+    tp = ROOT / "profiles" / "wilson_dslash_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+    line = {
+        "metric": "Wilson Dslash GFLOP/s at 32^4 fp64", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Wilson Dslash mul!(y,D,x) {args.lattice} SU(3) hot links, kappa={KAPPA}, r=1, bc={BC}",
+                   "procgrid": list(pg), "l2": "flushed between steps (512 MB memset outside the CUDA-event brackets); inputs 806 MB > 126 MB L2",
+                   "timing": "per-step CUDA events on the library stream, mean of K, max over ranks", "ms_min": ms_min,
+                   "wall_s_timed_region": t_wall},
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_SITE * V, "kernel": "wilson_dslash_kernel"},
+        "cg": {"iters_per_s": cg_ips, "iters": n_it, "ms": cg_ms, "roofline_frac_unfused": CG_BYTES_PER_SITE * V * cg_ips / 1e9 / peak,
+               "converged_iters_eps1e-10": it_conv, "resid_sq": rs_conv, "field": "warm eps=0.3"},
+        "e2e": e2e, "e2e_cg": e2e_cg, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    dims = tuple(int(v) for v in args.lattice.split("x"))
+    if args.impl == "reference":
+        run_reference(args, dims)
+    else:
+        run_b200(args, dims)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ SOURCES = ["context.cu", "wilson_dslash.cu", "staggered_dslash.cu", "blas.cu", "
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false" if False else "-fmad=true"]
+         "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2", "-fmad=true"]
 
 
 def _deps():
@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [str(objdir / (s + ".o")) for s in SOURCES]
     if jobs or not OUT.exists():
-        cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-o", str(OUT), *objs, "-lcudart"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOSTCXX, "-o", str(OUT), *objs, "-lcudart"]
         run(cmd)
     return OUT
 

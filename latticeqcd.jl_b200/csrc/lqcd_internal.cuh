@@ -51,7 +51,8 @@ struct SolverState {
     double eps;
     double are, aim, bre, bim, cre, cim;   // generic complex scalars (BiCGStab)
     double rho_re, rho_im, omega_re, omega_im, alpha_re, alpha_im;
-    int done;         // 1 once converged
+    int done;         // 1 once converged (or broken down)
+    int failed;       // 1 if |r|^2 became NaN/Inf (Krylov breakdown)
     int iters;        // iteration at which convergence was detected
     int it;           // running iteration counter
     int maxit;

@@ -168,5 +168,6 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
             tot[j] = s;
         }
         apply_finish(finish, tot, R.st, R.hist);
+        if (finish != FIN_STORE && !(fabs(tot[0]) <= 1.79e308)) { R.st->done = 1; R.st->failed = 1; R.st->iters = R.st->it; }
     }
 }

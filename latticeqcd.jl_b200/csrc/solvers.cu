@@ -127,6 +127,8 @@ static int run_loop(lqcd_ctx *ctx, int maxsteps, Body body, int *iters, double *
     if (iters) *iters = done ? fin.iters : fin.it;
     if (resid_sq) *resid_sq = fin.rr;
     (void)nb;
+    if (done && fin.failed)
+        return lqcd_fail(ctx, LQCD_ERR_NOCONV, "Krylov breakdown: |r|^2 is not finite at step %d (e.g. BiCGStab with r0~ = r0 on a point source)", fin.it);
     if (!done)
         return lqcd_fail(ctx, LQCD_ERR_NOCONV, "solver not converged after %d steps (|r|^2 = %.6e, eps = %.3e)", fin.it, fin.rr, fin.eps);
     return LQCD_OK;

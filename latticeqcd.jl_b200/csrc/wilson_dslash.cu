@@ -15,6 +15,8 @@
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 struct WilsonArgs {
     cplx *out;
@@ -120,8 +122,8 @@ __device__ __forceinline__ void hop_pair(cplx (&acc)[12], const WilsonArgs &A, i
     }
 }
 
-template <int DAG>
-__global__ void __launch_bounds__(256, 1) wilson_dslash_kernel(const WilsonArgs A) {
+template <int DAG, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int blk = block_of_warp(A.g, blockIdx.x, warp);
@@ -172,8 +174,27 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     A.red = ctx->red; A.it = 0;
     const int bs = 32 * ctx->g.wpc;
     const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
-    if (dagger) wilson_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
-    else        wilson_dslash_kernel<0><<<grid, bs, 0, s>>>(A);
+    // register budget variants (tuning knob LQCD_LB = "maxthreads,minblocks"; default picked by measurement)
+    static int lb = -1;
+    if (lb < 0) {
+        lb = 0;
+        if (const char *e = getenv("LQCD_LB")) {
+            int a = 0, b = 0;
+            if (sscanf(e, "%d,%d", &a, &b) == 2) lb = a * 100 + b;
+        }
+    }
+#define WL(MT, MB)                                                                   \
+    do {                                                                             \
+        if (dagger) wilson_dslash_kernel<1, MT, MB><<<grid, bs, 0, s>>>(A);          \
+        else        wilson_dslash_kernel<0, MT, MB><<<grid, bs, 0, s>>>(A);          \
+    } while (0)
+    if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
+    if (lb == 12803 && bs <= 128) WL(128, 3);
+    else if (lb == 12804 && bs <= 128) WL(128, 4);
+    else if (lb == 25602) WL(256, 2);
+    else if (lb == 12802 && bs <= 128) WL(128, 2);
+    else WL(256, 1);
+#undef WL
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;

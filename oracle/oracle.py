@@ -53,6 +53,9 @@ def lib() -> C.CDLL:
         so = _HERE / "liblqcd_oracle.so"
         if not so.exists():
             build()
+        # libgomp's default spin-waiting burns the container's CPU quota between parallel regions and gets
+        # the process throttled (observed: 60 ms instead of 1 ms per 8^4 application); sleep instead.
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         L = C.CDLL(str(so))
         vp, i64, dbl, ci = C.c_void_p, C.c_int64, C.c_double, C.c_int
         op = C.POINTER(OrcOp)

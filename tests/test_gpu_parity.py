@@ -186,7 +186,10 @@ def test_solve_D_matches_oracle(Uw, method):
     x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
     D = q.Dirac_operator(U, x, wparams(0.12, method_CG=method))
     q.clear_fermion_(x)
-    q.setindex_global_(x, 1, 1, 1, 1, 1, 1, 1)
+    if method == "bicg":
+        q.setindex_global_(x, 1, 1, 1, 1, 1, 1, 1)
+    else:       # BiCGStab with r0~ = r0 breaks down on a point source (rho_1 = 0 for r = 1)
+        x.from_host(orc.gaussian_field(dims, orc.WILSON, seed=21))
     src = x.to_host()
     sol = q.similar(x)
     q.clear_fermion_(sol)
@@ -233,6 +236,21 @@ def test_multishift(Us):
     assert info["iters"] == ref["iters"]
     for y, xr in zip(ys, ref["xs"]):
         assert relerr(y.to_host(), xr) < 1e-10
+
+
+def test_bicgstab_breakdown_is_reported(Uw):
+    """the oracle and the GPU agree that BiCGStab breaks down (NaN) on a point source; surfaced as an error."""
+    U = q.gaugefields_from_array(Uw)
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, wparams(0.12, method_CG="bicgstab"))
+    q.setindex_global_(x, 1, 1, 1, 1, 1, 1, 1)
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    with pytest.raises(q.NotConverged) as e:
+        q.solve_DinvX_(sol, D, x)
+    assert "breakdown" in str(e.value)
+    ref = orc.bicgstab(orc.make_op((4, 4, 4, 4), kappa=0.12), orc.WILSON, Uw, x.to_host())
+    assert not ref["converged"]
 
 
 def test_nonconvergence_is_an_error(Uw):
