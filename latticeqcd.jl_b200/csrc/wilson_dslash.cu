@@ -189,11 +189,12 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         else        wilson_dslash_kernel<0, MT, MB><<<grid, bs, 0, s>>>(A);          \
     } while (0)
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
-    if (lb == 12803 && bs <= 128) WL(128, 3);
-    else if (lb == 12804 && bs <= 128) WL(128, 4);
+    // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
+    // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
+    if (lb == 12804 && bs <= 128) WL(128, 4);
     else if (lb == 25602) WL(256, 2);
-    else if (lb == 12802 && bs <= 128) WL(128, 2);
-    else WL(256, 1);
+    else if (lb == 25601 || bs > 128) WL(256, 1);
+    else WL(128, 3);
 #undef WL
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
