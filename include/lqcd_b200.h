@@ -134,6 +134,10 @@ int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta
 #define LQCD_IPC_HANDLE_BYTES 256
 int lqcd_comm_export(lqcd_ctx *ctx, void *handle_out /* LQCD_IPC_HANDLE_BYTES */);
 int lqcd_comm_connect(lqcd_ctx *ctx, const void *all_handles /* nranks * LQCD_IPC_HANDLE_BYTES, rank order */);
+/* pure geometry (no GPU): local extents, origin and +-mu neighbour ranks of `rank` in the process grid;
+ * the PEs bookkeeping of src/mpi/mpimodule.jl:9-38 restated for the C side. */
+int lqcd_decompose(const int global_dims[4], const int procgrid[4], int rank, int local_dims[4], int origin[4],
+                   int nbr_lo[4], int nbr_hi[4]);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* number of kernels this library launched since context creation (bench.py's gpu_launches) */

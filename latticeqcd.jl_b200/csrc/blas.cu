@@ -48,6 +48,22 @@ __global__ void __launch_bounds__(BLAS_BS) k_dot(const cplx *__restrict__ a, con
     grid_reduce_finish<3>(red, R, finish);
 }
 
+// red0/1 = <w,y> (w may be null), red2 = |y|^2 -- the multi-rank Dslash epilogue (after the halo update)
+__global__ void __launch_bounds__(BLAS_BS) k_dot2(const cplx *__restrict__ w, const cplx *__restrict__ y, size_t n, Reduce R, int finish, int use_state) {
+    if (use_state && R.st->done) return;
+    double red[3] = {0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cplx yv = y[i];
+        if (w) {
+            cplx wv = w[i];
+            red[0] = fma(wv.x, yv.x, red[0]); red[0] = fma(wv.y, yv.y, red[0]);
+            red[1] = fma(wv.x, yv.y, red[1]); red[1] = fma(-wv.y, yv.x, red[1]);
+        }
+        red[2] = fma(yv.x, yv.x, red[2]); red[2] = fma(yv.y, yv.y, red[2]);
+    }
+    grid_reduce_finish<3>(red, R, finish);
+}
+
 // ---- solver kernels -----------------------------------------------------------------------------------
 // r = b - q ; p = r (optional) ; r0 = r (optional) ; red0 = |r|^2 ; red1/2 = <r0,r> = (|r|^2, 0)
 __global__ void __launch_bounds__(BLAS_BS) k_resid_init(const cplx *__restrict__ b, const cplx *__restrict__ q,
@@ -209,6 +225,10 @@ int blas_copy(lqcd_ctx *ctx, cplx *dst, const cplx *src, size_t n) {
 }
 int blas_dot_async(lqcd_ctx *ctx, const cplx *a, const cplx *b, size_t n, int finish) {
     LAUNCH(ctx, k_dot, n, a, b, n, ctx->red, finish);
+    return LQCD_OK;
+}
+int blas_dot2_async(lqcd_ctx *ctx, const cplx *w, const cplx *y, size_t n, int finish, int use_state) {
+    LAUNCH(ctx, k_dot2, n, w, y, n, ctx->red, finish, use_state);
     return LQCD_OK;
 }
 int blas_resid_init(lqcd_ctx *ctx, const cplx *b, const cplx *q, cplx *r, cplx *p, cplx *r0, size_t n, int finish) {

@@ -118,6 +118,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     CT(cudaMalloc(&ctx->red.st, sizeof(SolverState)));
     CT(cudaMemset(ctx->red.st, 0, sizeof(SolverState)));
     ctx->red.hist = nullptr;
+    memset(&ctx->red.cr, 0, sizeof ctx->red.cr);
     CT(cudaMallocHost(&ctx->st_host, 3 * sizeof(SolverState)));
 #undef CT
     *out = ctx;

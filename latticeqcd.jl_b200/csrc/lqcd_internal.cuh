@@ -63,13 +63,40 @@ struct SolverState {
     double red[LQCD_MAX_RED];   // raw reduction results of the last reducing kernel
 };
 
+#define LQCD_MAX_RANKS 8
+#define LQCD_RED_SLOTS 4
+#define LQCD_SPIN_TIMEOUT_CYCLES 6000000000ll      // ~3 s at 1.9 GHz: a lost peer becomes an error, not a hang
+
+// In-kernel all-reduce over NVLink peer memory (one process per GPU).  Every rank's reducing kernel
+// writes its local totals straight into slot [seq % SLOTS][my rank] of EVERY rank's buffer (peer stores),
+// raises a per-(slot, writer) sequence flag with release semantics, then spins on its own local flags until
+// all ranks have arrived and sums the contributions in rank order: identical bits on every rank, no NCCL
+// launch on the critical path of a Krylov iteration.
+struct CommRed {
+    int nranks, rank;
+    unsigned long long *seq;                      // local device counter of reductions performed
+    double *vals[LQCD_MAX_RANKS];                 // vals[r]: rank r's [SLOTS][nranks][LQCD_MAX_RED] array (peer mapped)
+    unsigned long long *flags[LQCD_MAX_RANKS];    // flags[r]: rank r's [SLOTS][nranks] sequence flags
+    int *err;                                     // local device error word (1 = timeout)
+};
+
 // deterministic grid reduction workspace
 struct Reduce {
     double *partials;          // [grid * LQCD_MAX_RED]
     unsigned int *ticket;      // last-block-done counter (self-resetting)
     SolverState *st;           // where results / derived scalars go
     double *hist;              // optional per-iteration |r|^2 history (device)
+    CommRed cr;                // cr.nranks <= 1: single GPU
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 enum FinishOp {
     FIN_STORE = 0,        // st->red[j] = sum_j

@@ -167,6 +167,33 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
             for (int w = 0; w < nwarp; w++) s += sm[j][w];
             tot[j] = s;
         }
+        if (R.cr.nranks > 1) {      // cross-GPU all-reduce over peer memory, deterministic rank order
+            const CommRed &c = R.cr;
+            const unsigned long long seq = ++(*c.seq);
+            const int slot = (int)(seq % LQCD_RED_SLOTS);
+            for (int r = 0; r < c.nranks; r++) {
+                double *dst = c.vals[r] + ((size_t)slot * c.nranks + c.rank) * LQCD_MAX_RED;
+#pragma unroll
+                for (int j = 0; j < NR; j++) dst[j] = tot[j];
+            }
+            __threadfence_system();
+            for (int r = 0; r < c.nranks; r++) st_release_sys(c.flags[r] + (size_t)slot * c.nranks + c.rank, seq);
+            const long long t0 = clock64();
+            bool ok = true;
+            for (int r = 0; r < c.nranks && ok; r++) {
+                while (ld_acquire_sys(c.flags[c.rank] + (size_t)slot * c.nranks + r) < seq) {
+                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { ok = false; break; }
+                }
+            }
+            if (!ok) { *c.err = 1; R.st->done = 1; R.st->failed = 2; }
+#pragma unroll
+            for (int j = 0; j < NR; j++) {
+                double s = 0.0;
+                for (int r = 0; r < c.nranks; r++)
+                    s += __ldcg(c.vals[c.rank] + ((size_t)slot * c.nranks + r) * LQCD_MAX_RED + j);
+                tot[j] = s;
+            }
+        }
         apply_finish(finish, tot, R.st, R.hist);
         if (finish != FIN_STORE && !(fabs(tot[0]) <= 1.79e308)) { R.st->done = 1; R.st->failed = 1; R.st->iters = R.st->it; }
     }

@@ -26,6 +26,7 @@ int blas_bi_xr(lqcd_ctx *ctx, cplx *x, const cplx *p, const cplx *s, cplx *r, co
 int blas_bi_p(lqcd_ctx *ctx, cplx *p, const cplx *r, const cplx *v, size_t n);
 int blas_ms_update_xp(lqcd_ctx *ctx, const MSPtrs &P, const cplx *r, size_t n, int it);
 int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse);   // comm.cu
+int comm_check_error(lqcd_ctx *ctx);
 
 static int check_op(const lqcd_ctx *ctx, const lqcd_op *op) {
     if (!op) return lqcd_fail(ctx, LQCD_ERR_ARG, "null operator descriptor");
@@ -64,7 +65,7 @@ extern "C" int lqcd_dslash(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, co
     if (mode == LQCD_OP_DDAGD) LQCD_TRY(get_scratch(ctx, op->kind, 0, &tmp));
     LQCD_TRY(apply_async(ctx, op, y->d, x->d, mode, tmp ? tmp->d : nullptr, nullptr, nullptr));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return LQCD_OK;
+    return comm_check_error(ctx);
 }
 
 // ---- solver driver -----------------------------------------------------------------------------------
@@ -127,6 +128,8 @@ static int run_loop(lqcd_ctx *ctx, int maxsteps, Body body, int *iters, double *
     if (iters) *iters = done ? fin.iters : fin.it;
     if (resid_sq) *resid_sq = fin.rr;
     (void)nb;
+    LQCD_TRY(comm_check_error(ctx));
+    if (done && fin.failed == 2) return lqcd_fail(ctx, LQCD_ERR_COMM, "all-reduce timed out on the device at step %d", fin.it);
     if (done && fin.failed)
         return lqcd_fail(ctx, LQCD_ERR_NOCONV, "Krylov breakdown: |r|^2 is not finite at step %d (e.g. BiCGStab with r0~ = r0 on a point source)", fin.it);
     if (!done)

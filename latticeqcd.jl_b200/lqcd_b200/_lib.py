@@ -73,6 +73,7 @@ SIGNATURES = {
     "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, pi32, pdbl]),
     "lqcd_comm_export": (i32, [vp, vp]),
     "lqcd_comm_connect": (i32, [vp, vp]),
+    "lqcd_decompose": (i32, [pi32, pi32, i32, pi32, pi32, pi32, pi32]),
     "lqcd_launch_count": (i32, [vp, C.POINTER(u64)]),
     "lqcd_time_dslash": (i32, [vp, pop, vp, vp, i32, i32, i32, pdbl, pdbl]),
     "lqcd_stream": (i32, [vp, pvp]),

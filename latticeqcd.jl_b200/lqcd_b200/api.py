@@ -73,6 +73,37 @@ def get_context(dims, procgrid=(1, 1, 1, 1), rank=0, device=0) -> Context:
     return _CTX[key]
 
 
+def decompose(dims, procgrid, rank):
+    """lqcd_decompose: (local_dims, origin, nbr_lo, nbr_hi) -- runs without a GPU."""
+    lib = L.load()
+    a = [(C.c_int * 4)() for _ in range(4)]
+    st = lib.lqcd_decompose((C.c_int * 4)(*dims), (C.c_int * 4)(*procgrid), int(rank), *a)
+    if st != 0:
+        raise ValueError(f"bad decomposition dims={dims} procgrid={procgrid} rank={rank}")
+    return tuple(tuple(v) for v in a)
+
+
+def exchange_handles(blob: bytes, dist) -> bytes:
+    """all-gather one fixed-size byte blob per rank, in rank order (torch.distributed: gloo on CPU tensors,
+    nccl on CUDA tensors).  The Julia shim does the same with MPI.Allgather."""
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
+
+def connect_ranks(ctx: Context, dist):
+    """Map every rank's comm buffer into every other rank (CUDA IPC over NVLink): lqcd_comm_export ->
+    all-gather -> lqcd_comm_connect -> barrier."""
+    buf = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+    ctx.call("lqcd_comm_export", buf)
+    allh = exchange_handles(buf.raw, dist)
+    ctx.call("lqcd_comm_connect", C.c_char_p(allh))
+    dist.barrier()
+
+
 # ---------------------------------------------------------------------------------------------------
 # link fields (Gaugefields.jl container; host-resident, Julia layout)
 # ---------------------------------------------------------------------------------------------------
@@ -125,10 +156,12 @@ def Initialize_Gaugefields(NC, Nwing, NX, NY, NZ, NT, condition="cold", seed=111
     return Gaugefields(data, dims, ctx_args)
 
 
-def gaugefields_from_array(arr, **ctx_args) -> Gaugefields:
-    """Wrap links given as [4,NT,NZ,NY,NX,3(b),3(a)] (what load_BridgeText!/ILDG produce, universe.jl:62-68)."""
+def gaugefields_from_array(arr, global_dims=None, **ctx_args) -> Gaugefields:
+    """Wrap links given as [4,NT,NZ,NY,NX,3(b),3(a)] (what load_BridgeText!/ILDG produce, universe.jl:62-68).
+    Multi-rank: `arr` is this rank's LOCAL block, `global_dims` the full lattice and ctx_args carries
+    procgrid / rank / device (upstream's *_mpi field types hold local arrays the same way)."""
     _, NT, NZ, NY, NX, _, _ = arr.shape
-    return Gaugefields(arr, (NX, NY, NZ, NT), ctx_args)
+    return Gaugefields(arr, tuple(global_dims) if global_dims else (NX, NY, NZ, NT), ctx_args)
 
 
 # ---------------------------------------------------------------------------------------------------

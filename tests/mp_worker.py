@@ -1,0 +1,117 @@
+"""
+Multi-rank parity worker (launched by tests/test_multirank.py through torch.distributed.run, gloo backend so
+that several ranks may share one GPU on a single-GPU box: the CUDA-IPC / peer-memory path is identical).
+
+Every rank builds the same global synthetic fields, uploads its LOCAL block, runs the operator and the
+solvers through the C ABI, and rank 0 compares the gathered result with the CPU oracle on the global lattice.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "latticeqcd.jl_b200")]
+import lqcd_b200 as q                     # noqa: E402
+from oracle import oracle as orc          # noqa: E402
+
+
+def main():
+    dims = tuple(int(v) for v in sys.argv[1].split("x"))
+    pg = tuple(int(v) for v in sys.argv[2].split("x"))
+    kind_name = sys.argv[3]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ndev = torch.cuda.device_count()
+    dev = int(os.environ.get("LOCAL_RANK", rank)) % ndev
+    kind = orc.WILSON if kind_name == "Wilson" else orc.STAGGERED
+    Ug = orc.random_su3(dims, seed=17, eps=0.4)
+    src = orc.gaussian_field(dims, kind, seed=23)
+    ctx = q.get_context(dims, procgrid=pg, rank=rank, device=dev)
+    q.connect_ranks(ctx, dist)
+    (lx, ly, lz, lt), (ox, oy, oz, ot) = ctx.local_dims, ctx.origin
+    sl = (slice(ot, ot + lt), slice(oz, oz + lz), slice(oy, oy + ly), slice(ox, ox + lx))
+    Ul = np.ascontiguousarray(Ug[(slice(None),) + sl])
+    U = q.gaugefields_from_array(Ul, global_dims=dims, procgrid=pg, rank=rank, device=dev)
+    x = q.Initialize_pseudofermion_fields(U[0], kind_name)
+    params = {"Dirac_operator": kind_name, "κ": 0.125, "mass": 0.2, "eps_CG": 1e-18, "MaxCGstep": 2000,
+              "boundarycondition": [1, 1, 1, -1]}
+    if kind_name != "Wilson":
+        params["Dirac_operator"] = "staggered"
+    D = q.Dirac_operator(U, x, params)
+    loc = (lambda a: np.ascontiguousarray(a[(slice(None),) + sl])) if kind == orc.WILSON else (lambda a: np.ascontiguousarray(a[sl]))
+    x.from_host(loc(src))
+    y = q.similar(x)
+    op = orc.make_op(dims, kappa=0.125, mass=0.2)
+
+    def gather(f):
+        h = torch.from_numpy(f.to_host())
+        out = [torch.empty_like(h) for _ in range(world)] if rank == 0 else None
+        dist.gather(h, out, dst=0)
+        if rank != 0:
+            return None
+        full = np.zeros(orc.field_shape(dims, kind), dtype=complex)
+        for r in range(world):
+            (ld, og, _, _) = q.decompose(dims, pg, r)
+            s2 = (slice(og[3], og[3] + ld[3]), slice(og[2], og[2] + ld[2]), slice(og[1], og[1] + ld[1]), slice(og[0], og[0] + ld[0]))
+            if kind == orc.WILSON:
+                full[(slice(None),) + s2] = out[r].numpy()
+            else:
+                full[s2] = out[r].numpy()
+        return full
+
+    fails = []
+
+    def check(name, got, want, tol):
+        if rank == 0:
+            err = np.abs(got - want).max() / np.abs(want).max()
+            print(f"[mp {world} ranks {pg}] {kind_name} {name}: rel err {err:.2e}", flush=True)
+            if not err < tol:
+                fails.append(name)
+
+    for A, m, nm in ((D, orc.D, "D"), (q.adjoint(D), orc.DDAG, "Ddag"), (q.DdagD(D), orc.DDAGD, "DdagD")):
+        q.mul_(y, A, x)
+        got = gather(y)
+        if rank == 0:
+            check(nm, got, orc.apply(op, kind, m, Ug, src), 1e-13)
+    # global dot product
+    d = q.dot(x, y)
+    if rank == 0:
+        want = np.vdot(src, orc.apply(op, kind, orc.DDAGD, Ug, src))
+        if abs(d - want) > 1e-10 * abs(want):
+            fails.append("dot")
+        print(f"[mp] dot rel err {abs(d - want) / abs(want):.2e}", flush=True)
+    # CG on DdagD and CGNR on D
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    got = gather(sol)
+    if rank == 0:
+        ref = orc.cg(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
+        print(f"[mp] CG iters {info['iters']} (oracle {ref['iters']})", flush=True)
+        if info["iters"] != ref["iters"]:
+            fails.append("cg iters")
+        check("CG solution", got, ref["x"], 1e-9)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, D, x)
+    got = gather(sol)
+    if rank == 0:
+        ref = orc.cgnr(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
+        print(f"[mp] CGNR iters {info['iters']} (oracle {ref['iters']})", flush=True)
+        if info["iters"] != ref["iters"]:
+            fails.append("cgnr iters")
+        check("CGNR solution", got, ref["x"], 1e-9)
+    flag = torch.tensor([len(fails)])
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    if rank == 0 and fails:
+        print("FAILED:", fails, flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
