@@ -22,6 +22,8 @@
 #include "wilson_spin.cuh"
 #include <unistd.h>
 #include <cstring>
+#include <cstdlib>
+#include <vector>
 
 struct HandleBlob {
     uint32_t magic;
@@ -48,6 +50,8 @@ struct CommState {
     int face[4];                      // face sites per direction
     int nbr[4][2];                    // neighbour ranks [mu][0 lower, 1 upper]
     unsigned long long halo_seq;
+    int *bsites;                      // device table of boundary sites (ascending site index)
+    int nbsites;
 };
 
 static int rank_of(const lqcd_ctx *ctx, const int pc[4]) {
@@ -85,6 +89,20 @@ static int comm_alloc(lqcd_ctx *ctx) {
     if (e != cudaSuccess) { delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMalloc(comm %zu) -> %s", off, cudaGetErrorString(e)); }
     e = cudaMemset(c->base, 0, c->bytes);
     if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMemset(comm) -> %s", cudaGetErrorString(e)); }
+    {   // boundary-site table: sites with a coordinate on a face of a partitioned direction
+        std::vector<int> bs;
+        for (int s = 0; s < g.V; s++) {
+            int r = s, cc[4];
+            for (int i = 0; i < 4; i++) { cc[i] = r % d[i]; r /= d[i]; }
+            bool b = false;
+            for (int i = 0; i < 4; i++) if (g.part[i] && (cc[i] == 0 || cc[i] == d[i] - 1)) b = true;
+            if (b) bs.push_back(s);
+        }
+        c->nbsites = (int)bs.size();
+        e = cudaMalloc(&c->bsites, sizeof(int) * (bs.size() + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(c->bsites, bs.data(), sizeof(int) * bs.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "boundary table -> %s", cudaGetErrorString(e)); }
+    }
     c->peer[ctx->rank] = c->base;
     ctx->comm = c;
     return LQCD_OK;
@@ -96,6 +114,7 @@ int comm_destroy(lqcd_ctx *ctx) {
     for (int r = 0; r < ctx->nranks; r++)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
     cudaFree(c->base);
+    cudaFree(c->bsites);
     delete c;
     ctx->comm = nullptr;
     return LQCD_OK;
@@ -185,7 +204,11 @@ struct HaloArgs {
     int *err;
     const SolverState *st;
     int use_state;
-    int mu;                    // exterior: direction handled by this launch
+    const int *bsites;         // exterior: table of boundary sites (on at least one partitioned face)
+    int nbsites;
+    DslashFuse fuse;           // exterior: fused epilogue (reductions finished here)
+    Reduce red;
+    unsigned int part_offset;  // exterior: partials deposited by the interior kernel precede ours
 };
 
 // face index -> site (coordinate mu fixed to cm); faces are enumerated lexicographically over the other three.
@@ -302,25 +325,34 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const HaloArgs A) {
     }
 }
 
+// face index of a site for direction MU: lexicographic over the other three coordinates (matches face_site()).
 template <int MU>
-__device__ __forceinline__ void wilson_ext_site(const HaloArgs &A, int side, int f, int s) {
+__device__ __forceinline__ int face_index(const Geom &g, int x, int y, int z, int t) {
+    if (MU == 0) return y + g.Y * (z + g.Z * t);
+    if (MU == 1) return x + g.X * (z + g.Z * t);
+    if (MU == 2) return x + g.X * (y + g.Y * t);
+    return x + g.X * (y + g.Y * z);
+}
+
+// Wilson: add the off-rank hop(s) of direction MU at face site s into acc (12 complex, in units of "hopping sum").
+template <int MU>
+__device__ __forceinline__ void wilson_ext_dir(const HaloArgs &A, cplx (&acc)[12], int s, int side, int f) {
     const cplx *src = A.recv[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
     cplx h0[3], h1[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { h0[c] = __ldcg(src + c * 32); h1[c] = __ldcg(src + (3 + c) * 32); }
-    cplx acc[12];
+    const double phase = side == 0 ? (A.pfirst[MU] ? A.bc[MU] : 1.0) : (A.plast[MU] ? A.bc[MU] : 1.0);
+    if (phase != 1.0) {
 #pragma unroll
-    for (int k = 0; k < 12; k++) acc[k] = cmake(0, 0);
-    double phase;
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
     if (side == 0) {                        // my low face, backward hop: data is already U^dag P psi
-        phase = A.pfirst[MU] ? A.bc[MU] : 1.0;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             if (A.dagger) reconstruct<MU, -1>(acc, a, h0[a], h1[a]);
             else          reconstruct<MU, +1>(acc, a, h0[a], h1[a]);
         }
     } else {                                // my high face, forward hop: apply U_mu(n)
-        phase = A.plast[MU] ? A.bc[MU] : 1.0;
         const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
@@ -334,97 +366,119 @@ __device__ __forceinline__ void wilson_ext_site(const HaloArgs &A, int side, int
             else          reconstruct<MU, -1>(acc, a, g0, g1);
         }
     }
-    const double cf = A.coef * phase;
-    cplx *yp = A.out + (size_t)(s >> 5) * (12 * 32) + (s & 31);
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        cplx v = yp[k * 32];
-        v.x = fma(cf, acc[k].x, v.x); v.y = fma(cf, acc[k].y, v.y);
-        yp[k * 32] = v;
-    }
 }
 
 template <int MU>
-__device__ __forceinline__ void stag_ext_site(const HaloArgs &A, int side, int f, int s, int x, int y, int z) {
+__device__ __forceinline__ void stag_ext_dir(const HaloArgs &A, cplx (&acc)[3], int s, int side, int f, double eta) {
     const cplx *src = A.recv[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
-    cplx h[3], acc[3];
+    cplx h[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) h[c] = __ldcg(src + c * 32);
-    const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
-    const int e = (MU == 0) ? 0 : (MU == 1) ? gx : (MU == 2) ? gx + gy : gx + gy + gz;
-    const double eta = (e & 1) ? -1.0 : 1.0;
-    double cf;
     if (side == 0) {
-        cf = -0.5 * eta * (A.pfirst[MU] ? A.bc[MU] : 1.0);
+        const double cf = -0.5 * eta * (A.pfirst[MU] ? A.bc[MU] : 1.0);
 #pragma unroll
-        for (int c = 0; c < 3; c++) acc[c] = h[c];
+        for (int c = 0; c < 3; c++) { acc[c].x = fma(cf, h[c].x, acc[c].x); acc[c].y = fma(cf, h[c].y, acc[c].y); }
     } else {
-        cf = 0.5 * eta * (A.plast[MU] ? A.bc[MU] : 1.0);
+        const double cf = 0.5 * eta * (A.plast[MU] ? A.bc[MU] : 1.0);
         const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             cplx g = cmake(0, 0);
 #pragma unroll
             for (int b = 0; b < 3; b++) cfma(g, ldg128(lk + (a * 3 + b) * 32), h[b]);
-            acc[a] = g;
+            acc[a].x = fma(cf, g.x, acc[a].x); acc[a].y = fma(cf, g.y, acc[a].y);
         }
-    }
-    cf *= A.coef;
-    cplx *yp = A.out + (size_t)(s >> 5) * (3 * 32) + (s & 31);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        cplx v = yp[k * 32];
-        v.x = fma(cf, acc[k].x, v.x); v.y = fma(cf, acc[k].y, v.y);
-        yp[k * 32] = v;
     }
 }
 
+#define EXT_DIR_W(MU, coord, dim)                                                            \
+    if (A.g.part[MU]) {                                                                      \
+        if ((coord) == 0) wilson_ext_dir<MU>(A, acc, s, 0, face_index<MU>(A.g, x, y, z, t)); \
+        if ((coord) == (dim)-1) wilson_ext_dir<MU>(A, acc, s, 1, face_index<MU>(A.g, x, y, z, t)); \
+    }
+#define EXT_DIR_S(MU, coord, dim, eta)                                                       \
+    if (A.g.part[MU]) {                                                                      \
+        if ((coord) == 0) stag_ext_dir<MU>(A, acc, s, 0, face_index<MU>(A.g, x, y, z, t), eta); \
+        if ((coord) == (dim)-1) stag_ext_dir<MU>(A, acc, s, 1, face_index<MU>(A.g, x, y, z, t), eta); \
+    }
+
+// One thread per BOUNDARY site (precomputed table): all its off-rank hops are added in registers and y is
+// updated once, so sites on several faces (edges/corners of a T x Z decomposition) have no write race, and the
+// fused <w,y>, |y|^2 reductions of these sites are finished here together with the interior kernel's partials.
 __global__ void __launch_bounds__(128) halo_exterior_kernel(const HaloArgs A) {
     if (A.use_state && A.st->done) return;
-    const int mu = A.mu;
-    // wait for both neighbours' data of this application
     __shared__ int ok;
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         int good = 1;
-        for (int side = 0; side < 2 && good; side++)
-            while (ld_acquire_sys(A.recv_flag[mu][side]) < A.seq)
-                if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { good = 0; *A.err = 1; break; }
+        for (int m = 0; m < 4 && good; m++) {
+            if (!A.g.part[m]) continue;
+            for (int side = 0; side < 2 && good; side++)
+                while (ld_acquire_sys(A.recv_flag[m][side]) < A.seq)
+                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { good = 0; *A.err = 1; break; }
+        }
         ok = good;
     }
     __syncthreads();
-    if (!ok) return;
-    const int d[4] = {A.g.X, A.g.Y, A.g.Z, A.g.T};
-    const int F = A.g.V / d[mu];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * F) return;
-    const int side = i / F, f = i % F;
-    int x, y, z, t;
-    const int s = face_site(A.g, mu, f, side ? d[mu] - 1 : 0, x, y, z, t);
-    if (A.kind == LQCD_WILSON) {
-        switch (mu) {
-        case 0: wilson_ext_site<0>(A, side, f, s); break;
-        case 1: wilson_ext_site<1>(A, side, f, s); break;
-        case 2: wilson_ext_site<2>(A, side, f, s); break;
-        default: wilson_ext_site<3>(A, side, f, s); break;
-        }
-    } else {
-        switch (mu) {
-        case 0: stag_ext_site<0>(A, side, f, s, x, y, z); break;
-        case 1: stag_ext_site<1>(A, side, f, s, x, y, z); break;
-        case 2: stag_ext_site<2>(A, side, f, s, x, y, z); break;
-        default: stag_ext_site<3>(A, side, f, s, x, y, z); break;
+    double red[3] = {0.0, 0.0, 0.0};
+    if (ok && i < A.nbsites) {
+        const int s = A.bsites[i];
+        int r = s;
+        const int x = r % A.g.X; r /= A.g.X;
+        const int y = r % A.g.Y; r /= A.g.Y;
+        const int z = r % A.g.Z;
+        const int t = r / A.g.Z;
+        if (A.kind == LQCD_WILSON) {
+            cplx acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = cmake(0, 0);
+            EXT_DIR_W(0, x, A.g.X) EXT_DIR_W(1, y, A.g.Y) EXT_DIR_W(2, z, A.g.Z) EXT_DIR_W(3, t, A.g.T)
+            const size_t base = (size_t)(s >> 5) * (12 * 32) + (s & 31);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                cplx v = A.out[base + k * 32];
+                v.x = fma(A.coef, acc[k].x, v.x); v.y = fma(A.coef, acc[k].y, v.y);
+                A.out[base + k * 32] = v;
+                if (A.fuse.dot_with) {
+                    cplx w = ldg128(A.fuse.dot_with + base + k * 32);
+                    red[0] = fma(w.x, v.x, red[0]); red[0] = fma(w.y, v.y, red[0]);
+                    red[1] = fma(w.x, v.y, red[1]); red[1] = fma(-w.y, v.x, red[1]);
+                }
+                red[2] = fma(v.x, v.x, red[2]); red[2] = fma(v.y, v.y, red[2]);
+            }
+        } else {
+            cplx acc[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[k] = cmake(0, 0);
+            const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
+            EXT_DIR_S(0, x, A.g.X, 1.0)
+            EXT_DIR_S(1, y, A.g.Y, ((gx & 1) ? -1.0 : 1.0))
+            EXT_DIR_S(2, z, A.g.Z, (((gx + gy) & 1) ? -1.0 : 1.0))
+            EXT_DIR_S(3, t, A.g.T, (((gx + gy + gz) & 1) ? -1.0 : 1.0))
+            const size_t base = (size_t)(s >> 5) * (3 * 32) + (s & 31);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                cplx v = A.out[base + k * 32];
+                v.x = fma(A.coef, acc[k].x, v.x); v.y = fma(A.coef, acc[k].y, v.y);
+                A.out[base + k * 32] = v;
+                if (A.fuse.dot_with) {
+                    cplx w = ldg128(A.fuse.dot_with + base + k * 32);
+                    red[0] = fma(w.x, v.x, red[0]); red[0] = fma(w.y, v.y, red[0]);
+                    red[1] = fma(w.x, v.y, red[1]); red[1] = fma(-w.y, v.x, red[1]);
+                }
+                red[2] = fma(v.x, v.x, red[2]); red[2] = fma(v.y, v.y, red[2]);
+            }
         }
     }
+    if (A.fuse.dot_with || A.fuse.want_norm)
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, A.part_offset, A.part_offset + gridDim.x, 1);
 }
-
-int blas_dot2_async(lqcd_ctx *ctx, const cplx *w, const cplx *y, size_t n, int finish, int use_state);   // blas.cu
 
 int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
     CommState *c = ctx->comm;
     if (!c || !c->connected) return lqcd_fail(ctx, LQCD_ERR_COMM, "multi-rank context is not connected (lqcd_comm_export / lqcd_comm_connect)");
     const Geom &g = ctx->g;
-    const int d[4] = {g.X, g.Y, g.Z, g.T};
     HaloArgs A;
     memset(&A, 0, sizeof A);
     A.in = x; A.out = y; A.gauge = ctx->gauge; A.g = g; A.kind = op->kind; A.dagger = dagger;
@@ -435,11 +489,13 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     A.ticket = (unsigned int *)(c->base + c->off_ticket);
     A.err = (int *)(c->base + c->off_err);
     A.st = ctx->red.st; A.use_state = fuse ? fuse->use_state : 0;
+    A.bsites = c->bsites; A.nbsites = c->nbsites;
+    A.red = ctx->red;
     int ncta = 0;
     for (int mu = 0; mu < 4; mu++) {
         A.bc[mu] = op->bc[mu];
         A.pfirst[mu] = ctx->pcoord[mu] == 0; A.plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
-        A.cta0[mu] = ncta;
+        A.cta0[mu] = ncta;      // number of CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
         if (!g.part[mu]) continue;
         ncta += (2 * c->face[mu] + 127) / 128;
         const int lo = c->nbr[mu][0], hi = c->nbr[mu][1];
@@ -453,31 +509,33 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
             A.recv_flag[mu][side] = (const unsigned long long *)(c->base + c->off_halo_flags) + (mu * 2 + side) * 2 + slot;
         }
     }
-    {   // cta0[mu] = number of CTAs of partitioned directions < mu (non-partitioned directions own zero CTAs)
-        int acc = 0;
-        for (int mu = 0; mu < 4; mu++) { A.cta0[mu] = acc; if (g.part[mu]) acc += (2 * c->face[mu] + 127) / 128; }
-        A.cta0[4] = acc;
+    A.cta0[4] = ncta;
+    // pack on the second stream (overlaps the interior kernel); it needs x, which earlier main-stream work produced
+    static int two_streams = -1;
+    if (two_streams < 0) { const char *e = getenv("LQCD_PACK_STREAM"); two_streams = (e && atoi(e) == 0) ? 0 : 1; }
+    cudaStream_t ps = two_streams ? ctx->stream2 : ctx->stream;
+    if (two_streams) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_int, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->ev_int, 0));
     }
-    halo_pack_kernel<<<ncta, 128, 0, ctx->stream>>>(A);
+    halo_pack_kernel<<<ncta, 128, 0, ps>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    // interior (all sites, off-rank hops masked), reductions deferred until the faces are complete
+    if (two_streams) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pack, ps));
+    // interior: all sites with off-rank hops masked; reductions over non-face sites deposited as partials
+    const bool want_red = fuse && (fuse->dot_with || fuse->want_norm);
     DslashFuse f2 = DslashFuse();
-    if (fuse) { f2 = *fuse; f2.dot_with = nullptr; f2.want_norm = 0; }
+    if (fuse) f2 = *fuse;
+    f2.interior_only = 1;
     if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
     else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
-    for (int mu = 0; mu < 4; mu++) {
-        if (!g.part[mu]) continue;
-        A.mu = mu;
-        halo_exterior_kernel<<<(2 * c->face[mu] + 127) / 128, 128, 0, ctx->stream>>>(A);
-        ctx->launches++;
-        CUDA_TRY(ctx, cudaGetLastError());
-    }
-    (void)d;
-    if (fuse && (fuse->dot_with || fuse->want_norm)) {
-        const size_t n = (size_t)g.nblk * ncomp_of(op->kind) * 32;
-        LQCD_TRY(blas_dot2_async(ctx, fuse->dot_with, y, n, fuse->finish, fuse->use_state));
-    }
+    // x must not be overwritten by later main-stream kernels before the pack has read it
+    if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
+    A.fuse = f2; A.fuse.interior_only = 0;
+    A.part_offset = want_red ? (unsigned int)((g.nblk + g.wpc - 1) / g.wpc) : 0u;
+    halo_exterior_kernel<<<(c->nbsites + 127) / 128, 128, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;
 }
 

@@ -202,6 +202,7 @@ struct DslashFuse {
     int use_state;             // kernels early-exit when st->done
     double shift;              // y += shift * x  (multi-shift base system: (DdagD + s) )
     const cplx *shift_src;     // field multiplied by `shift` (the input of the first hop of DdagD)
+    int interior_only;         // multi-GPU interior pass: reduce over non-boundary sites, deposit partials only
 };
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,

@@ -113,8 +113,14 @@ __device__ __forceinline__ void apply_finish(int op, const double *tot, SolverSt
 }
 
 // NR values per thread.  Must be called by ALL threads of ALL CTAs of the grid (no early return before it).
+// Split reductions (multi-GPU Dslash: interior kernel + exterior kernel contribute to ONE sum):
+//   part_offset  index of this grid's first partial in R.partials
+//   part_total   number of partials the finishing CTA sums (own grid + earlier kernels' partials)
+//   do_finish    0: only deposit the CTA partial (a later kernel finishes)
 template <int NR>
-__device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce &R, int finish) {
+__device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce &R, int finish,
+                                                   unsigned int part_offset = 0, unsigned int part_total = 0, int do_finish = 1) {
+    if (part_total == 0) part_total = gridDim.x;
     __shared__ double sm[NR][32];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -130,11 +136,14 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
         for (int j = 0; j < NR; j++) {
             double s = 0.0;
             for (int w = 0; w < nwarp; w++) s += sm[j][w];
-            R.partials[(size_t)blockIdx.x * LQCD_MAX_RED + j] = s;
+            R.partials[(size_t)(part_offset + blockIdx.x) * LQCD_MAX_RED + j] = s;
         }
-        __threadfence();
-        unsigned int t = atomicInc(R.ticket, gridDim.x - 1);
-        is_last = (t == gridDim.x - 1);
+        is_last = 0;
+        if (do_finish) {
+            __threadfence();
+            unsigned int t = atomicInc(R.ticket, gridDim.x - 1);
+            is_last = (t == gridDim.x - 1);
+        }
     }
     __syncthreads();
     if (!is_last) return;
@@ -142,7 +151,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
     double acc[NR];
 #pragma unroll
     for (int j = 0; j < NR; j++) acc[j] = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    for (unsigned int i = threadIdx.x; i < part_total; i += blockDim.x) {
 #pragma unroll
         for (int j = 0; j < NR; j++) acc[j] += __ldcg(&R.partials[(size_t)i * LQCD_MAX_RED + j]);
     }

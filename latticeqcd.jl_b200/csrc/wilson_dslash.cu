@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         const int s = blk * 32 + lane;
         int x, y, z, t;
         site_coords(A.g, s, x, y, z, t);
+        // multi-GPU interior pass: face sites are finished (and reduced) by the exterior kernel
+        const bool skip_red = A.fuse.interior_only &&
+            ((A.g.part[0] && (x == 0 || x == A.g.X - 1)) || (A.g.part[1] && (y == 0 || y == A.g.Y - 1)) ||
+             (A.g.part[2] && (z == 0 || z == A.g.Z - 1)) || (A.g.part[3] && (t == 0 || t == A.g.T - 1)));
         cplx acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
@@ -110,16 +114,16 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
                 cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
                 yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
             }
-            if (A.fuse.dot_with) {
+            if (A.fuse.dot_with && !skip_red) {
                 cplx w = ldg128(A.fuse.dot_with + base + k * 32);
                 red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
                 red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
             }
-            red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
+            if (!skip_red) { red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]); }
             A.out[base + k * 32] = yk;
         }
     }
-    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
+    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only);
 }
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,

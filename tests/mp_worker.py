@@ -48,7 +48,7 @@ def main():
     op = orc.make_op(dims, kappa=0.125, mass=0.2)
 
     def gather(f):
-        h = torch.from_numpy(f.to_host())
+        h = torch.from_numpy(f.to_host().view(np.float64))      # gloo has no complex dtypes
         out = [torch.empty_like(h) for _ in range(world)] if rank == 0 else None
         dist.gather(h, out, dst=0)
         if rank != 0:
@@ -58,9 +58,9 @@ def main():
             (ld, og, _, _) = q.decompose(dims, pg, r)
             s2 = (slice(og[3], og[3] + ld[3]), slice(og[2], og[2] + ld[2]), slice(og[1], og[1] + ld[1]), slice(og[0], og[0] + ld[0]))
             if kind == orc.WILSON:
-                full[(slice(None),) + s2] = out[r].numpy()
+                full[(slice(None),) + s2] = out[r].numpy().view(np.complex128)
             else:
-                full[s2] = out[r].numpy()
+                full[s2] = out[r].numpy().view(np.complex128)
         return full
 
     fails = []
