@@ -20,8 +20,10 @@
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "wilson_spin.cuh"
+#include "site_map.cuh"
 #include <unistd.h>
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -52,6 +54,8 @@ struct CommState {
     unsigned long long halo_seq;
     int *bsites;                      // device table of boundary sites (ascending site index)
     int nbsites;
+    int *cta_order;                   // Dslash CTA permutation: tiles without face sites first, face tiles last
+    int n_interior;
 };
 
 static int rank_of(const lqcd_ctx *ctx, const int pc[4]) {
@@ -103,6 +107,28 @@ static int comm_alloc(lqcd_ctx *ctx) {
         if (e == cudaSuccess) e = cudaMemcpy(c->bsites, bs.data(), sizeof(int) * bs.size(), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "boundary table -> %s", cudaGetErrorString(e)); }
     }
+    {   // CTA order for the fused-halo Dslash kernels
+        const int ncta = (g.nblk + g.wpc - 1) / g.wpc;
+        std::vector<int> inner, face;
+        for (int cta = 0; cta < ncta; cta++) {
+            bool b = false;
+            for (int w = 0; w < g.wpc && !b; w++) {
+                const int blk = block_of_warp(g, cta, w);
+                if (blk >= g.nblk) continue;
+                for (int l = 0; l < 32 && !b; l++) {
+                    int r = blk * 32 + l, cc[4];
+                    for (int i = 0; i < 4; i++) { cc[i] = r % d[i]; r /= d[i]; }
+                    for (int i = 0; i < 4; i++) if (g.part[i] && (cc[i] == 0 || cc[i] == d[i] - 1)) b = true;
+                }
+            }
+            (b ? face : inner).push_back(cta);
+        }
+        c->n_interior = (int)inner.size();
+        inner.insert(inner.end(), face.begin(), face.end());
+        e = cudaMalloc(&c->cta_order, sizeof(int) * (inner.size() + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(c->cta_order, inner.data(), sizeof(int) * inner.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(c->base); cudaFree(c->bsites); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cta order table -> %s", cudaGetErrorString(e)); }
+    }
     c->peer[ctx->rank] = c->base;
     ctx->comm = c;
     return LQCD_OK;
@@ -115,6 +141,7 @@ int comm_destroy(lqcd_ctx *ctx) {
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
     cudaFree(c->base);
     cudaFree(c->bsites);
+    cudaFree(c->cta_order);
     delete c;
     ctx->comm = nullptr;
     return LQCD_OK;
@@ -312,26 +339,20 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const HaloArgs A) {
             }
         }
     }
-    // publish: every CTA fences its peer stores, the last CTA raises the flags at the neighbours
-    __threadfence_system();
+    // publish: bar.sync orders the CTA's peer stores before thread 0's system-scope fence (cumulative), then the
+    // ticket; the last CTA to arrive raises the sequence flags at the neighbours.
     __syncthreads();
     __shared__ int last;
-    if (threadIdx.x == 0) last = (atomicInc(A.ticket, gridDim.x - 1) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = (atomicInc(A.ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
     __syncthreads();
     if (last && threadIdx.x < 8) {
         const int m = threadIdx.x >> 1, side = threadIdx.x & 1;
         __threadfence_system();
         if (A.g.part[m]) st_release_sys(A.send_flag[m][side], A.seq);
     }
-}
-
-// face index of a site for direction MU: lexicographic over the other three coordinates (matches face_site()).
-template <int MU>
-__device__ __forceinline__ int face_index(const Geom &g, int x, int y, int z, int t) {
-    if (MU == 0) return y + g.Y * (z + g.Z * t);
-    if (MU == 1) return x + g.X * (z + g.Z * t);
-    if (MU == 2) return x + g.X * (y + g.Y * t);
-    return x + g.X * (y + g.Y * z);
 }
 
 // Wilson: add the off-rank hop(s) of direction MU at face site s into acc (12 complex, in units of "hopping sum").
@@ -511,8 +532,16 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     }
     A.cta0[4] = ncta;
     // pack on the second stream (overlaps the interior kernel); it needs x, which earlier main-stream work produced
-    static int two_streams = -1;
+    static int two_streams = -1, timing = -1;
+    static cudaEvent_t te[4];
+    static double tacc[3] = {0, 0, 0};
+    static long tcount = 0;
     if (two_streams < 0) { const char *e = getenv("LQCD_PACK_STREAM"); two_streams = (e && atoi(e) == 0) ? 0 : 1; }
+    if (timing < 0) {
+        const char *e = getenv("LQCD_COMM_TIMING"); timing = (e && atoi(e) == 1) ? 1 : 0;
+        if (timing) { two_streams = 0; for (int i = 0; i < 4; i++) cudaEventCreate(&te[i]); }
+    }
+    if (timing) cudaEventRecord(te[0], ctx->stream);
     cudaStream_t ps = two_streams ? ctx->stream2 : ctx->stream;
     if (two_streams) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_int, ctx->stream));
@@ -522,6 +551,32 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     if (two_streams) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pack, ps));
+    if (timing) cudaEventRecord(te[1], ctx->stream);
+    static int fused = -1;
+    if (fused < 0) { const char *e = getenv("LQCD_FUSED_HALO"); fused = (e && atoi(e) == 0) ? 0 : 1; }
+    if (fused) {
+        // ONE kernel on the critical path: the Dslash kernel itself consumes the halo slots (face tiles run last and
+        // wait on the neighbours' flags in-kernel); reductions finish there as on a single GPU.
+        HaloIn H;
+        memset(&H, 0, sizeof H);
+        for (int mu = 0; mu < 4; mu++) {
+            H.pfirst[mu] = A.pfirst[mu]; H.plast[mu] = A.plast[mu];
+            for (int side = 0; side < 2; side++) { H.recv[mu][side] = A.recv[mu][side]; H.recv_flag[mu][side] = A.recv_flag[mu][side]; }
+        }
+        H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
+        if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
+        else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
+        if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
+        if (timing) {
+            cudaEventRecord(te[2], ctx->stream);
+            cudaEventSynchronize(te[2]);
+            for (int i = 0; i < 2; i++) { float ms; cudaEventElapsedTime(&ms, te[i], te[i + 1]); tacc[i] += ms; }
+            if (++tcount % 64 == 0)
+                fprintf(stderr, "[lqcd comm timing rank %d] pack %.1f us  fused dslash %.1f us (mean of %ld)\n",
+                        ctx->rank, 1e3 * tacc[0] / tcount, 1e3 * tacc[1] / tcount, tcount);
+        }
+        return LQCD_OK;
+    }
     // interior: all sites with off-rank hops masked; reductions over non-face sites deposited as partials
     const bool want_red = fuse && (fuse->dot_with || fuse->want_norm);
     DslashFuse f2 = DslashFuse();
@@ -529,6 +584,7 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     f2.interior_only = 1;
     if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
     else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
+    if (timing) cudaEventRecord(te[2], ctx->stream);
     // x must not be overwritten by later main-stream kernels before the pack has read it
     if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
     A.fuse = f2; A.fuse.interior_only = 0;
@@ -536,6 +592,14 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     halo_exterior_kernel<<<(c->nbsites + 127) / 128, 128, 0, ctx->stream>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (timing) {       // development aid: serialises the host; prints the mean split every 64 applications
+        cudaEventRecord(te[3], ctx->stream);
+        cudaEventSynchronize(te[3]);
+        for (int i = 0; i < 3; i++) { float ms; cudaEventElapsedTime(&ms, te[i], te[i + 1]); tacc[i] += ms; }
+        if (++tcount % 64 == 0)
+            fprintf(stderr, "[lqcd comm timing rank %d] pack %.1f us  interior %.1f us  exterior %.1f us (mean of %ld)\n",
+                    ctx->rank, 1e3 * tacc[0] / tcount, 1e3 * tacc[1] / tcount, 1e3 * tacc[2] / tcount, tcount);
+    }
     return LQCD_OK;
 }
 

@@ -205,10 +205,23 @@ struct DslashFuse {
     int interior_only;         // multi-GPU interior pass: reduce over non-boundary sites, deposit partials only
 };
 
+// multi-GPU: halo data consumed INSIDE the Dslash kernel (fused exterior).  CTAs are permuted so that tiles
+// without face sites run first and face tiles last; a face CTA spins (ld.acquire.sys + timeout) on the
+// neighbours' sequence flags, which by then have normally been raised by the neighbours' pack kernels.
+struct HaloIn {
+    const cplx *recv[4][2];                     // [mu][0: from lower nbr (my low face), 1: from upper nbr (my high face)]
+    const unsigned long long *recv_flag[4][2];
+    unsigned long long seq;
+    int *err;
+    int pfirst[4], plast[4];                    // this rank touches the global low / high boundary in mu
+    const int *cta_order;
+    int n_interior;
+};
+
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                         const DslashFuse *fuse, cudaStream_t s);
+                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                            const DslashFuse *fuse, cudaStream_t s);
+                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr);
 int apply_op(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
              lqcd_fermion *tmp, const DslashFuse *fuse_last);
 

@@ -7,7 +7,7 @@
 #pragma once
 #include "lqcd_internal.cuh"
 
-__device__ __forceinline__ int block_of_warp(const Geom &g, int cta, int warp) {
+__host__ __device__ __forceinline__ int block_of_warp(const Geom &g, int cta, int warp) {
     if (!g.regular) return cta * g.wpc + warp;
     int t0 = cta % g.nt[0]; cta /= g.nt[0];
     int t1 = cta % g.nt[1]; cta /= g.nt[1];
@@ -26,4 +26,28 @@ __device__ __forceinline__ void site_coords(const Geom &g, int s, int &x, int &y
     y = s % g.Y; s /= g.Y;
     z = s % g.Z;
     t = s / g.Z;
+}
+
+// face index of a site for direction MU: lexicographic over the other three coordinates.
+template <int MU>
+__host__ __device__ __forceinline__ int face_index(const Geom &g, int x, int y, int z, int t) {
+    if (MU == 0) return y + g.Y * (z + g.Z * t);
+    if (MU == 1) return x + g.X * (z + g.Z * t);
+    if (MU == 2) return x + g.X * (y + g.Y * t);
+    return x + g.X * (y + g.Y * z);
+}
+
+// face CTAs wait here for all neighbours' halo flags of this application (thread 0 spins, then bar.sync)
+__device__ __forceinline__ void wait_halo_flags(const Geom &g, const HaloIn &H) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        bool good = true;
+        for (int m = 0; m < 4 && good; m++) {
+            if (!g.part[m]) continue;
+            for (int side = 0; side < 2 && good; side++)
+                while (ld_acquire_sys(H.recv_flag[m][side]) < H.seq)
+                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { good = false; *H.err = 1; break; }
+        }
+    }
+    __syncthreads();
 }

@@ -12,6 +12,7 @@
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"
+#include <cstring>
 
 struct StagArgs {
     cplx *out;
@@ -23,6 +24,7 @@ struct StagArgs {
     double bc[4];
     DslashFuse fuse;
     Reduce red;
+    HaloIn halo;      // MULTI kernel only
 };
 
 template <int MU, int FWD>
@@ -43,26 +45,59 @@ __device__ __forceinline__ void shop(cplx (&acc)[3], const cplx *__restrict__ in
     }
 }
 
-template <int MU>
-__device__ __forceinline__ void shop_pair(cplx (&acc)[3], const StagArgs &A, int s, int coord, int dim, int stride, double eta) {
+// off-rank hop (multi-GPU): forward: chi(n+mu) arrives raw, U_mu(n) applied here; backward: U^dag chi(n-mu) arrives complete
+template <int MU, int FWD>
+__device__ __forceinline__ void halo_shop(cplx (&acc)[3], const StagArgs &A, int s, int f, double eta) {
+    const cplx *src = A.halo.recv[MU][FWD] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
+    cplx h[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) h[c] = __ldcg(src + c * 32);
+    if (FWD) {
+        const double cf = 0.5 * eta * (A.halo.plast[MU] ? A.bc[MU] : 1.0);
+        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cplx g = cmake(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < 3; b++) cfma(g, ldg128(lk + (a * 3 + b) * 32), h[b]);
+            acc[a].x = fma(cf, g.x, acc[a].x); acc[a].y = fma(cf, g.y, acc[a].y);
+        }
+    } else {
+        const double cf = -0.5 * eta * (A.halo.pfirst[MU] ? A.bc[MU] : 1.0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { acc[c].x = fma(cf, h[c].x, acc[c].x); acc[c].y = fma(cf, h[c].y, acc[c].y); }
+    }
+}
+
+template <int MU, int MULTI>
+__device__ __forceinline__ void shop_pair(cplx (&acc)[3], const StagArgs &A, int s, int coord, int dim, int stride, double eta,
+                                          int x, int y, int z, int t) {
     {
         bool w = (coord == dim - 1);
         int ns = w ? s - (dim - 1) * stride : s + stride;
         double coef = 0.5 * eta * (w ? A.bc[MU] : 1.0);
         if (!(w && A.g.part[MU])) shop<MU, 1>(acc, A.in, A.gauge, ns, s, coef);
+        else if (MULTI) halo_shop<MU, 1>(acc, A, s, face_index<MU>(A.g, x, y, z, t), eta);
     }
     {
         bool w = (coord == 0);
         int ns = w ? s + (dim - 1) * stride : s - stride;
         double coef = -0.5 * eta * (w ? A.bc[MU] : 1.0);
         if (!(w && A.g.part[MU])) shop<MU, 0>(acc, A.in, A.gauge, ns, ns, coef);
+        else if (MULTI) halo_shop<MU, 0>(acc, A, s, face_index<MU>(A.g, x, y, z, t), eta);
     }
 }
 
+template <int MULTI>
 __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int blk = block_of_warp(A.g, blockIdx.x, warp);
+    int cta = blockIdx.x;
+    if (MULTI) {
+        cta = A.halo.cta_order[blockIdx.x];
+        if ((int)blockIdx.x >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
+    }
+    const int blk = block_of_warp(A.g, cta, warp);
     const bool active = blk < A.g.nblk;
     double red[3] = {0.0, 0.0, 0.0};
     if (active) {
@@ -77,10 +112,10 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
         cplx acc[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) acc[k] = cmake(0.0, 0.0);
-        shop_pair<0>(acc, A, s, x, A.g.X, 1, 1.0);
-        shop_pair<1>(acc, A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0);
-        shop_pair<2>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0);
-        shop_pair<3>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0);
+        shop_pair<0, MULTI>(acc, A, s, x, A.g.X, 1, 1.0, x, y, z, t);
+        shop_pair<1, MULTI>(acc, A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0, x, y, z, t);
+        shop_pair<2, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, x, y, z, t);
+        shop_pair<3, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, x, y, z, t);
         const size_t base = (size_t)blk * (3 * 32) + lane;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -103,16 +138,18 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
 }
 
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                            const DslashFuse *fuse, cudaStream_t s) {
+                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo) {
     if (x == y) return lqcd_fail(ctx, LQCD_ERR_ARG, "dslash: in-place application is not allowed");
     StagArgs A;
     A.out = y; A.in = x; A.gauge = ctx->gauge; A.g = ctx->g; A.mass = op->mass; A.sign = dagger ? -1.0 : 1.0;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     if (fuse) A.fuse = *fuse; else A.fuse = DslashFuse();
     A.red = ctx->red;
+    if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
     const int bs = 32 * ctx->g.wpc;
     const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
-    staggered_dslash_kernel<<<grid, bs, 0, s>>>(A);
+    if (halo) staggered_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
+    else      staggered_dslash_kernel<0><<<grid, bs, 0, s>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;

@@ -18,6 +18,7 @@
 #include "wilson_spin.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 struct WilsonArgs {
     cplx *out;
@@ -28,7 +29,7 @@ struct WilsonArgs {
     double bc[4];
     DslashFuse fuse;
     Reduce red;
-    int it;          // unused here (kept for symmetry with blas kernels)
+    HaloIn halo;     // MULTI kernels only
 };
 
 // one of the eight hops.  FWD=1: U_mu(n) x(n+mu) with link at `ls` = n;  FWD=0: U_mu^dag(n-mu) x(n-mu), ls = n-mu.
@@ -66,27 +67,67 @@ __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in
     }
 }
 
-template <int MU, int DAG>
-__device__ __forceinline__ void hop_pair(cplx (&acc)[12], const WilsonArgs &A, int s, int coord, int dim, int stride) {
+// off-rank hops (multi-GPU): the neighbour's pack kernel already delivered the spin-projected half spinor
+// (forward hop: P psi(n+mu), U_mu(n) is applied here; backward hop: U^dag P psi(n-mu), complete) into our halo slot.
+template <int MU, int FWD, int DAG>
+__device__ __forceinline__ void halo_hop(cplx (&acc)[12], const WilsonArgs &A, int s, int f) {
+    constexpr int S = (FWD ^ DAG) ? -1 : +1;
+    const cplx *src = A.halo.recv[MU][FWD] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
+    cplx h0[3], h1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { h0[c] = __ldcg(src + c * 32); h1[c] = __ldcg(src + (3 + c) * 32); }
+    const double phase = FWD ? (A.halo.plast[MU] ? A.bc[MU] : 1.0) : (A.halo.pfirst[MU] ? A.bc[MU] : 1.0);
+    if (phase != 1.0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
+    if (FWD) {
+        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                cplx u = ldg128(lk + (a * 3 + b) * 32);
+                cfma(g0, u, h0[b]); cfma(g1, u, h1[b]);
+            }
+            reconstruct<MU, S>(acc, a, g0, g1);
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++) reconstruct<MU, S>(acc, a, h0[a], h1[a]);
+    }
+}
+
+template <int MU, int DAG, int MULTI>
+__device__ __forceinline__ void hop_pair(cplx (&acc)[12], const WilsonArgs &A, int s, int coord, int dim, int stride,
+                                         int x, int y, int z, int t) {
     // forward
     {
         bool w = (coord == dim - 1);
         int ns = w ? s - (dim - 1) * stride : s + stride;
         if (!(w && A.g.part[MU])) hop<MU, 1, DAG>(acc, A.in, A.gauge, ns, s, w, A.bc[MU]);
+        else if (MULTI) halo_hop<MU, 1, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
     // backward
     {
         bool w = (coord == 0);
         int ns = w ? s + (dim - 1) * stride : s - stride;
         if (!(w && A.g.part[MU])) hop<MU, 0, DAG>(acc, A.in, A.gauge, ns, ns, w, A.bc[MU]);
+        else if (MULTI) halo_hop<MU, 0, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
 }
 
-template <int DAG, int MAXT, int MINB>
+template <int DAG, int MAXT, int MINB, int MULTI>
 __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int blk = block_of_warp(A.g, blockIdx.x, warp);
+    int cta = blockIdx.x;
+    if (MULTI) {
+        cta = A.halo.cta_order[blockIdx.x];
+        if ((int)blockIdx.x >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
+    }
+    const int blk = block_of_warp(A.g, cta, warp);
     const bool active = blk < A.g.nblk;
     double red[3] = {0.0, 0.0, 0.0};
     if (active) {
@@ -100,10 +141,10 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         cplx acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
-        hop_pair<0, DAG>(acc, A, s, x, A.g.X, 1);
-        hop_pair<1, DAG>(acc, A, s, y, A.g.Y, A.g.X);
-        hop_pair<2, DAG>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y);
-        hop_pair<3, DAG>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z);
+        hop_pair<0, DAG, MULTI>(acc, A, s, x, A.g.X, 1, x, y, z, t);
+        hop_pair<1, DAG, MULTI>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
+        hop_pair<2, DAG, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
+        hop_pair<3, DAG, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
         const size_t base = (size_t)blk * (12 * 32) + lane;
         const double mk = -A.kappa;
 #pragma unroll
@@ -127,7 +168,7 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
 }
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                         const DslashFuse *fuse, cudaStream_t s) {
+                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo) {
     if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
     if (op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "clover term not built (csw = %g)", op->csw);
     if (x == y) return lqcd_fail(ctx, LQCD_ERR_ARG, "dslash: in-place application is not allowed");
@@ -135,7 +176,8 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     A.out = y; A.in = x; A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     if (fuse) A.fuse = *fuse; else { A.fuse = DslashFuse(); }
-    A.red = ctx->red; A.it = 0;
+    A.red = ctx->red;
+    if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
     const int bs = 32 * ctx->g.wpc;
     const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
     // register budget variants (tuning knob LQCD_LB = "maxthreads,minblocks"; default picked by measurement)
@@ -149,8 +191,13 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     }
 #define WL(MT, MB)                                                                   \
     do {                                                                             \
-        if (dagger) wilson_dslash_kernel<1, MT, MB><<<grid, bs, 0, s>>>(A);          \
-        else        wilson_dslash_kernel<0, MT, MB><<<grid, bs, 0, s>>>(A);          \
+        if (halo) {                                                                  \
+            if (dagger) wilson_dslash_kernel<1, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
+            else        wilson_dslash_kernel<0, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
+        } else {                                                                     \
+            if (dagger) wilson_dslash_kernel<1, MT, MB, 0><<<grid, bs, 0, s>>>(A);   \
+            else        wilson_dslash_kernel<0, MT, MB, 0><<<grid, bs, 0, s>>>(A);   \
+        }                                                                            \
     } while (0)
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
