@@ -193,6 +193,7 @@ def run_b200(args, dims):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.excepthook = lambda t, v, tb: (sys.__excepthook__(t, v, tb), sys.stderr.flush(), os._exit(1))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)

@@ -103,7 +103,13 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     if (prop.major != 10) { delete ctx; return lqcd_fail(nullptr, LQCD_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
     ctx->num_sms = prop.multiProcessorCount;
     CT(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CT(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {   // stream2 carries the halo pack kernels: highest priority so that its CTAs are dispatched before the
+        // Dslash kernel's remaining tiles (the face tiles of the Dslash kernel wait for the NEIGHBOUR's pack;
+        // if the local pack were starved behind them two GPUs could wait for each other).
+        int lo = 0, hi = 0;
+        CT(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CT(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+    }
     CT(cudaEventCreate(&ctx->ev0)); CT(cudaEventCreate(&ctx->ev1));
     CT(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
     CT(cudaEventCreateWithFlags(&ctx->ev_int, cudaEventDisableTiming));
