@@ -274,22 +274,32 @@ extern "C" int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int
     return LQCD_OK;
 }
 
-extern "C" int lqcd_gauge_download(lqcd_ctx *ctx, double *const U_mu[4], int nc, int ndw) {
-    if (!ctx || !U_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
-    if (nc != 3) return lqcd_fail(ctx, LQCD_ERR_ARG, "only NC = 3");
-    if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "no gauge field on the device");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+// device link-layout field -> the four host arrays (Julia layout, wing ndw)
+static int links_to_host(lqcd_ctx *ctx, const cplx *dev, double *const U_mu[4], int ndw) {
     const size_t Vh = host_volume(ctx->g, ndw), per = Vh * 9 * sizeof(cplx);
     LQCD_TRY(ensure_stage(ctx, per * 4));
     if (ndw > 0) CUDA_TRY(ctx, cudaMemsetAsync(ctx->stage, 0, per * 4, ctx->stream));
     int warps = ctx->g.nblk * 4, bs = 256, grid = (warps * 32 + bs - 1) / bs;
-    convert_links_kernel<0><<<grid, bs, 0, ctx->stream>>>(ctx->gauge, (cplx *)ctx->stage, ctx->g, ndw, Vh * 9);
+    convert_links_kernel<0><<<grid, bs, 0, ctx->stream>>>(const_cast<cplx *>(dev), (cplx *)ctx->stage, ctx->g, ndw, Vh * 9);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    for (int mu = 0; mu < 4; mu++)
+    for (int mu = 0; mu < 4; mu++) {
+        if (!U_mu[mu]) return lqcd_fail(ctx, LQCD_ERR_ARG, "output array %d is null", mu);
         CUDA_TRY(ctx, cudaMemcpyAsync(U_mu[mu], (char *)ctx->stage + mu * per, per, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LQCD_OK;
+}
+
+int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4]) { return links_to_host(ctx, dev_links, U_mu, 0); }
+
+extern "C" int lqcd_gauge_download(lqcd_ctx *ctx, double *const U_mu[4], int nc, int ndw) {
+    if (!ctx || !U_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (nc != 3) return lqcd_fail(ctx, LQCD_ERR_ARG, "only NC = 3");
+    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
+    if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "no gauge field on the device");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return links_to_host(ctx, ctx->gauge, U_mu, ndw);
 }
 
 // ---- fermion fields ----------------------------------------------------------------------------------

@@ -302,3 +302,43 @@ def test_16_4_size_independent_properties():
     q.add_(chk, -1.0, b)
     assert q.dot(chk, chk).real < 1e-17
     assert 5 < info["iters"] < 3000
+
+
+@pytest.mark.parametrize("kind", ["Wilson", "staggered"])
+def test_fermion_force_matches_oracle(Uw, Us, kind):
+    """calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129): device CG + outer products vs the oracle
+    (whose force is itself pinned by finite differences of S_f in tests/test_oracle.py)."""
+    dims = (4, 4, 4, 4)
+    Uh = Uw if kind == "Wilson" else Us
+    k = orc.WILSON if kind == "Wilson" else orc.STAGGERED
+    U = q.gaugefields_from_array(Uh)
+    x = q.Initialize_pseudofermion_fields(U[0], kind)
+    D = q.Dirac_operator(U, x, wparams(0.12, eps_CG=1e-24) if kind == "Wilson" else sparams(0.5, eps_CG=1e-24))
+    fa = q.FermiAction(D, {"Nf": 2})
+    eta = q.similar(x)
+    phi = orc.gaussian_field(dims, k, seed=41)
+    eta.from_host(phi)
+    F = np.zeros_like(Uh)
+    info = q.calc_UdSfdU_(F, fa, U, eta)
+    op = orc.make_op(dims, kappa=0.12, mass=0.5)
+    ref = orc.cg(op, k, Uh, phi, eps=1e-24)
+    Y = orc.apply(op, k, orc.D, Uh, ref["x"])
+    Fref = orc.force(op, k, Uh, ref["x"], Y)
+    assert info["iters"] == ref["iters"]
+    assert relerr(F, Fref) < 1e-10
+    assert abs(info["action"] - np.vdot(phi, ref["x"]).real) < 1e-9 * abs(info["action"])
+
+
+def test_pseudofermion_heatbath_identity(Uw):
+    """standardMD.jl:95-96 + standardHMC.jl:54,69: eta = D^dag xi  =>  S_f = eta^dag (D^dag D)^-1 eta = xi^dag xi."""
+    U = q.gaugefields_from_array(Uw)
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, wparams(0.125))
+    fa = q.FermiAction(D, {})
+    xi, eta = q.similar(x), q.similar(x)
+    q.gauss_sampling_in_action_(xi, U, fa, seed=7)
+    q.sample_pseudofermions_(eta, U, fa, xi)
+    Sold = q.dot(xi, xi).real
+    Snew = q.evaluate_FermiAction(fa, U, eta)
+    assert abs(Sold - Snew) < 1e-8 * Sold
+    assert abs(Sold - 12 * 256) < 0.1 * 12 * 256          # <xi^dag xi> = number of complex components
