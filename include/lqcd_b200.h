@@ -125,9 +125,10 @@ int lqcd_multishift_cg(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[
 
 /* ---- fermion force: calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129) ---------------
  * Given eta: X = (DdagD)^-1 eta by CG, Y = D X, then the 4 link-shaped outer-product fields are written
- * to the host arrays out_mu (same layout as links, ndw = 0).  x_inout (nullable) is X (initial guess / result). */
+ * to the host arrays out_mu (same layout as the links, wing width ndw; the halo is zero-filled).
+ * x_inout (nullable) is X (initial guess / result). */
 int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
-                       double eps, int maxsteps, double *const out_mu[4], int *iters, double *action);
+                       double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action);
 
 /* ---- multi-GPU plumbing (one process per GPU; handles are exchanged by the host: MPI.jl Allgather in
  *      Julia, torch.distributed.all_gather in the Python mirror) ---------------------------------- */

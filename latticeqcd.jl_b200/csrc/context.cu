@@ -291,7 +291,7 @@ static int links_to_host(lqcd_ctx *ctx, const cplx *dev, double *const U_mu[4], 
     return LQCD_OK;
 }
 
-int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4]) { return links_to_host(ctx, dev_links, U_mu, 0); }
+int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw) { return links_to_host(ctx, dev_links, U_mu, ndw); }
 
 extern "C" int lqcd_gauge_download(lqcd_ctx *ctx, double *const U_mu[4], int nc, int ndw) {
     if (!ctx || !U_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");

@@ -136,11 +136,12 @@ __global__ void __launch_bounds__(128) staggered_force_kernel(const ForceArgs A)
     stag_force_dir<3>(A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, Xn, Yn);
 }
 
-int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4]);     // context.cu
+int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);     // context.cu
 
 extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
-                                  double eps, int maxsteps, double *const out_mu[4], int *iters, double *action) {
+                                  double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action) {
     if (!ctx || !op || !eta || !out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
     if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "lqcd_fermion_force: single-rank only in this round");
     if (eta->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "fermion kind does not match the operator");
     if (op->kind == LQCD_WILSON && op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force implements r = 1 only");
@@ -175,7 +176,7 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
     cudaError_t e = cudaGetLastError();
     int rc = LQCD_OK;
     if (e != cudaSuccess) rc = lqcd_fail(ctx, LQCD_ERR_CUDA, "force kernel -> %s", cudaGetErrorString(e));
-    if (rc == LQCD_OK) rc = download_links_from(ctx, fbuf, out_mu);
+    if (rc == LQCD_OK) rc = download_links_from(ctx, fbuf, out_mu, ndw);
     cudaFree(fbuf);
     return rc;
 }

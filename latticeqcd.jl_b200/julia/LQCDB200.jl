@@ -1,0 +1,198 @@
+# LQCDB200.jl -- Julia-side shim that puts liblqcd_b200.so (include/lqcd_b200.h) behind the generic functions
+# LatticeQCD.jl calls on its Dirac-solve hot path.  Thin by design: every method is a `ccall` into the C ABI.
+#
+# STATUS: written against the reference's call sites; NOT executed in the build image (no Julia runtime, and
+# LatticeDiracOperators.jl / Gaugefields.jl sources are not vendored -- SURVEY.md section 0).  The Python twin
+# (latticeqcd.jl_b200/lqcd_b200/) binds the same symbols with the same argument order and is what the tests
+# and bench.py exercise.  Upstream type names marked [UPSTREAM-RECALL] must be checked against the installed
+# package versions (LatticeDiracOperators 0.6.x, Gaugefields 0.4-0.7; /root/reference/Project.toml:24,27).
+#
+# Selection (SURVEY.md 8b, option 1 -- run_LQCD() stays unchanged): with ENV["LQCD_B200"] = "1" the method
+#     Dirac_operator(U::Vector{<:AbstractGaugefields{3,4}}, x, params)           (src/system/universe.jl:137)
+# returns a B200Dirac instead of upstream's CPU operator.  Link fields and pseudofermion fields remain the
+# upstream CPU containers (the gauge sector keeps using them, src/md/AbstractMD.jl:78-118); links are mirrored
+# to the device when the operator is built or re-bound (`D(U)`), fermion fields are copied in/out per call
+# (a solve is hundreds of Dslash applications, the copies are noise).
+module LQCDB200
+
+using LinearAlgebra
+import LinearAlgebra: mul!, dot
+import Gaugefields: AbstractGaugefields                                   # [UPSTREAM-RECALL]
+import LatticeDiracOperators                                               # [UPSTREAM-RECALL]
+import LatticeDiracOperators: Dirac_operator, solve_DinvX!, FermiAction, calc_UdSfdU!, evaluate_FermiAction,
+                              gauss_sampling_in_action!, sample_pseudofermions!, AbstractFermionfields
+
+const LIB = get(ENV, "LQCD_B200_LIB", joinpath(@__DIR__, "..", "liblqcd_b200.so"))
+
+const WILSON, STAGGERED = Cint(0), Cint(1)
+const OP_D, OP_DDAG, OP_DDAGD = Cint(0), Cint(1), Cint(2)
+const SOLVER_CG, SOLVER_CGNR, SOLVER_BICGSTAB = Cint(0), Cint(1), Cint(2)
+
+# typedef struct { int kind; double kappa, r, mass, csw; double bc[4]; } lqcd_op;      (include/lqcd_b200.h)
+struct LqcdOp
+    kind::Cint
+    kappa::Cdouble
+    r::Cdouble
+    mass::Cdouble
+    csw::Cdouble
+    bc::NTuple{4,Cdouble}
+end
+
+# ---- errors: the reference's convention is error(...) (universe.jl:73-75,130) ------------------------------
+function check(ctx::Ptr{Cvoid}, st::Cint)
+    st == 0 && return nothing
+    msg = unsafe_string(ccall((:lqcd_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+    error("liblqcd_b200 error $st: $msg")          # LQCD_ERR_NOCONV (4) mirrors upstream's "The CG is not converged!"
+end
+
+# ---- context: one per process / GPU ---------------------------------------------------------------------------
+mutable struct B200Context
+    h::Ptr{Cvoid}
+    dims::NTuple{4,Int}
+    function B200Context(dims::NTuple{4,Int}; procgrid=(1, 1, 1, 1), rank=0, device=0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        d = Cint[dims...]; p = Cint[procgrid...]
+        st = ccall((:lqcd_ctx_create, LIB), Cint, (Ptr{Cint}, Ptr{Cint}, Cint, Cint, Ref{Ptr{Cvoid}}), d, p, rank, device, out)
+        check(C_NULL, st)
+        ctx = new(out[], dims)
+        finalizer(c -> ccall((:lqcd_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+const CONTEXTS = Dict{NTuple{4,Int},B200Context}()
+context(dims) = get!(() -> B200Context(dims), CONTEXTS, dims)
+
+# ---- device pseudofermion handle ------------------------------------------------------------------------------
+mutable struct B200Field
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    kind::Cint
+    function B200Field(ctx::B200Context, kind::Cint)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx.h, ccall((:lqcd_fermion_alloc, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), ctx.h, kind, out))
+        f = new(ctx, out[], kind)
+        finalizer(x -> ccall((:lqcd_fermion_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.h), f)
+        return f
+    end
+end
+
+# Upstream CPU fields keep their data in `.f` (Wilson nowing: ComplexF64[NC,NX,NY,NZ,NT,4]; staggered with wing:
+# [NC,NX+2,NY+2,NZ+2,NT+2,1]) [UPSTREAM-RECALL]; `wing(x)` is the halo width the library must strip / restore.
+wing(x) = hasproperty(x, :NDW) ? Int(x.NDW) : 0
+function upload!(d::B200Field, x::AbstractFermionfields)
+    GC.@preserve x check(d.ctx.h, ccall((:lqcd_fermion_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Cint),
+                                        d.ctx.h, d.h, pointer(x.f), wing(x)))
+end
+function download!(x::AbstractFermionfields, d::B200Field)
+    GC.@preserve x check(d.ctx.h, ccall((:lqcd_fermion_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Cint),
+                                        d.ctx.h, d.h, pointer(x.f), wing(x)))
+end
+
+# ---- the operator ---------------------------------------------------------------------------------------------
+mutable struct B200Dirac{Mode}                 # Mode = :D, :Ddag, :DdagD
+    ctx::B200Context
+    op::LqcdOp
+    eps::Float64
+    maxsteps::Int
+    method::Cint
+    verbose::Int
+    scratch::Vector{B200Field}                 # device twins of the host fields passed to mul!/solve
+    cpu_template::Any                          # a host pseudofermion field (for similar())
+    params::Dict
+end
+
+function upload_links!(ctx::B200Context, U::Vector{<:AbstractGaugefields{3,4}})
+    # U[mu].U :: Array{ComplexF64,6} of size (NC,NC,NX+2w,NY+2w,NZ+2w,NT+2w) [UPSTREAM-RECALL: field name `U`, width `NDW`]
+    w = hasproperty(U[1], :NDW) ? Int(U[1].NDW) : 0
+    ptrs = [pointer(U[mu].U) for mu = 1:4]
+    GC.@preserve U check(ctx.h, ccall((:lqcd_gauge_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{ComplexF64}}, Cint, Cint), ctx.h, ptrs, 3, w))
+end
+
+"Dirac_operator(U, x, params) -- src/system/universe.jl:103-137 builds exactly this params Dict."
+function Dirac_operator(U::Vector{<:AbstractGaugefields{3,4}}, x, params::Dict)
+    get(ENV, "LQCD_B200", "0") == "1" ||
+        return invoke(Dirac_operator, Tuple{Array{<:AbstractGaugefields,1},Any,Any}, U, x, params)   # upstream CPU path
+    name = params["Dirac_operator"]
+    bc = Tuple(Float64.(get(params, "boundarycondition", [1, 1, 1, -1])))        # parameter_structs.jl:133
+    op = if name == "Wilson"
+        LqcdOp(WILSON, params["κ"], get(params, "r", 1.0), 0.0, 0.0, bc)
+    elseif name == "staggered"
+        LqcdOp(STAGGERED, 0.0, 1.0, params["mass"], 0.0, bc)
+    else
+        error("Dirac_operator = $name is not on the B200 path (Wilson, staggered)")
+    end
+    ctx = context((U[1].NX, U[1].NY, U[1].NZ, U[1].NT))
+    upload_links!(ctx, U)
+    method = Dict("bicg" => SOLVER_CGNR, "bicgstab" => SOLVER_BICGSTAB, "preconditiond_bicgstab" => SOLVER_BICGSTAB)[get(params, "method_CG", "bicg")]
+    return B200Dirac{:D}(ctx, op, get(params, "eps_CG", 1e-19), get(params, "MaxCGstep", 3000), method,
+                         get(params, "verbose_level", 1), [B200Field(ctx, op.kind) for _ = 1:4], x, params)
+end
+
+# D(U): re-bind (re-upload) the links -- measure_Pion_correlator.jl:338, and every MD step via calc_UdSfdU!
+(D::B200Dirac)(U) = (upload_links!(D.ctx, U); D)
+Base.adjoint(D::B200Dirac{:D}) = B200Dirac{:Ddag}(D.ctx, D.op, D.eps, D.maxsteps, D.method, D.verbose, D.scratch, D.cpu_template, D.params)
+Base.adjoint(D::B200Dirac{:Ddag}) = B200Dirac{:D}(D.ctx, D.op, D.eps, D.maxsteps, D.method, D.verbose, D.scratch, D.cpu_template, D.params)
+DdagD(D::B200Dirac{:D}) = B200Dirac{:DdagD}(D.ctx, D.op, D.eps, D.maxsteps, D.method, D.verbose, D.scratch, D.cpu_template, D.params)
+LatticeDiracOperators.DdagD_operator(U, x, params) = DdagD(Dirac_operator(U, x, params))               # [UPSTREAM-RECALL]
+mode(::B200Dirac{:D}) = OP_D; mode(::B200Dirac{:Ddag}) = OP_DDAG; mode(::B200Dirac{:DdagD}) = OP_DDAGD
+
+"LinearAlgebra.mul!(y, D, x) -- measure_Pion_correlator.jl:379"
+function mul!(y::AbstractFermionfields, D::B200Dirac, x::AbstractFermionfields)
+    dx, dy = D.scratch[1], D.scratch[2]
+    upload!(dx, x)
+    check(D.ctx.h, ccall((:lqcd_dslash, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), D.ctx.h, D.op, dy.h, dx.h, mode(D)))
+    download!(y, dy)
+    return y
+end
+
+"solve_DinvX!(y, A, x): A y = x, y is the initial guess -- measure_Pion_correlator.jl:399, measure_chiral_condensate.jl:182"
+function solve_DinvX!(y::AbstractFermionfields, A::B200Dirac, x::AbstractFermionfields)
+    dx, dy = A.scratch[1], A.scratch[2]
+    upload!(dx, x); upload!(dy, y)
+    method = mode(A) == OP_DDAGD ? SOLVER_CG : A.method
+    iters = Ref{Cint}(0); rs = Ref{Cdouble}(0.0)
+    hist = A.verbose >= 3 ? zeros(Float64, A.maxsteps + 1) : Float64[]
+    st = ccall((:lqcd_solve, LIB), Cint,
+               (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}, Ptr{Cdouble}),
+               A.ctx.h, A.op, dy.h, dx.h, method, mode(A), A.eps, A.maxsteps, iters, rs, isempty(hist) ? C_NULL : pointer(hist))
+    check(A.ctx.h, st)
+    A.verbose >= 3 && foreach(i -> println("$(i-1)-th eps: $(hist[i])"), 1:iters[]+1)     # upstream println_verbose_level3
+    download!(y, dy)
+    return y
+end
+
+# ---- fermion action (Wilson two-flavour / staggered Nf=8 form; RHMC fractions go through lqcd_multishift_cg) ----
+struct B200FermiAction
+    D::B200Dirac{:D}
+    _temporary_fermionfields::Vector{Any}        # src/md/standardMD.jl:50 does similar(fermi_action._temporary_fermionfields[1])
+    parameters_action::Dict
+end
+FermiAction(D::B200Dirac{:D}, parameters_action) = B200FermiAction(D, [similar(D.cpu_template) for _ = 1:4], parameters_action)
+
+"gauss_sampling_in_action!(xi, U, fa) -- src/md/standardMD.jl:95 (host RNG stays the reference's, seeded by Random.seed!, lqcd.jl:61)"
+gauss_sampling_in_action!(ξ, U, fa::B200FermiAction) = LatticeDiracOperators.gauss_distribution_fermion!(ξ)     # [UPSTREAM-RECALL]
+"sample_pseudofermions!(eta, U, fa, xi): eta = D^dag xi -- src/md/standardMD.jl:96"
+sample_pseudofermions!(η, U, fa::B200FermiAction, ξ) = mul!(η, adjoint(fa.D(U)), ξ)
+"evaluate_FermiAction(fa, U, eta) = eta^dag (D^dag D)^-1 eta -- src/updates/standardHMC.jl:69-71"
+function evaluate_FermiAction(fa::B200FermiAction, U, η)
+    X = fa._temporary_fermionfields[1]
+    LatticeDiracOperators.clear_fermion!(X)
+    solve_DinvX!(X, DdagD(fa.D(U)), η)
+    return real(dot(η, X))
+end
+
+"calc_UdSfdU!(UdSfdU, fa, U, eta) -- src/md/AbstractMD.jl:129; CG, Y = D X and the outer products all run on the device"
+function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200FermiAction, U, η)
+    D = fa.D(U)
+    dη = D.scratch[1]
+    upload!(dη, η)
+    outs = [pointer(UdSfdU[mu].U) for mu = 1:4]                 # temporaries from get_temp(temps, Dim), AbstractMD.jl:123
+    w = hasproperty(UdSfdU[1], :NDW) ? Int(UdSfdU[1].NDW) : 0
+    iters = Ref{Cint}(0); act = Ref{Cdouble}(0.0)
+    GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Ptr{ComplexF64}}, Cint, Ref{Cint}, Ref{Cdouble}),
+        D.ctx.h, D.op, dη.h, C_NULL, D.eps, D.maxsteps, outs, w, iters, act))
+    return nothing
+end
+
+end # module

@@ -70,7 +70,7 @@ SIGNATURES = {
     "lqcd_dslash": (i32, [vp, pop, vp, vp, i32]),
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_multishift_cg": (i32, [vp, pop, pvp, vp, pdbl, i32, dbl, i32, pi32, pdbl]),
-    "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, pi32, pdbl]),
+    "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, i32, pi32, pdbl]),
     "lqcd_comm_export": (i32, [vp, vp]),
     "lqcd_comm_connect": (i32, [vp, vp]),
     "lqcd_decompose": (i32, [pi32, pi32, i32, pi32, pi32, pi32, pi32]),

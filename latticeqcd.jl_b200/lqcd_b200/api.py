@@ -392,6 +392,6 @@ def calc_UdSfdU_(UdSfdU: np.ndarray, fa: FermiActionB200, U, eta: FermionField):
     clear_fermion_(X)
     out = (C.c_void_p * 4)(*[UdSfdU[mu].ctypes.data for mu in range(4)])
     it, act = C.c_int(0), C.c_double(0.0)
-    D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, C.byref(it), C.byref(act))
+    D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, 0, C.byref(it), C.byref(act))
     fa.last = {"iters": it.value, "action": act.value}
     return fa.last
