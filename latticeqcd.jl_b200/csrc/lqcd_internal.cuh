@@ -218,6 +218,18 @@ struct HaloIn {
     int n_interior;
 };
 
+struct WilsonArgs {
+    cplx *out;
+    const cplx *in;
+    const cplx *gauge;
+    Geom g;
+    double kappa;
+    double bc[4];
+    DslashFuse fuse;
+    Reduce red;
+    HaloIn halo;     // MULTI kernels only
+};
+
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                          const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,

@@ -20,17 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 
-struct WilsonArgs {
-    cplx *out;
-    const cplx *in;
-    const cplx *gauge;
-    Geom g;
-    double kappa;
-    double bc[4];
-    DslashFuse fuse;
-    Reduce red;
-    HaloIn halo;     // MULTI kernels only
-};
+int launch_wilson_dslash2(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash2.cu
 
 // one of the eight hops.  FWD=1: U_mu(n) x(n+mu) with link at `ls` = n;  FWD=0: U_mu^dag(n-mu) x(n-mu), ls = n-mu.
 template <int MU, int FWD, int DAG>
@@ -200,6 +190,10 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         }                                                                            \
     } while (0)
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
+    // kernel family: 1 = one lane per site (this file), 2 = two lanes per site (wilson_dslash2.cu)
+    static int family = -1;
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && atoi(e) == 1) ? 1 : 2; }
+    if (family == 2 && !halo && bs <= 128) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
     if (lb == 12804 && bs <= 128) WL(128, 4);
