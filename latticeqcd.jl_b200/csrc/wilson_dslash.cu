@@ -190,9 +190,12 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         }                                                                            \
     } while (0)
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
-    // kernel family: 1 = one lane per site (this file), 2 = two lanes per site (wilson_dslash2.cu)
+    // kernel family: 1 = one lane per site (this file, default), 2 = two lanes per site (wilson_dslash2.cu).
+    // Measured on B200 at 32^4: family 2 with 16/24/32 warps per SM runs 222/261/355 us against 192 us here --
+    // more resident warps LOWER the L1 hit rate and the kernel then saturates the ~10.8 TB/s L2->SM fabric
+    // (2.1 GB of L2 reads per application at 28 % L1 hits), so occupancy is not the lever; L2 traffic is.
     static int family = -1;
-    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && atoi(e) == 1) ? 1 : 2; }
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && atoi(e) == 2) ? 2 : 1; }
     if (family == 2 && !halo && bs <= 128) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
