@@ -577,6 +577,8 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         }
         return LQCD_OK;
     }
+    if (fuse && fuse->axpy_r)
+        return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_FUSED_HALO=0 (separate exterior kernel) needs LQCD_CG_FUSE=0 as well");
     // interior: all sites with off-rank hops masked; reductions over non-face sites deposited as partials
     const bool want_red = fuse && (fuse->dot_with || fuse->want_norm);
     DslashFuse f2 = DslashFuse();

@@ -103,6 +103,8 @@ enum FinishOp {
     FIN_CG_PQ,            // red0 = Re<p,q>        -> pq, alpha = rr/pq
     FIN_CG_RR,            // red0 = |r_new|^2      -> convergence test, beta, rr, it++
     FIN_CG_INIT,          // red0 = |r0|^2         -> rr, convergence test at step 0
+    FIN_CG_PQN,           // red2 = |D p|^2 = <p, D^dag D p> -> pq, alpha   (norm form: no extra read of p)
+    FIN_CG_RRN,           // red2 = |r_new|^2 from the fused r -= alpha q epilogue -> convergence test, beta, rr, it++
     FIN_NR_C2,            // red0 = |q|^2          -> alpha = c1/c2
     FIN_NR_RR,            // red0 = |res|^2        -> convergence test, it++
     FIN_NR_C3,            // red0 = |s|^2          -> beta = c3/c1, c1 = c3
@@ -203,6 +205,7 @@ struct DslashFuse {
     double shift;              // y += shift * x  (multi-shift base system: (DdagD + s) )
     const cplx *shift_src;     // field multiplied by `shift` (the input of the first hop of DdagD)
     int interior_only;         // multi-GPU interior pass: reduce over non-boundary sites, deposit partials only
+    cplx *axpy_r;              // CG: do not store y; instead r <- r - alpha*y (alpha from SolverState) and reduce |r|^2 in red2
 };
 
 // multi-GPU: halo data consumed INSIDE the Dslash kernel (fused exterior).  CTAs are permuted so that tiles

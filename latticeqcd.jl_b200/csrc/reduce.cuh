@@ -23,9 +23,14 @@ __device__ __forceinline__ void apply_finish(int op, const double *tot, SolverSt
         st->pq = tot[0];
         st->alpha = st->rr / tot[0];
         break;
-    case FIN_CG_RR: {
+    case FIN_CG_PQN:
+        st->pq = tot[2];
+        st->alpha = st->rr / tot[2];
+        break;
+    case FIN_CG_RR:
+    case FIN_CG_RRN: {
         int it = ++st->it;
-        double c3 = tot[0];
+        double c3 = (op == FIN_CG_RRN) ? tot[2] : tot[0];
         if (hist) hist[it] = c3;
         if (c3 < st->eps) { st->done = 1; st->iters = it; st->rr = c3; }
         else { st->beta = c3 / st->rr; st->rr = c3; }
@@ -204,6 +209,6 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
             }
         }
         apply_finish(finish, tot, R.st, R.hist);
-        if (finish != FIN_STORE && !(fabs(tot[0]) <= 1.79e308)) { R.st->done = 1; R.st->failed = 1; R.st->iters = R.st->it; }
+        if (finish != FIN_STORE && !(fabs(tot[0]) <= 1.79e308 && fabs(tot[2]) <= 1.79e308)) { R.st->done = 1; R.st->failed = 1; R.st->iters = R.st->it; }
     }
 }

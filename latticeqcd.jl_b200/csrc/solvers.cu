@@ -167,10 +167,22 @@ extern "C" int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, con
         cplx *r = fr->d, *p = fp->d, *q = fq->d, *t = ft->d;
         LQCD_TRY(apply_async(ctx, op, q, x, LQCD_OP_DDAGD, t, nullptr, nullptr));
         LQCD_TRY(blas_resid_init(ctx, bb, q, r, p, nullptr, n, FIN_CG_INIT));
+        // Per iteration: 3 kernels, 3072 B/site.  <p, D^dag D p> = |D p|^2 is reduced in the epilogue of the FIRST
+        // Dslash (no extra read of p), so alpha is known before the second Dslash starts; that kernel then applies
+        // r <- r - alpha (D^dag t) in its epilogue and reduces |r|^2 -- q = D^dag D p is never written to memory.
+        // LQCD_CG_FUSE=0 selects the 4-kernel form (explicit <p,q> dot fused in the second Dslash, separate r update).
+        static int cgfuse = -1;
+        if (cgfuse < 0) { const char *e = getenv("LQCD_CG_FUSE"); cgfuse = (e && atoi(e) == 0) ? 0 : 1; }
         DslashFuse pq = DslashFuse(); pq.use_state = 1; pq.dot_with = p; pq.finish = FIN_CG_PQ;
+        DslashFuse f1 = DslashFuse(); f1.use_state = 1; f1.want_norm = 1; f1.finish = FIN_CG_PQN;
+        DslashFuse f2 = DslashFuse(); f2.use_state = 1; f2.want_norm = 1; f2.finish = FIN_CG_RRN; f2.axpy_r = r;
         rc = run_loop(ctx, maxsteps, [&](int it) -> int {
-            LQCD_TRY(apply_async(ctx, op, q, p, LQCD_OP_DDAGD, t, &plain, &pq));      // q = D^dag D p, pq = <p,q>
-            LQCD_TRY(blas_cg_update_r(ctx, r, q, n, FIN_CG_RR));                      // r -= alpha q, |r|^2, beta
+            if (cgfuse) {
+                LQCD_TRY(apply_async(ctx, op, q, p, LQCD_OP_DDAGD, t, &f1, &f2));     // t = D p (alpha); r -= alpha D^dag t (|r|^2, beta)
+            } else {
+                LQCD_TRY(apply_async(ctx, op, q, p, LQCD_OP_DDAGD, t, &plain, &pq));  // q = D^dag D p, pq = <p,q>
+                LQCD_TRY(blas_cg_update_r(ctx, r, q, n, FIN_CG_RR));                  // r -= alpha q, |r|^2, beta
+            }
             return blas_cg_update_xp(ctx, x, p, r, n, it);                            // x += alpha p, p = r + beta p
         }, iters, resid_sq);
     } else if (method == LQCD_SOLVER_CGNR) {

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
         shop_pair<2, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, x, y, z, t);
         shop_pair<3, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, x, y, z, t);
         const size_t base = (size_t)blk * (3 * 32) + lane;
+        cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
+        const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             cplx xi = ldg128(A.in + base + k * 32);
@@ -125,13 +127,17 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
                 cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
                 yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
             }
+            if (A.fuse.axpy_r) {
+                cplx rv = A.fuse.axpy_r[base + k * 32];
+                yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
+            }
             if (A.fuse.dot_with && !skip_red) {
                 cplx w = ldg128(A.fuse.dot_with + base + k * 32);
                 red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
                 red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
             }
             if (!skip_red) { red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]); }
-            A.out[base + k * 32] = yk;
+            dst[base + k * 32] = yk;
         }
     }
     if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only);

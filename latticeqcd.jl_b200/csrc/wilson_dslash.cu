@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         hop_pair<3, DAG, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
         const size_t base = (size_t)blk * (12 * 32) + lane;
         const double mk = -A.kappa;
+        cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
+        const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
 #pragma unroll
         for (int k = 0; k < 12; k++) {
             cplx xi = ldg128(A.in + base + k * 32);
@@ -145,13 +147,17 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
                 cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
                 yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
             }
+            if (A.fuse.axpy_r) {           // fused CG residual update: r <- r - alpha * (D^dag t); q is never stored
+                cplx rv = A.fuse.axpy_r[base + k * 32];
+                yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
+            }
             if (A.fuse.dot_with && !skip_red) {
                 cplx w = ldg128(A.fuse.dot_with + base + k * 32);
                 red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
                 red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
             }
             if (!skip_red) { red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]); }
-            A.out[base + k * 32] = yk;
+            dst[base + k * 32] = yk;
         }
     }
     if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only);
@@ -196,7 +202,7 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     // (2.1 GB of L2 reads per application at 28 % L1 hits), so occupancy is not the lever; L2 traffic is.
     static int family = -1;
     if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && atoi(e) == 2) ? 2 : 1; }
-    if (family == 2 && !halo && bs <= 128) return launch_wilson_dslash2(ctx, A, dagger, s);
+    if (family == 2 && !halo && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
     if (lb == 12804 && bs <= 128) WL(128, 4);
