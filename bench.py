@@ -185,6 +185,10 @@ def choose_procgrid(n):
 
 
 def run_b200(args, dims):
+    # stdout must carry exactly ONE JSON line: park the real stdout, send everything else (library banners) to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import lqcd_b200 as q
@@ -199,6 +203,10 @@ def run_b200(args, dims):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL is host plumbing only (handle exchange, barrier, max-over-ranks); with NCCL_DEBUG=VERSION/INFO it
+        # prints a banner on STDOUT, which must carry exactly one JSON line -> silence it.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -352,7 +360,8 @@ def run_b200(args, dims):
                "converged_iters_eps1e-10": it_conv, "resid_sq": rs_conv, "field": "warm eps=0.3"},
         "e2e": e2e, "e2e_cg": e2e_cg, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():

@@ -193,6 +193,11 @@ extern "C" int lqcd_comm_connect(lqcd_ctx *ctx, const void *all_handles) {
     cr.nranks = ctx->nranks; cr.rank = ctx->rank;
     cr.seq = (unsigned long long *)(c->base + c->off_seq);
     cr.err = (int *)(c->base + c->off_err);
+    {
+        double secs = LQCD_SPIN_TIMEOUT_DEFAULT_S;
+        if (const char *e = getenv("LQCD_COMM_TIMEOUT_S")) { double v = atof(e); if (v > 0.01 && v < 3600.0) secs = v; }
+        cr.timeout_cycles = (long long)(secs * 1.9e9);
+    }
     for (int r = 0; r < ctx->nranks; r++) {
         cr.vals[r] = (double *)(c->peer[r] + c->off_red_vals);
         cr.flags[r] = (unsigned long long *)(c->peer[r] + c->off_red_flags);
@@ -207,7 +212,7 @@ int comm_check_error(lqcd_ctx *ctx) {
     if (ctx->nranks == 1 || !ctx->comm) return LQCD_OK;
     int err = 0;
     CUDA_TRY(ctx, cudaMemcpy(&err, ctx->comm->base + ctx->comm->off_err, sizeof err, cudaMemcpyDeviceToHost));
-    if (err) return lqcd_fail(ctx, LQCD_ERR_COMM, "peer wait timed out on the device (a neighbouring rank did not arrive)");
+    if (err) return lqcd_fail(ctx, LQCD_ERR_COMM, "peer wait timed out on the device (code %d: 1xxxxxx = halo flag [dir*2+side][seq], 2xxxxxx = all-reduce [seq]; host halo_seq = %llu)", err, ctx->comm->halo_seq);
     return LQCD_OK;
 }
 
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(128) halo_exterior_kernel(const HaloArgs A) {
             if (!A.g.part[m]) continue;
             for (int side = 0; side < 2 && good; side++)
                 while (ld_acquire_sys(A.recv_flag[m][side]) < A.seq)
-                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { good = 0; *A.err = 1; break; }
+                    if (clock64() - t0 > A.red.cr.timeout_cycles) { good = 0; *A.err = 1; break; }
         }
         ok = good;
     }
@@ -537,19 +542,28 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     static double tacc[3] = {0, 0, 0};
     static long tcount = 0;
     if (two_streams < 0) { const char *e = getenv("LQCD_PACK_STREAM"); two_streams = (e && atoi(e) == 0) ? 0 : 1; }
+    // LQCD_COMM_TIMING=2: non-intrusive timeline (events recorded on both streams, no host sync until 200 samples)
+    static const int TLN = 200;
+    static cudaEvent_t tl[4][TLN];      // 0 pack start, 1 pack end, 2 dslash start, 3 dslash end
+    static int tln = 0, timeline = 0;
     if (timing < 0) {
         const char *e = getenv("LQCD_COMM_TIMING"); timing = (e && atoi(e) == 1) ? 1 : 0;
+        timeline = (e && atoi(e) == 2) ? 1 : 0;
         if (timing) { two_streams = 0; for (int i = 0; i < 4; i++) cudaEventCreate(&te[i]); }
+        if (timeline) for (int i = 0; i < 4; i++) for (int j = 0; j < TLN; j++) cudaEventCreate(&tl[i][j]);
     }
+    const bool tlrec = timeline && tln < TLN;
     if (timing) cudaEventRecord(te[0], ctx->stream);
     cudaStream_t ps = two_streams ? ctx->stream2 : ctx->stream;
     if (two_streams) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_int, ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->ev_int, 0));
     }
+    if (tlrec) cudaEventRecord(tl[0][tln], ps);
     halo_pack_kernel<<<ncta, 128, 0, ps>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (tlrec) cudaEventRecord(tl[1][tln], ps);
     if (two_streams) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pack, ps));
     if (timing) cudaEventRecord(te[1], ctx->stream);
     static int fused = -1;
@@ -564,8 +578,29 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
             for (int side = 0; side < 2; side++) { H.recv[mu][side] = A.recv[mu][side]; H.recv_flag[mu][side] = A.recv_flag[mu][side]; }
         }
         H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
+        H.timeout_cycles = ctx->red.cr.timeout_cycles;
+        if (tlrec) cudaEventRecord(tl[2][tln], ctx->stream);
         if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
         else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
+        if (tlrec) {
+            cudaEventRecord(tl[3][tln], ctx->stream);
+            if (++tln == TLN) {
+                cudaEventSynchronize(tl[3][TLN - 1]); cudaEventSynchronize(tl[1][TLN - 1]);
+                double a[6] = {0, 0, 0, 0, 0, 0};
+                int n = 0;
+                for (int k = TLN / 2; k < TLN; k++, n++) {          // second half: steady state
+                    float ms;
+                    cudaEventElapsedTime(&ms, tl[0][k], tl[1][k]); a[0] += ms;          // pack duration
+                    cudaEventElapsedTime(&ms, tl[2][k], tl[3][k]); a[1] += ms;          // dslash duration
+                    cudaEventElapsedTime(&ms, tl[3][k - 1], tl[2][k]); a[2] += ms;      // gap: previous dslash end -> this start
+                    cudaEventElapsedTime(&ms, tl[2][k], tl[0][k]); a[3] += ms;          // pack start relative to dslash start
+                    cudaEventElapsedTime(&ms, tl[2][k], tl[1][k]); a[4] += ms;          // pack end relative to dslash start
+                    cudaEventElapsedTime(&ms, tl[3][k - 1], tl[3][k]); a[5] += ms;      // period
+                }
+                fprintf(stderr, "[lqcd timeline rank %d] pack %.1f us | dslash %.1f us | gap %.1f us | pack start %+.1f us, end %+.1f us after dslash start | period %.1f us\n",
+                        ctx->rank, 1e3 * a[0] / n, 1e3 * a[1] / n, 1e3 * a[2] / n, 1e3 * a[3] / n, 1e3 * a[4] / n, 1e3 * a[5] / n);
+            }
+        }
         if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
         if (timing) {
             cudaEventRecord(te[2], ctx->stream);

@@ -65,7 +65,9 @@ struct SolverState {
 
 #define LQCD_MAX_RANKS 8
 #define LQCD_RED_SLOTS 4
-#define LQCD_SPIN_TIMEOUT_CYCLES 6000000000ll      // ~3 s at 1.9 GHz: a lost peer becomes an error, not a hang
+#define LQCD_SPIN_TIMEOUT_DEFAULT_S 20.0          // device-side spin limit: a lost peer becomes LQCD_ERR_COMM, not a hung GPU
+                                                    // (override: LQCD_COMM_TIMEOUT_S; ranks may legitimately be seconds apart, e.g.
+                                                    //  when one rank's host does CPU work between collective solves)
 
 // In-kernel all-reduce over NVLink peer memory (one process per GPU).  Every rank's reducing kernel
 // writes its local totals straight into slot [seq % SLOTS][my rank] of EVERY rank's buffer (peer stores),
@@ -77,7 +79,8 @@ struct CommRed {
     unsigned long long *seq;                      // local device counter of reductions performed
     double *vals[LQCD_MAX_RANKS];                 // vals[r]: rank r's [SLOTS][nranks][LQCD_MAX_RED] array (peer mapped)
     unsigned long long *flags[LQCD_MAX_RANKS];    // flags[r]: rank r's [SLOTS][nranks] sequence flags
-    int *err;                                     // local device error word (1 = timeout)
+    int *err;                                     // local device error word (non-zero = timeout code)
+    long long timeout_cycles;
 };
 
 // deterministic grid reduction workspace
@@ -219,6 +222,7 @@ struct HaloIn {
     int pfirst[4], plast[4];                    // this rank touches the global low / high boundary in mu
     const int *cta_order;
     int n_interior;
+    long long timeout_cycles;
 };
 
 struct WilsonArgs {

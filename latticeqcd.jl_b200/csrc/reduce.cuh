@@ -196,10 +196,10 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
             bool ok = true;
             for (int r = 0; r < c.nranks && ok; r++) {
                 while (ld_acquire_sys(c.flags[c.rank] + (size_t)slot * c.nranks + r) < seq) {
-                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { ok = false; break; }
+                    if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }
                 }
             }
-            if (!ok) { *c.err = 1; R.st->done = 1; R.st->failed = 2; }
+            if (!ok) { *c.err = 2000000 + (int)(seq % 1000000); R.st->done = 1; R.st->failed = 2; }
 #pragma unroll
             for (int j = 0; j < NR; j++) {
                 double s = 0.0;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void wait_halo_flags(const Geom &g, const HaloIn &H) 
             if (!g.part[m]) continue;
             for (int side = 0; side < 2 && good; side++)
                 while (ld_acquire_sys(H.recv_flag[m][side]) < H.seq)
-                    if (clock64() - t0 > LQCD_SPIN_TIMEOUT_CYCLES) { good = false; *H.err = 1; break; }
+                    if (clock64() - t0 > H.timeout_cycles) { good = false; *H.err = 1000000 + (m * 2 + side) * 100000 + (int)(H.seq % 100000); break; }
         }
     }
     __syncthreads();

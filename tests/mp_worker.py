@@ -4,6 +4,8 @@ that several ranks may share one GPU on a single-GPU box: the CUDA-IPC / peer-me
 
 Every rank builds the same global synthetic fields, uploads its LOCAL block, runs the operator and the
 solvers through the C ABI, and rank 0 compares the gathered result with the CPU oracle on the global lattice.
+Rank 0 computes ALL oracle references first (the other ranks wait at a host barrier): between two
+collective library calls the ranks must not be seconds apart, the device-side waits have a timeout.
 """
 import os
 import sys
@@ -25,11 +27,23 @@ def main():
     kind_name = sys.argv[3]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    assert world == int(np.prod(pg)), f"procgrid {pg} needs {int(np.prod(pg))} ranks, got {world}"
     ndev = torch.cuda.device_count()
     dev = int(os.environ.get("LOCAL_RANK", rank)) % ndev
     kind = orc.WILSON if kind_name == "Wilson" else orc.STAGGERED
     Ug = orc.random_su3(dims, seed=17, eps=0.4)
     src = orc.gaussian_field(dims, kind, seed=23)
+    op = orc.make_op(dims, kappa=0.125, mass=0.2)
+    ref = {}
+    if rank == 0:
+        orc.set_threads(max(1, (os.cpu_count() or 8) // 2))
+        for m, nm in ((orc.D, "D"), (orc.DDAG, "Ddag"), (orc.DDAGD, "DdagD")):
+            ref[nm] = orc.apply(op, kind, m, Ug, src)
+        ref["dot"] = np.vdot(src, ref["DdagD"])
+        ref["cg"] = orc.cg(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
+        ref["cgnr"] = orc.cgnr(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
+    dist.barrier()
+
     ctx = q.get_context(dims, procgrid=pg, rank=rank, device=dev)
     q.connect_ranks(ctx, dist)
     (lx, ly, lz, lt), (ox, oy, oz, ot) = ctx.local_dims, ctx.origin
@@ -37,15 +51,12 @@ def main():
     Ul = np.ascontiguousarray(Ug[(slice(None),) + sl])
     U = q.gaugefields_from_array(Ul, global_dims=dims, procgrid=pg, rank=rank, device=dev)
     x = q.Initialize_pseudofermion_fields(U[0], kind_name)
-    params = {"Dirac_operator": kind_name, "κ": 0.125, "mass": 0.2, "eps_CG": 1e-18, "MaxCGstep": 2000,
-              "boundarycondition": [1, 1, 1, -1]}
-    if kind_name != "Wilson":
-        params["Dirac_operator"] = "staggered"
+    params = {"Dirac_operator": "Wilson" if kind == orc.WILSON else "staggered", "κ": 0.125, "mass": 0.2,
+              "eps_CG": 1e-18, "MaxCGstep": 2000, "boundarycondition": [1, 1, 1, -1]}
     D = q.Dirac_operator(U, x, params)
     loc = (lambda a: np.ascontiguousarray(a[(slice(None),) + sl])) if kind == orc.WILSON else (lambda a: np.ascontiguousarray(a[sl]))
     x.from_host(loc(src))
     y = q.similar(x)
-    op = orc.make_op(dims, kappa=0.125, mass=0.2)
 
     def gather(f):
         h = torch.from_numpy(f.to_host().view(np.float64))      # gloo has no complex dtypes
@@ -72,38 +83,27 @@ def main():
             if not err < tol:
                 fails.append(name)
 
-    for A, m, nm in ((D, orc.D, "D"), (q.adjoint(D), orc.DDAG, "Ddag"), (q.DdagD(D), orc.DDAGD, "DdagD")):
+    for A, nm in ((D, "D"), (q.adjoint(D), "Ddag"), (q.DdagD(D), "DdagD")):
         q.mul_(y, A, x)
         got = gather(y)
         if rank == 0:
-            check(nm, got, orc.apply(op, kind, m, Ug, src), 1e-13)
-    # global dot product
-    d = q.dot(x, y)
+            check(nm, got, ref[nm], 1e-13)
+    d = q.dot(x, y)                                     # global dot product (in-kernel all-reduce)
     if rank == 0:
-        want = np.vdot(src, orc.apply(op, kind, orc.DDAGD, Ug, src))
-        if abs(d - want) > 1e-10 * abs(want):
+        e = abs(d - ref["dot"]) / abs(ref["dot"])
+        print(f"[mp] dot rel err {e:.2e}", flush=True)
+        if e > 1e-10:
             fails.append("dot")
-        print(f"[mp] dot rel err {abs(d - want) / abs(want):.2e}", flush=True)
-    # CG on DdagD and CGNR on D
-    sol = q.similar(x)
-    q.clear_fermion_(sol)
-    info = q.solve_DinvX_(sol, q.DdagD(D), x)
-    got = gather(sol)
-    if rank == 0:
-        ref = orc.cg(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
-        print(f"[mp] CG iters {info['iters']} (oracle {ref['iters']})", flush=True)
-        if info["iters"] != ref["iters"]:
-            fails.append("cg iters")
-        check("CG solution", got, ref["x"], 1e-9)
-    q.clear_fermion_(sol)
-    info = q.solve_DinvX_(sol, D, x)
-    got = gather(sol)
-    if rank == 0:
-        ref = orc.cgnr(op, kind, Ug, src, eps=1e-18, maxsteps=2000)
-        print(f"[mp] CGNR iters {info['iters']} (oracle {ref['iters']})", flush=True)
-        if info["iters"] != ref["iters"]:
-            fails.append("cgnr iters")
-        check("CGNR solution", got, ref["x"], 1e-9)
+    for name, A, key in (("CG", q.DdagD(D), "cg"), ("CGNR", D, "cgnr")):
+        sol = q.similar(x)
+        q.clear_fermion_(sol)
+        info = q.solve_DinvX_(sol, A, x)
+        got = gather(sol)
+        if rank == 0:
+            print(f"[mp] {name} iters {info['iters']} (oracle {ref[key]['iters']})", flush=True)
+            if info["iters"] != ref[key]["iters"]:
+                fails.append(f"{name} iters")
+            check(f"{name} solution", got, ref[key]["x"], 1e-9)
     flag = torch.tensor([len(fails)])
     dist.broadcast(flag, 0)
     dist.barrier()
