@@ -21,6 +21,7 @@
 #include "reduce.cuh"
 #include "wilson_spin.cuh"
 #include "site_map.cuh"
+#include "halo_pack.cuh"
 #include <unistd.h>
 #include <cstring>
 #include <cstdio>
@@ -226,13 +227,10 @@ struct HaloArgs {
     double coef;               // Wilson: -kappa ; staggered: sign
     double bc[4];
     int pfirst[4], plast[4];   // this rank sits on the global low / high boundary in mu
-    cplx *send[4][2];          // pack: [mu][0] my LOW face  -> lower nbr's "from upper" slot ; [1] my HIGH face -> upper nbr's "from lower" slot
-    unsigned long long *send_flag[4][2];
+    HaloOut hout;              // pack: destinations, flags, CTA prefix, ticket, seq
     const cplx *recv[4][2];    // exterior: [mu][0] data from lower nbr (for my low face), [1] from upper nbr (for my high face)
     const unsigned long long *recv_flag[4][2];
-    int cta0[5];               // pack: first CTA of direction mu (prefix sums over partitioned directions)
     unsigned long long seq;
-    unsigned int *ticket;
     int *err;
     const SolverState *st;
     int use_state;
@@ -243,121 +241,9 @@ struct HaloArgs {
     unsigned int part_offset;  // exterior: partials deposited by the interior kernel precede ours
 };
 
-// face index -> site (coordinate mu fixed to cm); faces are enumerated lexicographically over the other three.
-__device__ __forceinline__ int face_site(const Geom &g, int mu, int f, int cm, int &x, int &y, int &z, int &t) {
-    const int d[4] = {g.X, g.Y, g.Z, g.T};
-    int c[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (i == mu) c[i] = cm;
-        else { c[i] = f % d[i]; f /= d[i]; }
-    }
-    x = c[0]; y = c[1]; z = c[2]; t = c[3];
-    return c[0] + g.X * (c[1] + g.Y * (c[2] + g.Z * c[3]));
-}
-
-template <int MU>
-__device__ __forceinline__ void wilson_pack_site(const HaloArgs &A, int side, int f, int s) {
-    const cplx *sp = A.in + (size_t)(s >> 5) * (12 * 32) + (s & 31);
-    cplx p[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) p[k] = ldg128(sp + k * 32);
-    cplx o0[3], o1[3];
-    if (side == 0) {                       // my low face: receiver's FORWARD hop, projector sign S = DAG ? +1 : -1
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (A.dagger) project<MU, +1>(o0[c], o1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
-            else          project<MU, -1>(o0[c], o1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
-        }
-    } else {                               // my high face: receiver's BACKWARD hop: U^dag(m) P psi(m), S = DAG ? -1 : +1
-        cplx h0[3], h1[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (A.dagger) project<MU, -1>(h0[c], h1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
-            else          project<MU, +1>(h0[c], h1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
-        }
-        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            cplx g0 = cmake(0, 0), g1 = cmake(0, 0);
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                cplx u = ldg128(lk + (b * 3 + a) * 32);
-                cfmac(g0, u, h0[b]); cfmac(g1, u, h1[b]);
-            }
-            o0[a] = g0; o1[a] = g1;
-        }
-    }
-    cplx *dst = A.send[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
-#pragma unroll
-    for (int c = 0; c < 3; c++) { dst[c * 32] = o0[c]; dst[(3 + c) * 32] = o1[c]; }
-}
-
-template <int MU>
-__device__ __forceinline__ void stag_pack_site(const HaloArgs &A, int side, int f, int s) {
-    const cplx *sp = A.in + (size_t)(s >> 5) * (3 * 32) + (s & 31);
-    cplx v[3], o[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) v[c] = ldg128(sp + c * 32);
-    if (side == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) o[c] = v[c];
-    } else {
-        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            cplx acc = cmake(0, 0);
-#pragma unroll
-            for (int b = 0; b < 3; b++) cfmac(acc, ldg128(lk + (b * 3 + a) * 32), v[b]);
-            o[a] = acc;
-        }
-    }
-    cplx *dst = A.send[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
-#pragma unroll
-    for (int c = 0; c < 3; c++) dst[c * 32] = o[c];
-}
-
 __global__ void __launch_bounds__(128) halo_pack_kernel(const HaloArgs A) {
     if (A.use_state && A.st->done) return;
-    int mu = 0;
-    while (mu < 3 && (int)blockIdx.x >= A.cta0[mu + 1]) mu++;
-    const int d[4] = {A.g.X, A.g.Y, A.g.Z, A.g.T};
-    const int F = A.g.V / d[mu];
-    const int i = (blockIdx.x - A.cta0[mu]) * blockDim.x + threadIdx.x;
-    if (i < 2 * F) {
-        const int side = i / F, f = i % F;
-        int x, y, z, t;
-        const int s = face_site(A.g, mu, f, side ? d[mu] - 1 : 0, x, y, z, t);
-        if (A.kind == LQCD_WILSON) {
-            switch (mu) {
-            case 0: wilson_pack_site<0>(A, side, f, s); break;
-            case 1: wilson_pack_site<1>(A, side, f, s); break;
-            case 2: wilson_pack_site<2>(A, side, f, s); break;
-            default: wilson_pack_site<3>(A, side, f, s); break;
-            }
-        } else {
-            switch (mu) {
-            case 0: stag_pack_site<0>(A, side, f, s); break;
-            case 1: stag_pack_site<1>(A, side, f, s); break;
-            case 2: stag_pack_site<2>(A, side, f, s); break;
-            default: stag_pack_site<3>(A, side, f, s); break;
-            }
-        }
-    }
-    // publish: bar.sync orders the CTA's peer stores before thread 0's system-scope fence (cumulative), then the
-    // ticket; the last CTA to arrive raises the sequence flags at the neighbours.
-    __syncthreads();
-    __shared__ int last;
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        last = (atomicInc(A.ticket, gridDim.x - 1) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last && threadIdx.x < 8) {
-        const int m = threadIdx.x >> 1, side = threadIdx.x & 1;
-        __threadfence_system();
-        if (A.g.part[m]) st_release_sys(A.send_flag[m][side], A.seq);
-    }
+    halo_pack_cta(A.g, A.kind, A.dagger, A.in, A.gauge, A.hout, blockIdx.x);
 }
 
 // Wilson: add the off-rank hop(s) of direction MU at face site s into acc (12 complex, in units of "hopping sum").
@@ -512,7 +398,8 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     const unsigned long long seq = ++c->halo_seq;
     const int slot = (int)(seq & 1);
     A.seq = seq;
-    A.ticket = (unsigned int *)(c->base + c->off_ticket);
+    A.hout.seq = seq;
+    A.hout.ticket = (unsigned int *)(c->base + c->off_ticket);
     A.err = (int *)(c->base + c->off_err);
     A.st = ctx->red.st; A.use_state = fuse ? fuse->use_state : 0;
     A.bsites = c->bsites; A.nbsites = c->nbsites;
@@ -521,21 +408,43 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     for (int mu = 0; mu < 4; mu++) {
         A.bc[mu] = op->bc[mu];
         A.pfirst[mu] = ctx->pcoord[mu] == 0; A.plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
-        A.cta0[mu] = ncta;      // number of CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
+        A.hout.cta0[mu] = ncta;      // number of CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
         if (!g.part[mu]) continue;
         ncta += (2 * c->face[mu] + 127) / 128;
         const int lo = c->nbr[mu][0], hi = c->nbr[mu][1];
         // my low face feeds the LOWER neighbour's "from upper" (side 1) slot; my high face the UPPER neighbour's side 0
-        A.send[mu][0] = (cplx *)(c->peer[lo] + c->halo_off[mu][1][slot]);
-        A.send[mu][1] = (cplx *)(c->peer[hi] + c->halo_off[mu][0][slot]);
-        A.send_flag[mu][0] = (unsigned long long *)(c->peer[lo] + c->off_halo_flags) + (mu * 2 + 1) * 2 + slot;
-        A.send_flag[mu][1] = (unsigned long long *)(c->peer[hi] + c->off_halo_flags) + (mu * 2 + 0) * 2 + slot;
+        A.hout.send[mu][0] = (cplx *)(c->peer[lo] + c->halo_off[mu][1][slot]);
+        A.hout.send[mu][1] = (cplx *)(c->peer[hi] + c->halo_off[mu][0][slot]);
+        A.hout.send_flag[mu][0] = (unsigned long long *)(c->peer[lo] + c->off_halo_flags) + (mu * 2 + 1) * 2 + slot;
+        A.hout.send_flag[mu][1] = (unsigned long long *)(c->peer[hi] + c->off_halo_flags) + (mu * 2 + 0) * 2 + slot;
         for (int side = 0; side < 2; side++) {
             A.recv[mu][side] = (const cplx *)(c->base + c->halo_off[mu][side][slot]);
             A.recv_flag[mu][side] = (const unsigned long long *)(c->base + c->off_halo_flags) + (mu * 2 + side) * 2 + slot;
         }
     }
-    A.cta0[4] = ncta;
+    A.hout.cta0[4] = ncta;
+    // Default: SELF-PACKING Dslash kernel -- the first npack CTAs of the kernel itself ship this application's halo
+    // (halo_pack.cuh), the interior tiles follow, the face tiles (last) consume the neighbours' slots: one launch,
+    // no second stream, no events.  LQCD_SELF_PACK=0 falls back to a separate pack kernel on the priority stream.
+    static int self_pack = -1;
+    if (self_pack < 0) { const char *e = getenv("LQCD_SELF_PACK"); self_pack = (e && atoi(e) == 0) ? 0 : 1; }
+    if (self_pack) {
+        const int bs = 32 * g.wpc;
+        HaloOut O = A.hout;
+        int np = 0;
+        for (int mu = 0; mu < 4; mu++) { O.cta0[mu] = np; if (g.part[mu]) np += (2 * c->face[mu] + bs - 1) / bs; }
+        O.cta0[4] = np;
+        HaloIn H;
+        memset(&H, 0, sizeof H);
+        for (int mu = 0; mu < 4; mu++) {
+            H.pfirst[mu] = A.pfirst[mu]; H.plast[mu] = A.plast[mu];
+            for (int side = 0; side < 2; side++) { H.recv[mu][side] = A.recv[mu][side]; H.recv_flag[mu][side] = A.recv_flag[mu][side]; }
+        }
+        H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
+        H.timeout_cycles = ctx->red.cr.timeout_cycles;
+        if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
+        return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
+    }
     // pack on the second stream (overlaps the interior kernel); it needs x, which earlier main-stream work produced
     static int two_streams = -1, timing = -1;
     static cudaEvent_t te[4];

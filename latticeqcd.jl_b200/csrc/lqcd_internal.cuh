@@ -225,6 +225,14 @@ struct HaloIn {
     long long timeout_cycles;
 };
 
+struct HaloOut {
+    cplx *send[4][2];                    // [mu][0] my LOW face -> lower nbr's "from upper" slot ; [1] my HIGH face -> upper nbr's "from lower" slot
+    unsigned long long *send_flag[4][2];
+    int cta0[5];                         // first pack CTA of direction mu (prefix over partitioned directions), cta0[4] = npack
+    unsigned int *ticket;                // last-pack-CTA detector (self resetting)
+    unsigned long long seq;              // application number published in the flags
+};
+
 struct WilsonArgs {
     cplx *out;
     const cplx *in;
@@ -235,12 +243,13 @@ struct WilsonArgs {
     DslashFuse fuse;
     Reduce red;
     HaloIn halo;     // MULTI kernels only
+    HaloOut hout;    // MULTI == 2 (self-packing) only
 };
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr);
+                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr);
+                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
 int apply_op(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
              lqcd_fermion *tmp, const DslashFuse *fuse_last);
 

@@ -124,8 +124,12 @@ __device__ __forceinline__ void apply_finish(int op, const double *tot, SolverSt
 //   do_finish    0: only deposit the CTA partial (a later kernel finishes)
 template <int NR>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce &R, int finish,
-                                                   unsigned int part_offset = 0, unsigned int part_total = 0, int do_finish = 1) {
-    if (part_total == 0) part_total = gridDim.x;
+                                                   unsigned int part_offset = 0, unsigned int part_total = 0, int do_finish = 1,
+                                                   unsigned int cta_index = 0xffffffffu, unsigned int n_ctas = 0) {
+    // cta_index / n_ctas: the CTAs that take part (default: the whole grid); self-packing Dslash kernels exclude
+    // their leading pack CTAs.
+    if (n_ctas == 0) { n_ctas = gridDim.x; cta_index = blockIdx.x; }
+    if (part_total == 0) part_total = n_ctas;
     __shared__ double sm[NR][32];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -141,13 +145,13 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
         for (int j = 0; j < NR; j++) {
             double s = 0.0;
             for (int w = 0; w < nwarp; w++) s += sm[j][w];
-            R.partials[(size_t)(part_offset + blockIdx.x) * LQCD_MAX_RED + j] = s;
+            R.partials[(size_t)(part_offset + cta_index) * LQCD_MAX_RED + j] = s;
         }
         is_last = 0;
         if (do_finish) {
             __threadfence();
-            unsigned int t = atomicInc(R.ticket, gridDim.x - 1);
-            is_last = (t == gridDim.x - 1);
+            unsigned int t = atomicInc(R.ticket, n_ctas - 1);
+            is_last = (t == n_ctas - 1);
         }
     }
     __syncthreads();

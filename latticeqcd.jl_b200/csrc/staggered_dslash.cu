@@ -12,6 +12,7 @@
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"
+#include "halo_pack.cuh"
 #include <cstring>
 
 struct StagArgs {
@@ -25,6 +26,7 @@ struct StagArgs {
     DslashFuse fuse;
     Reduce red;
     HaloIn halo;      // MULTI kernel only
+    HaloOut hout;     // MULTI == 2 (self-packing) only
 };
 
 template <int MU, int FWD>
@@ -92,10 +94,16 @@ template <int MULTI>
 __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int cta = blockIdx.x;
+    int bid = blockIdx.x, npack = 0;
+    if (MULTI == 2) {
+        npack = A.hout.cta0[4];
+        if (bid < npack) { halo_pack_cta(A.g, LQCD_STAGGERED, 0, A.in, A.gauge, A.hout, bid); return; }
+        bid -= npack;
+    }
+    int cta = bid;
     if (MULTI) {
-        cta = A.halo.cta_order[blockIdx.x];
-        if ((int)blockIdx.x >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
+        cta = A.halo.cta_order[bid];
+        if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
     }
     const int blk = block_of_warp(A.g, cta, warp);
     const bool active = blk < A.g.nblk;
@@ -140,11 +148,12 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
             dst[base + k * 32] = yk;
         }
     }
-    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only);
+    if (A.fuse.dot_with || A.fuse.want_norm)
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid, gridDim.x - (unsigned)npack);
 }
 
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo) {
+                            const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo, const HaloOut *hout) {
     if (x == y) return lqcd_fail(ctx, LQCD_ERR_ARG, "dslash: in-place application is not allowed");
     StagArgs A;
     A.out = y; A.in = x; A.gauge = ctx->gauge; A.g = ctx->g; A.mass = op->mass; A.sign = dagger ? -1.0 : 1.0;
@@ -152,9 +161,11 @@ int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cpl
     if (fuse) A.fuse = *fuse; else A.fuse = DslashFuse();
     A.red = ctx->red;
     if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
+    if (hout) A.hout = *hout; else memset(&A.hout, 0, sizeof A.hout);
     const int bs = 32 * ctx->g.wpc;
-    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
-    if (halo) staggered_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
+    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
+    if (halo && hout) staggered_dslash_kernel<2><<<grid, bs, 0, s>>>(A);
+    else if (halo) staggered_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
     else      staggered_dslash_kernel<0><<<grid, bs, 0, s>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -16,6 +16,7 @@
 #include "reduce.cuh"
 #include "site_map.cuh"
 #include "wilson_spin.cuh"
+#include "halo_pack.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -112,10 +113,16 @@ template <int DAG, int MAXT, int MINB, int MULTI>
 __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int cta = blockIdx.x;
+    int bid = blockIdx.x, npack = 0;
+    if (MULTI == 2) {      // self-packing: the first npack CTAs ship this application's halo to the neighbours
+        npack = A.hout.cta0[4];
+        if (bid < npack) { halo_pack_cta(A.g, LQCD_WILSON, DAG, A.in, A.gauge, A.hout, bid); return; }
+        bid -= npack;
+    }
+    int cta = bid;
     if (MULTI) {
-        cta = A.halo.cta_order[blockIdx.x];
-        if ((int)blockIdx.x >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
+        cta = A.halo.cta_order[bid];
+        if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
     }
     const int blk = block_of_warp(A.g, cta, warp);
     const bool active = blk < A.g.nblk;
@@ -160,11 +167,12 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
             dst[base + k * 32] = yk;
         }
     }
-    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only);
+    if (A.fuse.dot_with || A.fuse.want_norm)
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid, gridDim.x - (unsigned)npack);
 }
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
-                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo) {
+                         const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo, const HaloOut *hout) {
     if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
     if (op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "clover term not built (csw = %g)", op->csw);
     if (x == y) return lqcd_fail(ctx, LQCD_ERR_ARG, "dslash: in-place application is not allowed");
@@ -174,8 +182,9 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     if (fuse) A.fuse = *fuse; else { A.fuse = DslashFuse(); }
     A.red = ctx->red;
     if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
+    if (hout) A.hout = *hout; else memset(&A.hout, 0, sizeof A.hout);
     const int bs = 32 * ctx->g.wpc;
-    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
+    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
     // register budget variants (tuning knob LQCD_LB = "maxthreads,minblocks"; default picked by measurement)
     static int lb = -1;
     if (lb < 0) {
@@ -187,7 +196,10 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     }
 #define WL(MT, MB)                                                                   \
     do {                                                                             \
-        if (halo) {                                                                  \
+        if (halo && hout) {                                                          \
+            if (dagger) wilson_dslash_kernel<1, MT, MB, 2><<<grid, bs, 0, s>>>(A);   \
+            else        wilson_dslash_kernel<0, MT, MB, 2><<<grid, bs, 0, s>>>(A);   \
+        } else if (halo) {                                                           \
             if (dagger) wilson_dslash_kernel<1, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
             else        wilson_dslash_kernel<0, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
         } else {                                                                     \
