@@ -399,6 +399,11 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     const int slot = (int)(seq & 1);
     A.seq = seq;
     A.hout.seq = seq;
+    {
+        static int gf = -1;
+        if (gf < 0) { const char *e = getenv("LQCD_PACK_FENCE"); gf = (e && e[0] == 'g') ? 1 : 0; }
+        A.hout.gpu_fence = gf;
+    }
     A.hout.ticket = (unsigned int *)(c->base + c->off_ticket);
     A.err = (int *)(c->base + c->off_err);
     A.st = ctx->red.st; A.use_state = fuse ? fuse->use_state : 0;

@@ -122,7 +122,9 @@ __device__ __forceinline__ void halo_pack_cta(const Geom &g, int kind, int dagge
     __syncthreads();
     __shared__ int pack_last;
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        // sys scope: wait here for this CTA's NVLink write acks.  gpu scope (H.gpu_fence): only order the stores before
+        // the ticket; the last CTA observes every ticket and its system-scope fence below is cumulative over them.
+        if (H.gpu_fence) __threadfence(); else __threadfence_system();
         const unsigned int npack = (unsigned int)H.cta0[4];
         pack_last = (atomicInc(H.ticket, npack - 1) == npack - 1);
     }

@@ -231,6 +231,7 @@ struct HaloOut {
     int cta0[5];                         // first pack CTA of direction mu (prefix over partitioned directions), cta0[4] = npack
     unsigned int *ticket;                // last-pack-CTA detector (self resetting)
     unsigned long long seq;              // application number published in the flags
+    int gpu_fence;                       // 1: pack CTAs fence at gpu scope only; the LAST pack CTA's system fence (cumulative) covers them
 };
 
 struct WilsonArgs {
