@@ -431,8 +431,12 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     // Default: SELF-PACKING Dslash kernel -- the first npack CTAs of the kernel itself ship this application's halo
     // (halo_pack.cuh), the interior tiles follow, the face tiles (last) consume the neighbours' slots: one launch,
     // no second stream, no events.  LQCD_SELF_PACK=0 falls back to a separate pack kernel on the priority stream.
-    static int self_pack = -1;
-    if (self_pack < 0) { const char *e = getenv("LQCD_SELF_PACK"); self_pack = (e && atoi(e) == 0) ? 0 : 1; }
+    // Measured (2xB200): local volume 32.32.16.8 -> 39.0 us self-packing vs 41.7 us separate pack; local volume
+    // 32.32.32.16 -> 122.5-126.5 vs 119.9 us (the leading pack CTAs delay the first interior wave).  Default: self-pack
+    // for local volumes up to 2^18 sites, separate pack kernel above; LQCD_SELF_PACK=0/1 forces either.
+    static int self_pack_env = -2;
+    if (self_pack_env == -2) { const char *e = getenv("LQCD_SELF_PACK"); self_pack_env = e ? (atoi(e) != 0) : -1; }
+    const int self_pack = self_pack_env >= 0 ? self_pack_env : (g.V <= (1 << 18));
     if (self_pack) {
         const int bs = 32 * g.wpc;
         HaloOut O = A.hout;

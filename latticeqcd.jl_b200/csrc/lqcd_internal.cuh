@@ -197,6 +197,8 @@ __device__ __forceinline__ cplx cmuli(cplx a) { return make_double2(-a.y, a.x); 
 __device__ __forceinline__ cplx cmulmi(cplx a) { return make_double2(a.y, -a.x); }   // -i*a
 
 __device__ __forceinline__ cplx ldg128(const cplx *p) { return __ldg(p); }
+// pull a line towards L2 without holding a register (epilogue operands of the fused Dslash kernels)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- kernels' host-side entry points (one per .cu) ----------------------------------------------
 struct DslashFuse {

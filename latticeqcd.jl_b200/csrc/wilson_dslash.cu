@@ -138,6 +138,17 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         cplx acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
+        {   // the fused epilogue reads its extra operands ~10 us from now, after the last hop: start them towards L2
+            const size_t pb = (size_t)blk * (12 * 32) + lane;
+            if (A.fuse.axpy_r || A.fuse.dot_with || A.fuse.shift_src) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    if (A.fuse.axpy_r) prefetch_l2(A.fuse.axpy_r + pb + k * 32);
+                    if (A.fuse.dot_with) prefetch_l2(A.fuse.dot_with + pb + k * 32);
+                    if (A.fuse.shift_src) prefetch_l2(A.fuse.shift_src + pb + k * 32);
+                }
+            }
+        }
         hop_pair<0, DAG, MULTI>(acc, A, s, x, A.g.X, 1, x, y, z, t);
         hop_pair<1, DAG, MULTI>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
         hop_pair<2, DAG, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
