@@ -23,7 +23,13 @@ def _deps():
 
 
 def build(force=False, verbose=False):
-    objdir = HERE / "build"
+    # experiment builds: LQCD_BUILD_DEFS="-DLQCD_LINK_HINT=2" LQCD_BUILD_SUFFIX=_hint2 -> liblqcd_b200_hint2.so
+    global OUT
+    defs = os.environ.get("LQCD_BUILD_DEFS", "").split()
+    suffix = os.environ.get("LQCD_BUILD_SUFFIX", "")
+    if suffix:
+        OUT = HERE / f"liblqcd_b200{suffix}.so"
+    objdir = HERE / ("build" + suffix)
     objdir.mkdir(exist_ok=True)
     newest_dep = max(p.stat().st_mtime for p in _deps())
     jobs = []
@@ -31,7 +37,7 @@ def build(force=False, verbose=False):
         s = CSRC / src
         o = objdir / (src + ".o")
         if force or not o.exists() or o.stat().st_mtime < max(s.stat().st_mtime, newest_dep):
-            cmd = [NVCC, *FLAGS, "-c", str(s), "-o", str(o)]
+            cmd = [NVCC, *FLAGS, *defs, "-c", str(s), "-o", str(o)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

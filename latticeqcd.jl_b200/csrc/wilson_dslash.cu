@@ -23,8 +23,24 @@
 
 int launch_wilson_dslash2(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash2.cu
 
+// Cache policy of the link loads.  Links have at most one reuse (as the backward link of the +mu neighbour), spinors up
+// to nine.  Measured on B200 (tools/quick_bench.py): marking link lines evict-first in L1 helps when the local lattice is
+// L2 resident (32.32.16.8: 34.4 -> 31.3 us) and hurts at 32^4 (203 -> 228 us: the backward-link L1 hits are lost and L2
+// is already the bottleneck); L1::no_allocate / spinor evict_last variants were slower in both regimes.  So LH = 1 is
+// selected only for local volumes <= 2^18 sites (the strong-scaling regime).
+template <int LH>
+__device__ __forceinline__ cplx ldlink(const cplx *p) {
+    if (LH == 1) {
+        cplx v;
+        asm("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        return v;
+    }
+    return __ldg(p);
+}
+__device__ __forceinline__ cplx ldspinor(const cplx *p) { return __ldg(p); }
+
 // one of the eight hops.  FWD=1: U_mu(n) x(n+mu) with link at `ls` = n;  FWD=0: U_mu^dag(n-mu) x(n-mu), ls = n-mu.
-template <int MU, int FWD, int DAG>
+template <int MU, int FWD, int DAG, int LH>
 __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in, const cplx *__restrict__ gauge,
                                     int ns, int ls, bool wrapped, double phase) {
     constexpr int S = (FWD ^ DAG) ? -1 : +1;     // D: forward (1-g), backward (1+g); D^dag swaps
@@ -32,8 +48,8 @@ __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in
     cplx h0[3], h1[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        cplx p0 = ldg128(sp + (0 + c) * 32), p1 = ldg128(sp + (3 + c) * 32);
-        cplx p2 = ldg128(sp + (6 + c) * 32), p3 = ldg128(sp + (9 + c) * 32);
+        cplx p0 = ldspinor(sp + (0 + c) * 32), p1 = ldspinor(sp + (3 + c) * 32);
+        cplx p2 = ldspinor(sp + (6 + c) * 32), p3 = ldspinor(sp + (9 + c) * 32);
         project<MU, S>(h0[c], h1[c], p0, p1, p2, p3);
     }
     if (wrapped) {
@@ -47,10 +63,10 @@ __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             if (FWD) {
-                cplx u = ldg128(lk + (a * 3 + b) * 32);
+                cplx u = ldlink<LH>(lk + (a * 3 + b) * 32);
                 cfma(g0, u, h0[b]); cfma(g1, u, h1[b]);
             } else {
-                cplx u = ldg128(lk + (b * 3 + a) * 32);
+                cplx u = ldlink<LH>(lk + (b * 3 + a) * 32);
                 cfmac(g0, u, h0[b]); cfmac(g1, u, h1[b]);
             }
         }
@@ -79,7 +95,7 @@ __device__ __forceinline__ void halo_hop(cplx (&acc)[12], const WilsonArgs &A, i
             cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                cplx u = ldg128(lk + (a * 3 + b) * 32);
+                cplx u = ldlink<0>(lk + (a * 3 + b) * 32);
                 cfma(g0, u, h0[b]); cfma(g1, u, h1[b]);
             }
             reconstruct<MU, S>(acc, a, g0, g1);
@@ -90,26 +106,26 @@ __device__ __forceinline__ void halo_hop(cplx (&acc)[12], const WilsonArgs &A, i
     }
 }
 
-template <int MU, int DAG, int MULTI>
+template <int MU, int DAG, int MULTI, int LH>
 __device__ __forceinline__ void hop_pair(cplx (&acc)[12], const WilsonArgs &A, int s, int coord, int dim, int stride,
                                          int x, int y, int z, int t) {
     // forward
     {
         bool w = (coord == dim - 1);
         int ns = w ? s - (dim - 1) * stride : s + stride;
-        if (!(w && A.g.part[MU])) hop<MU, 1, DAG>(acc, A.in, A.gauge, ns, s, w, A.bc[MU]);
+        if (!(w && A.g.part[MU])) hop<MU, 1, DAG, LH>(acc, A.in, A.gauge, ns, s, w, A.bc[MU]);
         else if (MULTI) halo_hop<MU, 1, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
     // backward
     {
         bool w = (coord == 0);
         int ns = w ? s + (dim - 1) * stride : s - stride;
-        if (!(w && A.g.part[MU])) hop<MU, 0, DAG>(acc, A.in, A.gauge, ns, ns, w, A.bc[MU]);
+        if (!(w && A.g.part[MU])) hop<MU, 0, DAG, LH>(acc, A.in, A.gauge, ns, ns, w, A.bc[MU]);
         else if (MULTI) halo_hop<MU, 0, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
 }
 
-template <int DAG, int MAXT, int MINB, int MULTI>
+template <int DAG, int MAXT, int MINB, int MULTI, int LH>
 __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,10 +165,10 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
                 }
             }
         }
-        hop_pair<0, DAG, MULTI>(acc, A, s, x, A.g.X, 1, x, y, z, t);
-        hop_pair<1, DAG, MULTI>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
-        hop_pair<2, DAG, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
-        hop_pair<3, DAG, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
+        hop_pair<0, DAG, MULTI, LH>(acc, A, s, x, A.g.X, 1, x, y, z, t);
+        hop_pair<1, DAG, MULTI, LH>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
+        hop_pair<2, DAG, MULTI, LH>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
+        hop_pair<3, DAG, MULTI, LH>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
         const size_t base = (size_t)blk * (12 * 32) + lane;
         const double mk = -A.kappa;
         cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
@@ -205,19 +221,20 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
             if (sscanf(e, "%d,%d", &a, &b) == 2) lb = a * 100 + b;
         }
     }
-#define WL(MT, MB)                                                                   \
-    do {                                                                             \
-        if (halo && hout) {                                                          \
-            if (dagger) wilson_dslash_kernel<1, MT, MB, 2><<<grid, bs, 0, s>>>(A);   \
-            else        wilson_dslash_kernel<0, MT, MB, 2><<<grid, bs, 0, s>>>(A);   \
-        } else if (halo) {                                                           \
-            if (dagger) wilson_dslash_kernel<1, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
-            else        wilson_dslash_kernel<0, MT, MB, 1><<<grid, bs, 0, s>>>(A);   \
-        } else {                                                                     \
-            if (dagger) wilson_dslash_kernel<1, MT, MB, 0><<<grid, bs, 0, s>>>(A);   \
-            else        wilson_dslash_kernel<0, MT, MB, 0><<<grid, bs, 0, s>>>(A);   \
-        }                                                                            \
+#define WLK(MT, MB, MU_, LH_)                                                                   \
+    do {                                                                                        \
+        if (dagger) wilson_dslash_kernel<1, MT, MB, MU_, LH_><<<grid, bs, 0, s>>>(A);           \
+        else        wilson_dslash_kernel<0, MT, MB, MU_, LH_><<<grid, bs, 0, s>>>(A);           \
     } while (0)
+#define WL(MT, MB)                                                                              \
+    do {                                                                                        \
+        const int mu_ = (halo && hout) ? 2 : (halo ? 1 : 0);                                    \
+        if (lh) { if (mu_ == 2) WLK(MT, MB, 2, 1); else if (mu_ == 1) WLK(MT, MB, 1, 1); else WLK(MT, MB, 0, 1); } \
+        else    { if (mu_ == 2) WLK(MT, MB, 2, 0); else if (mu_ == 1) WLK(MT, MB, 1, 0); else WLK(MT, MB, 0, 0); } \
+    } while (0)
+    static int lh_env = -2;
+    if (lh_env == -2) { const char *e = getenv("LQCD_LINK_HINT"); lh_env = e ? (atoi(e) != 0) : -1; }
+    const int lh = lh_env >= 0 ? lh_env : (ctx->g.V <= (1 << 18));
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
     // kernel family: 1 = one lane per site (this file, default), 2 = two lanes per site (wilson_dslash2.cu).
     // Measured on B200 at 32^4: family 2 with 16/24/32 warps per SM runs 222/261/355 us against 192 us here --
@@ -233,6 +250,7 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     else if (lb == 25601 || bs > 128) WL(256, 1);
     else WL(128, 3);
 #undef WL
+#undef WLK
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;

@@ -7,10 +7,11 @@ missing or no B200 is visible, loading / context creation raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parents[1]
-SO_PATH = PKG / "liblqcd_b200.so"
+SO_PATH = Path(os.environ["LQCD_B200_LIB"]) if os.environ.get("LQCD_B200_LIB") else PKG / "liblqcd_b200.so"
 HEADER = PKG.parent / "include" / "lqcd_b200.h"
 
 LQCD_OK, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_NOCONV, ERR_NOGPU, ERR_STATE = range(7)
