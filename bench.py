@@ -211,6 +211,8 @@ def run_b200(args, dims):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pg = choose_procgrid(world)
+    if os.environ.get("LQCD_PROCGRID"):          # experiment knob, e.g. LQCD_PROCGRID=1,1,1,8
+        pg = tuple(int(v) for v in os.environ["LQCD_PROCGRID"].split(","))
     ctx = q.get_context(dims, procgrid=pg, rank=rank, device=local_rank)
     if world > 1:
         q.connect_ranks(ctx, dist)
