@@ -92,6 +92,8 @@ __device__ __forceinline__ void apply_finish(int op, const double *tot, SolverSt
         for (int j = 1; j < st->nshift; j++) {
             double ds = st->shift[j] - st->shift[0];
             double z = st->zeta[j], zo = st->zeta_old[j];
+            // heavily shifted systems converge early: their zeta underflows -> freeze (same rule as the oracle)
+            if (fabs(z) < 1e-140) { st->zeta[j] = st->zeta_old[j] = 0.0; st->alpha_s[j] = 0.0; continue; }
             double znew = z * zo * st->alpha_old /
                           (alpha * st->beta_old * (zo - z) + zo * st->alpha_old * (1.0 + ds * alpha));
             st->alpha_s[j] = alpha * znew / z;
@@ -107,6 +109,7 @@ __device__ __forceinline__ void apply_finish(int op, const double *tot, SolverSt
             double beta = c3 / st->rr;
             st->beta = beta; st->beta_s[0] = beta;
             for (int j = 1; j < st->nshift; j++) {
+                if (st->zeta[j] == 0.0) { st->beta_s[j] = 0.0; continue; }      // frozen shift: p_j <- 0
                 double ratio = st->zeta[j] / st->zeta_old[j];
                 st->beta_s[j] = beta * ratio * ratio;
             }

@@ -326,6 +326,9 @@ int orc_mscg(const orc_op *op, int kind, zc *const xs[], const zc *const u[4], c
         /* shifted coefficients (relative shift ds = sigma_j - s0) */
         for (int j = 1; j < nshift; j++) {
             double ds = shifts[j] - s0;
+            /* a heavily shifted system converges long before the base one: its zeta underflows and the recurrence
+             * would produce 0/0.  Freeze it (its residual zeta_j^2 |r|^2 is far below eps by then). */
+            if (fabs(zeta[j]) < 1e-140) { zeta_old[j] = zeta[j] = 0.0; continue; }
             double znew = zeta[j] * zeta_old[j] * alpha_old /
                           (alpha * beta_old * (zeta_old[j] - zeta[j]) + zeta_old[j] * alpha_old * (1.0 + ds * alpha));
             double alpha_j = alpha * znew / zeta[j];
@@ -341,6 +344,7 @@ int orc_mscg(const orc_op *op, int kind, zc *const xs[], const zc *const u[4], c
         xpby(ps[0], r, beta, n);
         for (int j = 1; j < nshift; j++) {
             /* beta_j = beta * (zeta_new/zeta_old_iter)^2 ; p_j = zeta_new r + beta_j p_j */
+            if (zeta[j] == 0.0) continue;            /* frozen shift */
             double ratio = zeta[j] / zeta_old[j];
             double beta_j = beta * ratio * ratio;
             zc *pj = ps[j];
