@@ -7,10 +7,12 @@ A "step" is ONE application y = D x of the Wilson operator (LinearAlgebra.mul!(y
 32^4 lattice (configs[3] volume; 16^4 of configs[1] is L2-resident and is a parity-test size, not a bench line),
 synthetic hot SU(3) links generated on the device (seed 111) and a Gaussian source (seed 112).
 
-  value      whole-job Dslash GFLOP/s = 1368 flop/site x V / (mean CUDA-event time of the K timed
-             applications, max over ranks); inputs resident in HBM; L2 flushed between applications
-             (512 MB memset outside the event brackets).
-  roofline   HBM: achieved = 960 B/site x V / t  against MEASURED_PEAKS.json:hbm_gbs.
+  value      whole-job Dslash GFLOP/s = 1368 flop/site x V / t, t = (one CUDA-event bracket around the K timed
+             back-to-back applications on the library stream) / K, max over ranks; inputs resident in HBM and
+             larger than L2 at N=1 (806 MB vs 126 MB); the L2-flushed per-application time is reported next to it
+             (config.ms_flushed).
+  roofline   HBM: achieved = 960 B/site x V / t  against MEASURED_PEAKS.json:hbm_gbs; traffic = DRAM bytes per
+             launch from the committed ncu capture (profiles/wilson_dslash_traffic.json).
   e2e        the same metric through the reference-facing call with HOST buffers: per step the source is
              copied host->device (pinned), mul_(y, D, x) runs, and the result is copied back.
   cg         CG iterations/s of solve_DinvX_(y, DdagD, b) (device resident and through host buffers).
