@@ -434,6 +434,8 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     // Measured (2xB200): local volume 32.32.16.8 -> 39.0 us self-packing vs 41.7 us separate pack; local volume
     // 32.32.32.16 -> 122.5-126.5 vs 119.9 us (the leading pack CTAs delay the first interior wave).  Default: self-pack
     // for local volumes up to 2^18 sites, separate pack kernel above; LQCD_SELF_PACK=0/1 forces either.
+    static int relaxed_poll = -1;
+    if (relaxed_poll < 0) { const char *e = getenv("LQCD_HALO_POLL"); relaxed_poll = (e && e[0] == 'r') ? 1 : 0; }
     static int self_pack_env = -2;
     if (self_pack_env == -2) { const char *e = getenv("LQCD_SELF_PACK"); self_pack_env = e ? (atoi(e) != 0) : -1; }
     const int self_pack = self_pack_env >= 0 ? self_pack_env : (g.V <= (1 << 18));
@@ -451,6 +453,7 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         }
         H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
         H.timeout_cycles = ctx->red.cr.timeout_cycles;
+        H.relaxed_poll = relaxed_poll;
         if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
         return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
     }
@@ -497,6 +500,7 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         }
         H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
         H.timeout_cycles = ctx->red.cr.timeout_cycles;
+        H.relaxed_poll = relaxed_poll;
         if (tlrec) cudaEventRecord(tl[2][tln], ctx->stream);
         if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
         else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));

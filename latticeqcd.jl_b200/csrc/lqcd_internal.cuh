@@ -95,6 +95,14 @@ struct Reduce {
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// relaxed system-scope load: coherent at L2, no acquire fence (no L1 invalidation on this SM).  Round-2 experiment
+// knob LQCD_HALO_POLL=relaxed: safe together with halo data read through __ldcg (never cached in L1) because the spin
+// loop's control dependency keeps the data loads behind the flag observation.
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -225,6 +233,7 @@ struct HaloIn {
     const int *cta_order;
     int n_interior;
     long long timeout_cycles;
+    int relaxed_poll;                           // 1: poll the flags with ld.relaxed.sys (experiment, default 0 = acquire)
 };
 
 struct HaloOut {

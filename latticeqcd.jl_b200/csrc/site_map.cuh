@@ -45,7 +45,7 @@ __device__ __forceinline__ void wait_halo_flags(const Geom &g, const HaloIn &H) 
         for (int m = 0; m < 4 && good; m++) {
             if (!g.part[m]) continue;
             for (int side = 0; side < 2 && good; side++)
-                while (ld_acquire_sys(H.recv_flag[m][side]) < H.seq)
+                while ((H.relaxed_poll ? ld_relaxed_sys(H.recv_flag[m][side]) : ld_acquire_sys(H.recv_flag[m][side])) < H.seq)
                     if (clock64() - t0 > H.timeout_cycles) { good = false; *H.err = 1000000 + (m * 2 + side) * 100000 + (int)(H.seq % 100000); break; }
         }
     }
