@@ -22,6 +22,7 @@
 #include <cstring>
 
 int launch_wilson_dslash2(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash2.cu
+int launch_wilson_dslash3(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash3.cu (experimental)
 
 // Cache policy of the link loads.  Links have at most one reuse (as the backward link of the +mu neighbour), spinors up
 // to nine.  Measured on B200 (tools/quick_bench.py): marking link lines evict-first in L1 helps when the local lattice is
@@ -241,7 +242,11 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     // more resident warps LOWER the L1 hit rate and the kernel then saturates the ~10.8 TB/s L2->SM fabric
     // (2.1 GB of L2 reads per application at 28 % L1 hits), so occupancy is not the lever; L2 traffic is.
     static int family = -1;
-    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && atoi(e) == 2) ? 2 : 1; }
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && (atoi(e) == 2 || atoi(e) == 3)) ? atoi(e) : 1; }
+    if (family == 3 && !halo) {        // experimental t-marching kernel; falls through when the geometry does not qualify
+        const int rc = launch_wilson_dslash3(ctx, A, dagger, s);
+        if (rc != LQCD_ERR_STATE) return rc;
+    }
     if (family == 2 && !halo && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
