@@ -500,6 +500,30 @@ extern "C" int lqcd_fermion_gaussian(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t se
     return LQCD_OK;
 }
 
+__global__ void fermion_mask_parity_kernel(cplx *f, Geom g, int ncomp, int parity) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // same indexing as fermion_gaussian_kernel
+    if (idx >= g.V * ncomp) return;
+    const int lane = idx & 31, blk = (idx >> 5) / ncomp;
+    int s = blk * 32 + lane;
+    const int x = s % g.X; s /= g.X;
+    const int y = s % g.Y; s /= g.Y;
+    const int z = s % g.Z; const int t = s / g.Z;
+    const int p = (x + g.o[0] + y + g.o[1] + z + g.o[2] + t + g.o[3]) & 1;
+    if (p != parity) f[idx] = make_double2(0.0, 0.0);
+}
+
+extern "C" int lqcd_fermion_mask_parity(lqcd_ctx *ctx, lqcd_fermion *f, int parity) {
+    LQCD_TRY(check_f(ctx, f));
+    if (parity != 0 && parity != 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "parity must be 0 (even) or 1 (odd)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int n = ctx->g.V * f->ncomp, bs = 256;
+    fermion_mask_parity_kernel<<<(n + bs - 1) / bs, bs, 0, ctx->stream>>>(f->d, ctx->g, f->ncomp, parity);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LQCD_OK;
+}
+
 extern "C" int lqcd_fermion_point_source(lqcd_ctx *ctx, lqcd_fermion *f, const int site[4], int color, int spin) {
     LQCD_TRY(check_f(ctx, f));
     const Geom &g = ctx->g;

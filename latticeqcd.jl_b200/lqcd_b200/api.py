@@ -225,6 +225,11 @@ def setindex_global_(b: FermionField, v, ic, ix, iy, iz, it, ialpha):   # measur
     b.ctx.call("lqcd_fermion_point_source", b.h, site, ic - 1, ialpha - 1)
 
 
+def mask_parity_(x: FermionField, parity=0):
+    """keep the sites with (x+y+z+t) % 2 == parity, zero the others (staggered Nf = 4 even-site pseudofermions)."""
+    x.ctx.call("lqcd_fermion_mask_parity", x.h, int(parity))
+
+
 def gauss_distribution_fermion_(x: FermionField, seed=112):
     x.ctx.call("lqcd_fermion_gaussian", x.h, int(seed))
 
@@ -370,7 +375,9 @@ def gauss_sampling_in_action_(xi: FermionField, U, fa: FermiActionB200, seed=112
 
 
 def sample_pseudofermions_(eta: FermionField, U, fa: FermiActionB200, xi: FermionField):   # standardMD.jl:96
-    """Wilson / staggered: eta = D^dag xi  (SURVEY.md App. C.6)."""
+    """Wilson / staggered Nf=8: eta = D^dag xi.  The staggered Nf=4 even-site variant (App. C.7)
+    is NOT wired: its exact upstream convention (which of xi / eta is restricted, and how S_old = xi.xi is kept exact)
+    cannot be established without the LatticeDiracOperators.jl source; the building block is mask_parity_()."""
     fa.D(U)
     mul_(eta, adjoint(fa.D), xi)
 

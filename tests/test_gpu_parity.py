@@ -342,3 +342,26 @@ def test_pseudofermion_heatbath_identity(Uw):
     Snew = q.evaluate_FermiAction(fa, U, eta)
     assert abs(Sold - Snew) < 1e-8 * Sold
     assert abs(Sold - 12 * 256) < 0.1 * 12 * 256          # <xi^dag xi> = number of complex components
+
+
+def test_mask_parity(Us):
+    """lqcd_fermion_mask_parity: even-site restriction (building block of the staggered Nf=4 fields); D^dag D keeps it."""
+    dims = (4, 4, 4, 4)
+    U = q.gaugefields_from_array(Us)
+    x = q.Initialize_pseudofermion_fields(U[0], "staggered")
+    D = q.Dirac_operator(U, x, sparams(0.5))
+    src = orc.gaussian_field(dims, orc.STAGGERED, seed=5)
+    x.from_host(src)
+    q.mask_parity_(x, 0)
+    t, z, y, xx = np.meshgrid(*[np.arange(4)] * 4, indexing="ij")
+    even = ((xx + y + z + t) % 2 == 0)[..., None]
+    assert np.array_equal(x.to_host(), src * even)
+    out = q.similar(x)
+    q.mul_(out, q.DdagD(D), x)
+    assert np.abs(out.to_host() * (~even)).max() == 0.0
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    ref = orc.cg(orc.make_op(dims, mass=0.5), orc.STAGGERED, Us, np.ascontiguousarray(src * even))
+    assert info["iters"] == ref["iters"]
+    assert np.abs(sol.to_host() * (~even)).max() == 0.0
