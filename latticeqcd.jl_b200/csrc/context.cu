@@ -314,7 +314,11 @@ static int alloc_fermion(lqcd_ctx *ctx, int kind, lqcd_fermion **out) {
     f->kind = kind; f->ncomp = ncomp_of(kind); f->owner = ctx;
     f->bytes = (size_t)ctx->g.nblk * f->ncomp * 32 * sizeof(cplx);
     cudaError_t e = cudaMalloc(&f->d, f->bytes);
-    if (e != cudaSuccess) { delete f; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMalloc(%zu) -> %s", f->bytes, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        const size_t want = f->bytes;
+        delete f;
+        return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+    }
     *out = f;
     return LQCD_OK;
 }
