@@ -94,7 +94,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     g.V = (int)V; g.nblk = g.V / 32;
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
-    ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr;
+    ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
     CT(cudaSetDevice(device));
@@ -140,7 +140,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     comm_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
-    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev);
+    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf);
     cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);

@@ -163,9 +163,11 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
         *action = d[0];
     }
     // force field in the device link layout, then the same conversion path as lqcd_gauge_download
-    cplx *fbuf = nullptr;
-    const size_t fbytes = (size_t)ctx->g.nblk * 4 * 9 * 32 * sizeof(cplx);
-    CUDA_TRY(ctx, cudaMalloc(&fbuf, fbytes));
+    if (!ctx->force_buf) {
+        const size_t fbytes = (size_t)ctx->g.nblk * 4 * 9 * 32 * sizeof(cplx);
+        CUDA_TRY(ctx, cudaMalloc(&ctx->force_buf, fbytes));
+    }
+    cplx *fbuf = ctx->force_buf;
     ForceArgs A;
     A.out = fbuf; A.X = X->d; A.Y = Y->d; A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
@@ -177,6 +179,5 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
     int rc = LQCD_OK;
     if (e != cudaSuccess) rc = lqcd_fail(ctx, LQCD_ERR_CUDA, "force kernel -> %s", cudaGetErrorString(e));
     if (rc == LQCD_OK) rc = download_links_from(ctx, fbuf, out_mu, ndw);
-    cudaFree(fbuf);
     return rc;
 }

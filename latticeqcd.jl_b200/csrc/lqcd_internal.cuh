@@ -157,6 +157,7 @@ struct lqcd_ctx {
     std::vector<lqcd_fermion *> scratch[2];
     // L2 flush buffer
     void *flush; size_t flush_bytes;
+    cplx *force_buf;           // link-shaped output of the force kernel (allocated on first use, reused every MD step)
     uint64_t launches;
     int num_sms;
     mutable std::string err;
