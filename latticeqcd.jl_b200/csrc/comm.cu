@@ -14,9 +14,26 @@
 //                    adds the halo contributions to the face sites;
 //   reductions       in-kernel all-reduce (reduce.cuh / CommRed).
 //
-// Halo slots are double buffered by application parity; all spin loops carry a clock64 timeout that turns a
-// lost peer into LQCD_ERR_COMM instead of a hung GPU.  torch.distributed / MPI is used by the HOST only to
-// all-gather the 256-byte handles (lqcd_comm_export -> lqcd_comm_connect) and to barrier.
+// Protocol and why it is safe (k = application number = HaloOut.seq, slot = k & 1):
+//   producer (pack CTAs of rank A, application k)  : peer stores of the face data into B's slot[k&1]; bar.sync; thread 0:
+//       fence (sys) + ticket; the LAST pack CTA: fence.sys, then st.release.sys flag_B[mu][side][k&1] = k.
+//   consumer (face CTAs of rank B, application k)  : thread 0 spins on ld.acquire.sys flag >= k (clock64 timeout ->
+//       error word, never a hang); bar.sync; halo data is read with ld.global.cg (never cached in L1).
+//   write-after-read on a slot: A's pack(k+2) reuses slot[k&1].  It runs after A's Dslash(k+1) finished (stream order),
+//       whose face CTAs waited for B's pack(k+1) flag, which B raises only inside its application k+1, i.e. after B's
+//       Dslash(k) -- the reader of slot[k&1] -- has completed.  Hence two slots suffice.
+//   skipped applications: kernels launched after a solver converged return at once on every rank alike (the converged
+//       flag derives from all-reduced, bit-identical values), so no rank ever waits for a flag that is not raised; flags are
+//       monotonic sequence numbers, a later application simply publishes a larger one.
+//   deadlock freedom: self-packing kernels dispatch their pack CTAs first (lowest blockIdx) and their face CTAs last, pack
+//       CTAs never wait; with the separate pack kernel the pack stream has the highest priority so that its CTAs are
+//       dispatched before the remaining Dslash CTAs.  A rank's application k only needs its neighbours' pack(k), which
+//       needs nothing from this rank's application k.
+//   all-reduce (reduce.cuh): slot = seq % 4 with a per-(slot, writer) sequence flag; a rank can be at most one reduction
+//       ahead of any other (every reduction waits for all ranks), so a slot is never overwritten before it was read.
+// All spin loops carry a clock64 timeout (LQCD_COMM_TIMEOUT_S, default 20 s) that turns a lost peer into LQCD_ERR_COMM
+// instead of a hung GPU.  torch.distributed / MPI is used by the HOST only to all-gather the 256-byte handles
+// (lqcd_comm_export -> lqcd_comm_connect) and to barrier.
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "wilson_spin.cuh"
