@@ -41,6 +41,14 @@ KAPPA = 0.12
 BC = [1, 1, 1, -1]
 
 
+def metric_name():
+    """BASELINE.json's metric string (the Dslash GFLOP/s part is `value`, the CG part is reported under "cg")."""
+    try:
+        return json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+    except Exception:
+        return "Wilson Dslash GFLOP/s & CG iters/s at 32^4, 1/2/4/8 B200 vs CPU ref"
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -102,7 +110,7 @@ def run_reference(args, dims):
     r = cpu_dslash(dims, steps, warm, thr)
     V = dims[0] * dims[1] * dims[2] * dims[3]
     line = {
-        "impl": "reference", "metric": "Wilson Dslash GFLOP/s at 32^4 fp64", "value": r["gflops"], "unit": "GFLOP/s",
+        "impl": "reference", "metric": metric_name(), "value": r["gflops"], "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Wilson Dslash mul!(y,D,x), {args.lattice}, kappa={KAPPA}, bc={BC}, CPU oracle port of the reference's Julia path"},
@@ -351,7 +359,7 @@ def run_b200(args, dims):
     if tp.exists():
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     line = {
-        "metric": "Wilson Dslash GFLOP/s at 32^4 fp64", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(), "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Wilson Dslash mul!(y,D,x) {args.lattice} SU(3) hot links, kappa={KAPPA}, r=1, bc={BC}",
