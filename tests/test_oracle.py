@@ -237,3 +237,31 @@ def test_force_finite_difference(Uw, Us, kind):
             vals.append(action(np.ascontiguousarray(U2))[0])
         fd = (vals[0] - vals[1]) / (2 * h)
         assert abs(fd - want) < 1e-6 * max(1.0, abs(want)), (fd, want)
+
+
+def test_oracle_regression(golden_dir, Uw, Us):
+    """Freezes the oracle (tests/golden/oracle_regression.json, written by make_oracle_regression.py from the oracle
+    itself -- not reference data): the checker of every GPU parity test must not drift unnoticed."""
+    ref = json.loads((golden_dir / "oracle_regression.json").read_text())
+    opw, ops = orc.make_op(DIMS, kappa=KAPPA), orc.make_op(DIMS, mass=0.5)
+    pw, ps = orc.gaussian_field(DIMS, orc.WILSON, seed=112), orc.gaussian_field(DIMS, orc.STAGGERED, seed=112)
+
+    def sig(a):
+        a = np.asarray(a).ravel()
+        w = np.cos(np.arange(a.size) * 0.37) + 1j * np.sin(np.arange(a.size) * 0.11)
+        return np.array([np.vdot(a, a).real, np.vdot(w, a).real, np.vdot(w, a).imag])
+
+    def close(name, a, tol=1e-10):
+        want = np.array([ref[name]["norm2"], ref[name]["probe_re"], ref[name]["probe_im"]])
+        assert np.allclose(sig(a), want, rtol=tol, atol=tol * abs(want).max()), name
+
+    close("wilson_D", orc.apply(opw, orc.WILSON, orc.D, Uw, pw))
+    close("wilson_Ddag", orc.apply(opw, orc.WILSON, orc.DDAG, Uw, pw))
+    close("stag_D", orc.apply(ops, orc.STAGGERED, orc.D, Us, ps))
+    r = orc.cg(opw, orc.WILSON, Uw, pw)
+    assert r["iters"] == ref["wilson_cg"]["iters"] == 114          # also the count the GPU reproduces (smoke)
+    close("wilson_cg", r["x"], 1e-8)
+    r = orc.cgnr(opw, orc.WILSON, Uw, orc.point_source(DIMS, orc.WILSON, 0, 0))
+    assert r["iters"] == ref["wilson_cgnr_point"]["iters"]
+    r = orc.cg(ops, orc.STAGGERED, Us, ps)
+    assert r["iters"] == ref["stag_cg"]["iters"]
