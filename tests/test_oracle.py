@@ -259,7 +259,7 @@ def test_oracle_regression(golden_dir, Uw, Us):
     close("wilson_Ddag", orc.apply(opw, orc.WILSON, orc.DDAG, Uw, pw))
     close("stag_D", orc.apply(ops, orc.STAGGERED, orc.D, Us, ps))
     r = orc.cg(opw, orc.WILSON, Uw, pw)
-    assert r["iters"] == ref["wilson_cg"]["iters"] == 114          # also the count the GPU reproduces (smoke)
+    assert r["iters"] == ref["wilson_cg"]["iters"]
     close("wilson_cg", r["x"], 1e-8)
     r = orc.cgnr(opw, orc.WILSON, Uw, orc.point_source(DIMS, orc.WILSON, 0, 0))
     assert r["iters"] == ref["wilson_cgnr_point"]["iters"]
