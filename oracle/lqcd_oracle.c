@@ -72,6 +72,7 @@ static inline int64_t nbr(const geom *g, int64_t s, const int c[4], int mu, int 
  *  spinor when the shift wraps (upstream applies it when filling the fermion "wing").                    */
 static void wilson_apply(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x) {
     geom g = mkgeom(op->dims);
+    if (op->csw != 0.0 && !op->clov) abort();      /* orc_clover_build first */
     const int64_t V = g.V;
     const zc (*Gf)[4][4] = dagger ? op->rplusg : op->rminusg;   /* multiplies the forward hop */
     const zc (*Gb)[4][4] = dagger ? op->rminusg : op->rplusg;   /* multiplies the backward hop */
@@ -114,6 +115,16 @@ static void wilson_apply(const orc_op *op, int dagger, zc *y, const zc *const u[
                     acc[al][a] += kappa * t1 + kappa * t2;
                 }
         }
+        if (op->csw != 0.0) {       /* Wilson-clover: y = A(n) x(n) - acc, A block diagonal in chirality (spins 01 | 23) */
+            const zc *A = op->clov + 72 * s;
+            for (int blk = 0; blk < 2; blk++)
+                for (int i = 0; i < 6; i++) {
+                    zc sum = 0;
+                    for (int j = 0; j < 6; j++)
+                        sum += A[36 * blk + i + 6 * j] * x[(j % 3) + 3 * (s + V * (2 * blk + j / 3))];
+                    y[(i % 3) + 3 * (s + V * (2 * blk + i / 3))] = sum - acc[2 * blk + i / 3][i % 3];
+                }
+        } else
         for (int al = 0; al < 4; al++)
             for (int a = 0; a < 3; a++)
                 y[a + 3 * (s + V * al)] = x[a + 3 * (s + V * al)] - acc[al][a];
@@ -477,5 +488,82 @@ void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4
                     out[mu][a + 3 * (b + 3 * s)] =
                         0.5 * eta * (hX[a] * conj(Y[b + 3 * s]) + X[a + 3 * s] * conj(hY[b]));
         }
+    }
+}
+
+/* ---- clover term (Wilson-clover; NEW capability, not reachable from run_LQCD at this commit: universe.jl:106-131,
+ *      parameter parsed at parameter_structs.jl:125).  In-tree evidence used: the four-leaf clover of the (dead)
+ *      topological-charge code, src/measurements/unusedfiles/measure_topological_charge.jl:299-309 (leaf paths),
+ *      :177-200 (traceless anti-Hermitian part, /numofloops=4).  Normalisation of the term itself: see orc_op.csw. */
+static void mulx(zc *c, const zc *a, int adja, const zc *b, int adjb) {      /* c = op(a) op(b), [row + 3 col] */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        zc s = 0;
+        for (int k = 0; k < 3; k++) {
+            zc av = adja ? conj(a[k + 3 * i]) : a[i + 3 * k];
+            zc bv = adjb ? conj(b[j + 3 * k]) : b[k + 3 * j];
+            s += av * bv;
+        }
+        c[i + 3 * j] = s;
+    }
+}
+static int64_t hopsite(const geom *g, int64_t s, int c[4], int mu, int sign) {   /* moves c[] too */
+    int w; int64_t ns = nbr(g, s, c, mu, sign, &w);
+    c[mu] = (c[mu] + sign + g->d[mu]) % g->d[mu];
+    return ns;
+}
+/* ordered product along a closed path starting at n: steps (dir, +1/-1) */
+static void path_product(const geom *g, const zc *const u[4], int64_t s, const int c0[4], const int dir[4], const int sgn[4], zc out[9]) {
+    int c[4] = {c0[0], c0[1], c0[2], c0[3]};
+    zc acc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tmp[9];
+    for (int k = 0; k < 4; k++) {
+        if (sgn[k] > 0) { mulx(tmp, acc, 0, u[dir[k]] + 9 * s, 0); s = hopsite(g, s, c, dir[k], +1); }
+        else            { s = hopsite(g, s, c, dir[k], -1); mulx(tmp, acc, 0, u[dir[k]] + 9 * s, 1); }
+        memcpy(acc, tmp, sizeof acc);
+    }
+    memcpy(out, acc, sizeof acc);
+}
+void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4]) {
+    geom g = mkgeom(op->dims);
+    const double coef = op->kappa * op->csw;
+    /* sigma_mu_nu = (i/2)[g_mu, g_nu] from the operator's own gamma tables */
+    zc gam[4][4][4], sig[6][4][4];
+    for (int mu = 0; mu < 4; mu++) for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++)
+        gam[mu][a][b] = 0.5 * (op->rplusg[mu][a][b] - op->rminusg[mu][a][b]);
+    int pl = 0;
+    for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++, pl++)
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) {
+            zc s = 0;
+            for (int k = 0; k < 4; k++) s += gam[mu][a][k] * gam[nu][k][b] - gam[nu][a][k] * gam[mu][k][b];
+            sig[pl][a][b] = 0.5 * I * s;
+        }
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < g.V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        zc F[6][9];
+        int p = 0;
+        for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++, p++) {
+            const int d1[4] = {mu, nu, mu, nu}, s1[4] = {+1, +1, -1, -1};
+            const int d2[4] = {nu, mu, nu, mu}, s2[4] = {+1, -1, -1, +1};
+            const int d3[4] = {mu, nu, mu, nu}, s3[4] = {-1, -1, +1, +1};
+            const int d4[4] = {nu, mu, nu, mu}, s4[4] = {-1, +1, +1, -1};
+            zc q[9], Q[9] = {0};
+            path_product(&g, u, s, c, d1, s1, q); for (int k = 0; k < 9; k++) Q[k] += q[k];
+            path_product(&g, u, s, c, d2, s2, q); for (int k = 0; k < 9; k++) Q[k] += q[k];
+            path_product(&g, u, s, c, d3, s3, q); for (int k = 0; k < 9; k++) Q[k] += q[k];
+            path_product(&g, u, s, c, d4, s4, q); for (int k = 0; k < 9; k++) Q[k] += q[k];
+            zc tr = 0;
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) F[p][a + 3 * b] = (Q[a + 3 * b] - conj(Q[b + 3 * a])) / 8.0;
+            for (int a = 0; a < 3; a++) tr += F[p][a + 3 * a];
+            for (int a = 0; a < 3; a++) F[p][a + 3 * a] -= tr / 3.0;
+            if (fmunu) memcpy(fmunu + (s * 6 + p) * 9, F[p], sizeof F[p]);
+        }
+        zc *A = clov + 72 * s;
+        for (int blk = 0; blk < 2; blk++)
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+                zc sum = (i == j) ? 1.0 : 0.0;
+                for (p = 0; p < 6; p++)
+                    sum += coef * sig[p][2 * blk + i / 3][2 * blk + j / 3] * (I * F[p][(i % 3) + 3 * (j % 3)]);
+                A[36 * blk + i + 6 * j] = sum;
+            }
     }
 }

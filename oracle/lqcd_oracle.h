@@ -38,8 +38,14 @@ typedef struct {
     zc rminusg[4][4][4];    /* r*1 - gamma_mu  ("rminusγ") */
     /* staggered */
     double mass;            /* universe.jl:109 */
-    /* Wilson clover (new capability, unpinned): csw = 0 disables */
+    /* Wilson clover (new capability, unpinned -- SURVEY.md 8a "not reachable from run_LQCD"): csw = 0 disables.
+     * Convention (textbook / openQCD, isolated in orc_clover_build):
+     *   M = A - kappa*H,  A(n) = 1 + kappa*csw * sum_{mu<nu} sigma_mu_nu (x) [i F^_mu_nu(n)],
+     *   sigma_mu_nu = (i/2)[gamma_mu, gamma_nu],  F^ = (Q - Q^dag)/8 made traceless, Q = sum of the four plaquette leaves
+     *   (leaf order of src/measurements/unusedfiles/measure_topological_charge.jl:299-309). */
     double csw;
+    const zc *clov;         /* V*72 complex: per site two dense 6x6 blocks (chirality +,-), [i + 6 j], i = 3*spin_in_block + colour;
+                               filled by orc_clover_build; must be set when csw != 0 */
 } orc_op;
 
 enum { ORC_WILSON = 0, ORC_STAGGERED = 1 };
@@ -79,8 +85,8 @@ void orc_wilson_force(const orc_op *op, zc *const out[4], const zc *const u[4], 
 /* staggered analogue */
 void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y);
 
-/* clover term support (Wilson-clover, new capability): builds the 4 V (6x6 hermitian x2) packed as
- * full 12x12 block-diagonal-in-chirality matrices: clov[site*72*... ] -- see lqcd_oracle.c */
-void orc_clover_build(const orc_op *op, zc *clov /* V*2*36 */, const zc *const u[4]);
+/* clover term A(n) (see orc_op.csw): clov[site*72 + blk*36 + i + 6*j].  fmunu (nullable, V*6*9, plane order
+ * (0,1),(0,2),(0,3),(1,2),(1,3),(2,3), [a + 3 b]) receives F^_mu_nu for tests. */
+void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4]);
 
 #endif

@@ -35,6 +35,7 @@ class OrcOp(C.Structure):
         ("rminusg", C.c_double * (4 * 4 * 4 * 2)),
         ("mass", C.c_double),
         ("csw", C.c_double),
+        ("clov", C.c_void_p),
     ]
 
 
@@ -72,6 +73,7 @@ def lib() -> C.CDLL:
         L.orc_plaquette.argtypes = [C.POINTER(ci), pp]; L.orc_plaquette.restype = dbl
         L.orc_wilson_force.argtypes = [op, pp, pp, vp, vp]
         L.orc_staggered_force.argtypes = [op, pp, pp, vp, vp]
+        L.orc_clover_build.argtypes = [op, vp, vp, pp]
         _LIB = L
     return _LIB
 
@@ -159,6 +161,18 @@ def mscg(op, kind, U, b, shifts, eps=1e-19, maxsteps=3000):
                         shifts.ctypes.data_as(C.POINTER(C.c_double)), len(xs), float(eps), int(maxsteps),
                         C.byref(rs))
     return {"xs": xs, "iters": it, "resid_sq": rs.value, "converged": it >= 0}
+
+
+def clover_build(op: OrcOp, U: np.ndarray, want_f=False):
+    """Builds the clover term A(n) for op (kappa, csw, gamma tables) and attaches it to op (op.clov points into the
+    returned array, which is also kept alive on the op object).  Returns clov [V, 2, 6(j), 6(i)] (and F^ [V,6,3(b),3(a)])."""
+    V = int(np.prod([op.dims[i] for i in range(4)]))
+    clov = np.zeros((V, 2, 6, 6), dtype=np.complex128)
+    f = np.zeros((V, 6, 3, 3), dtype=np.complex128) if want_f else None
+    lib().orc_clover_build(C.byref(op), clov.ctypes.data, f.ctypes.data if want_f else None, _uptrs(U))
+    op._clov_keepalive = clov
+    op.clov = clov.ctypes.data
+    return (clov, f) if want_f else clov
 
 
 def plaquette(dims, U) -> float:

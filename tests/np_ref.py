@@ -74,3 +74,52 @@ def gauge_transform(U, g):
         gf = np.roll(g, -1, axis=AX[mu])
         out[mu] = g @ M[mu] @ np.conj(np.swapaxes(gf, -1, -2))
     return np.ascontiguousarray(np.swapaxes(out, -1, -2))
+
+
+# ---- Wilson-clover (new capability; convention in oracle/lqcd_oracle.h orc_op.csw) -----------------------------
+PLANES = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+def _at(M, *steps):
+    """field M[t,z,y,x,...] evaluated at n + sum of steps (mu, s)"""
+    for mu, s in steps:
+        M = np.roll(M, -s, axis=AX[mu])
+    return M
+
+
+def _dag(M):
+    return np.conj(np.swapaxes(M, -1, -2))
+
+
+def fmunu(U, traceless=True):
+    """F^_mu_nu = (Q - Q^dag)/8 per plane, Q = four leaves; returns [plane, t,z,y,x, a, b]"""
+    M = links_mat(U)
+    out = []
+    for mu, nu in PLANES:
+        Um, Un = M[mu], M[nu]
+        Q = Um @ _at(Un, (mu, 1)) @ _dag(_at(Um, (nu, 1))) @ _dag(Un)
+        Q = Q + Un @ _dag(_at(Um, (mu, -1), (nu, 1))) @ _dag(_at(Un, (mu, -1))) @ _at(Um, (mu, -1))
+        Q = Q + _dag(_at(Um, (mu, -1))) @ _dag(_at(Un, (mu, -1), (nu, -1))) @ _at(Um, (mu, -1), (nu, -1)) @ _at(Un, (nu, -1))
+        Q = Q + _dag(_at(Un, (nu, -1))) @ _at(Um, (nu, -1)) @ _at(Un, (mu, 1), (nu, -1)) @ _dag(Um)
+        F = (Q - _dag(Q)) / 8
+        if traceless:
+            F = F - np.trace(F, axis1=-2, axis2=-1)[..., None, None] * np.eye(3) / 3
+        out.append(F)
+    return np.array(out)
+
+
+def sigma(mu, nu):
+    return 0.5j * (G[mu] @ G[nu] - G[nu] @ G[mu])
+
+
+def clover_term(U, psi, kappa, csw):
+    """(A - 1) psi = kappa csw sum_{mu<nu} sigma_mu_nu (x) (i F^_mu_nu) psi"""
+    F = fmunu(U)
+    out = np.zeros_like(psi)
+    for p, (mu, nu) in enumerate(PLANES):
+        out += kappa * csw * np.einsum("sr,tzyxab,rtzyxb->stzyxa", sigma(mu, nu), 1j * F[p], psi)
+    return out
+
+
+def wilson_clover(U, psi, kappa, csw, r=1.0, bc=(1, 1, 1, -1), dagger=False):
+    return wilson(U, psi, kappa, r, bc, dagger) + clover_term(U, psi, kappa, csw)

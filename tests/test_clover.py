@@ -1,0 +1,118 @@
+"""
+Wilson-clover oracle checks (CPU).  The clover term is NEW capability (not reachable from run_LQCD at the
+surveyed commit), so it is pinned by construction-independent properties and an independent numpy restatement:
+leaf geometry on a constant-field-strength background, Hermiticity / gamma5-Hermiticity, gauge covariance, dense numpy.
+"""
+import numpy as np
+import pytest
+
+import np_ref
+from oracle import oracle as orc
+
+DIMS = (4, 4, 4, 4)
+KAPPA, CSW = 0.125, 1.5612      # csw: reference default, src/system/parameter_structs.jl:125
+
+
+def fields(seed=21, dims=DIMS, eps=None):
+    U = orc.random_su3(dims, seed=seed, eps=eps)
+    psi = orc.gaussian_field(dims, orc.WILSON, seed=seed + 1)
+    return U, psi
+
+
+def test_sigma_is_chirality_block_diagonal_and_hermitian():
+    for mu, nu in np_ref.PLANES:
+        s = np_ref.sigma(mu, nu)
+        assert np.abs(s - s.conj().T).max() < 1e-15
+        assert np.abs(s[:2, 2:]).max() == 0 and np.abs(s[2:, :2]).max() == 0
+        assert np.abs(np_ref.G5 @ s - s @ np_ref.G5).max() == 0
+
+
+def test_fmunu_matches_numpy_and_is_antihermitian_traceless():
+    U, _ = fields()
+    op = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    clov, F = orc.clover_build(op, U, want_f=True)
+    Fo = np.swapaxes(F.reshape(4, 4, 4, 4, 6, 3, 3), -1, -2)               # [t,z,y,x,plane,a,b]
+    Fn = np.moveaxis(np_ref.fmunu(U), 0, 4)
+    assert np.abs(Fo - Fn).max() < 1e-14
+    assert np.abs(Fo + np.conj(np.swapaxes(Fo, -1, -2))).max() < 1e-15
+    assert np.abs(np.trace(Fo, axis1=-2, axis2=-1)).max() < 1e-15
+    A = np.swapaxes(clov, -1, -2)                                           # [V, blk, i, j]
+    assert np.abs(A - np.conj(np.swapaxes(A, -1, -2))).max() < 1e-15        # Hermitian 6x6 blocks
+
+
+def test_constant_field_strength_background():
+    """Abelian background with uniform plaquette exp(i theta T) in the (x,y) plane: every leaf equals the plaquette,
+    so F^_xy = i sin(theta T) (made traceless) and all other planes vanish."""
+    X, Y, Z, T = dims = (4, 6, 2, 2)
+    theta = 2 * np.pi / (X * Y)
+    Tg = np.array([1.0, 1.0, -2.0])
+    M = np.zeros((4, T, Z, Y, X, 3, 3), dtype=complex)
+    M[..., :, :] = np.eye(3)
+    ys, xs = np.arange(Y), np.arange(X)
+    for c in range(3):
+        M[0, :, :, :, :, c, c] = np.exp(-1j * theta * Tg[c] * ys)[None, None, :, None]
+        M[1, :, :, Y - 1, :, c, c] = np.exp(1j * theta * Tg[c] * Y * xs)[None, None, :]
+    U = np.ascontiguousarray(np.swapaxes(M, -1, -2))
+    assert abs(orc.plaquette(dims, U) - (5 + np.cos(theta * Tg).sum() / 3) / 6) < 1e-14
+    op = orc.make_op(dims, kappa=KAPPA, csw=CSW)
+    _, F = orc.clover_build(op, U, want_f=True)
+    want = 1j * np.sin(theta * Tg)
+    want = want - want.sum() / 3
+    for p in range(6):
+        for a in range(3):
+            for b in range(3):
+                w = want[a] if (p == 0 and a == b) else 0.0
+                assert np.abs(F[:, p, b, a] - w).max() < 1e-14, (p, a, b)
+
+
+@pytest.mark.parametrize("dagger", [False, True])
+def test_apply_matches_numpy(dagger):
+    U, psi = fields()
+    op = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    orc.clover_build(op, U)
+    got = orc.apply(op, orc.WILSON, orc.DDAG if dagger else orc.D, U, psi)
+    want = np_ref.wilson_clover(U, psi, KAPPA, CSW, dagger=dagger)
+    assert np.abs(got - want).max() < 1e-13
+    plain = orc.apply(orc.make_op(DIMS, kappa=KAPPA), orc.WILSON, orc.D, U, psi)
+    assert np.abs(got - plain).max() > 1e-3            # the term is really there
+
+
+def test_adjoint_and_gamma5_hermiticity():
+    U, a = fields(seed=5)
+    b = orc.gaussian_field(DIMS, orc.WILSON, seed=77)
+    op = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    orc.clover_build(op, U)
+    Mb = orc.apply(op, orc.WILSON, orc.D, U, b)
+    Mda = orc.apply(op, orc.WILSON, orc.DDAG, U, a)
+    assert abs(np.vdot(a, Mb) - np.vdot(Mda, b)) < 1e-11
+    g5 = np.array([1, 1, -1, -1])[:, None, None, None, None, None]
+    g5Mg5a = g5 * orc.apply(op, orc.WILSON, orc.D, U, g5 * a)
+    assert np.abs(g5Mg5a - Mda).max() < 1e-13
+
+
+def test_gauge_covariance():
+    U, psi = fields(seed=9)
+    rng = np.random.default_rng(3)
+    h = rng.standard_normal((4, 4, 4, 4, 3, 3)) + 1j * rng.standard_normal((4, 4, 4, 4, 3, 3))
+    q, _ = np.linalg.qr(h)
+    g = q / np.linalg.det(q)[..., None, None] ** (1 / 3)
+    Ug = np_ref.gauge_transform(U, g)
+    gpsi = np.einsum("tzyxab,stzyxb->stzyxa", g, psi)
+    op = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    orc.clover_build(op, U)
+    lhs_src = orc.apply(op, orc.WILSON, orc.D, U, psi)
+    op2 = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    orc.clover_build(op2, Ug)
+    rhs = orc.apply(op2, orc.WILSON, orc.D, Ug, np.ascontiguousarray(gpsi))
+    lhs = np.einsum("tzyxab,stzyxb->stzyxa", g, lhs_src)
+    assert np.abs(lhs - rhs).max() < 1e-13
+
+
+def test_cg_true_residual_with_clover():
+    U, b = fields(seed=31, eps=0.4)
+    op = orc.make_op(DIMS, kappa=0.12, csw=CSW)
+    orc.clover_build(op, U)
+    res = orc.cg(op, orc.WILSON, U, b, eps=1e-20)
+    assert res["converged"]
+    r = b - orc.apply(op, orc.WILSON, orc.DDAGD, U, res["x"])
+    assert np.vdot(r, r).real < 1e-18
