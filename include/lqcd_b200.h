@@ -114,6 +114,15 @@ int lqcd_blas_norm2(lqcd_ctx *ctx, const lqcd_fermion *a, double *out);
 /* ---- operator application: LinearAlgebra.mul!(y, D, x), mul!(y, D', x), mul!(y, DdagD, x) -------- */
 int lqcd_dslash(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode);
 
+/* ---- Wilson-clover term (op->csw != 0; NEW capability: BASELINE.json configs[3]; the surveyed wrapper parses
+ *      Clover_coefficient at src/system/parameter_structs.jl:125 but cannot reach a clover operator, universe.jl:106-131).
+ *      A(n) = 1 + kappa*csw*sum_{mu<nu} sigma_mu_nu (x) i F^_mu_nu(n), four-leaf F^ as in
+ *      src/measurements/unusedfiles/measure_topological_charge.jl:299-309.  The term is (re)built lazily from the device
+ *      links by the first lqcd_dslash / lqcd_solve that uses csw != 0 after a gauge upload; this call forces the build and,
+ *      when out != NULL, returns the dense blocks out[((site*2 + b)*36 + i + 6*j)] (complex re,im; b = chirality block,
+ *      i = 3*spin_in_block + colour).  Multi-rank: all ranks must have finished lqcd_gauge_upload (host barrier) first. */
+int lqcd_clover_term(lqcd_ctx *ctx, const lqcd_op *op, double *out);
+
 /* ---- solvers: solve_DinvX!(y, A, x) (measure_Pion_correlator.jl:399, measure_chiral_condensate.jl:182;
  *      inside calc_UdSfdU! AbstractMD.jl:129 and evaluate_FermiAction standardHMC.jl:69-71) ---------
  * y is initial guess and result.  eps is compared with the ABSOLUTE SQUARED residual (params["eps_CG"],

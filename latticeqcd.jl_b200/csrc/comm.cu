@@ -54,6 +54,10 @@ struct HandleBlob {
     uint64_t raw_ptr;
     uint64_t bytes;
     cudaIpcMemHandle_t ipc;
+    // link array of the rank (read by peers' setup kernels that need links beyond the local lattice: clover leaves)
+    uint32_t has_gauge; uint32_t pad2;
+    uint64_t gauge_raw;
+    cudaIpcMemHandle_t gauge_ipc;
 };
 static_assert(sizeof(HandleBlob) <= LQCD_IPC_HANDLE_BYTES, "handle blob too large");
 #define LQCD_HANDLE_MAGIC 0x4c514344u
@@ -74,6 +78,8 @@ struct CommState {
     int nbsites;
     int *cta_order;                   // Dslash CTA permutation: tiles without face sites first, face tiles last
     int n_interior;
+    const cplx *gauge_peer[LQCD_MAX_RANKS];   // every rank's link array (nullptr where the mapping failed)
+    bool gauge_opened[LQCD_MAX_RANKS];
 };
 
 static int rank_of(const lqcd_ctx *ctx, const int pc[4]) {
@@ -157,6 +163,8 @@ int comm_destroy(lqcd_ctx *ctx) {
     if (!c) return LQCD_OK;
     for (int r = 0; r < ctx->nranks; r++)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    for (int r = 0; r < ctx->nranks; r++)
+        if (c->gauge_opened[r]) cudaIpcCloseMemHandle((void *)c->gauge_peer[r]);
     cudaFree(c->base);
     cudaFree(c->bsites);
     cudaFree(c->cta_order);
@@ -174,6 +182,9 @@ extern "C" int lqcd_comm_export(lqcd_ctx *ctx, void *handle_out) {
     b.magic = LQCD_HANDLE_MAGIC; b.rank = ctx->rank; b.pid = (int64_t)getpid(); b.device = ctx->device;
     b.raw_ptr = (uint64_t)(uintptr_t)ctx->comm->base; b.bytes = ctx->comm->bytes;
     CUDA_TRY(ctx, cudaIpcGetMemHandle(&b.ipc, ctx->comm->base));
+    // optional second mapping (never fatal: only the multi-rank clover build needs it)
+    if (cudaIpcGetMemHandle(&b.gauge_ipc, ctx->gauge) == cudaSuccess) { b.has_gauge = 1; b.gauge_raw = (uint64_t)(uintptr_t)ctx->gauge; }
+    else cudaGetLastError();
     memset(handle_out, 0, LQCD_IPC_HANDLE_BYTES);
     memcpy(handle_out, &b, sizeof b);
     return LQCD_OK;
@@ -206,7 +217,17 @@ extern "C" int lqcd_comm_connect(lqcd_ctx *ctx, const void *all_handles) {
             if (e != cudaSuccess) return lqcd_fail(ctx, LQCD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) -> %s (NVLink/P2P peer access is required)", r, cudaGetErrorString(e));
             c->peer[r] = (char *)p; c->opened[r] = true;
         }
+        // link array of rank r (optional; failures leave gauge_peer[r] null and only disable the multi-rank clover build)
+        if (b.has_gauge && !c->gauge_peer[r]) {
+            if (b.pid == (int64_t)getpid()) c->gauge_peer[r] = (const cplx *)(uintptr_t)b.gauge_raw;
+            else {
+                void *p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, b.gauge_ipc, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) { c->gauge_peer[r] = (const cplx *)p; c->gauge_opened[r] = true; }
+                else cudaGetLastError();
+            }
+        }
     }
+    c->gauge_peer[ctx->rank] = ctx->gauge;
     CommRed &cr = ctx->red.cr;
     cr.nranks = ctx->nranks; cr.rank = ctx->rank;
     cr.seq = (unsigned long long *)(c->base + c->off_seq);
@@ -221,6 +242,17 @@ extern "C" int lqcd_comm_connect(lqcd_ctx *ctx, const void *all_handles) {
         cr.flags[r] = (unsigned long long *)(c->peer[r] + c->off_red_flags);
     }
     c->connected = true;
+    return LQCD_OK;
+}
+
+// every rank's link array as seen from this GPU.  The CALLER must have barriered the ranks after their gauge uploads.
+int comm_link_view(lqcd_ctx *ctx, const cplx **bases) {
+    CommState *c = ctx->comm;
+    if (!c || !c->connected) return lqcd_fail(ctx, LQCD_ERR_COMM, "multi-rank context is not connected (lqcd_comm_export / lqcd_comm_connect)");
+    for (int r = 0; r < ctx->nranks; r++) {
+        if (!c->gauge_peer[r]) return lqcd_fail(ctx, LQCD_ERR_COMM, "link array of rank %d is not peer mapped (clover build across ranks needs it)", r);
+        bases[r] = c->gauge_peer[r];
+    }
     return LQCD_OK;
 }
 

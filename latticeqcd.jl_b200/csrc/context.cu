@@ -95,6 +95,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr;
+    ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
     CT(cudaSetDevice(device));
@@ -140,7 +141,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     comm_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
-    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf);
+    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->clover);
     cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);
@@ -270,7 +271,7 @@ extern "C" int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->gauge_valid = true;
+    ctx->gauge_valid = true; ctx->gauge_epoch++;
     return LQCD_OK;
 }
 
@@ -478,7 +479,7 @@ extern "C" int lqcd_gauge_random(lqcd_ctx *ctx, uint64_t seed, double warm_eps) 
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->gauge_valid = true;
+    ctx->gauge_valid = true; ctx->gauge_epoch++;
     return LQCD_OK;
 }
 

@@ -158,6 +158,9 @@ struct lqcd_ctx {
     // L2 flush buffer
     void *flush; size_t flush_bytes;
     cplx *force_buf;           // link-shaped output of the force kernel (allocated on first use, reused every MD step)
+    uint64_t gauge_epoch;      // bumped by every lqcd_gauge_upload / lqcd_gauge_random
+    cplx *clover;              // packed clover term (clover.cu), valid for (clover_epoch, clover_coef)
+    uint64_t clover_epoch; double clover_coef;
     uint64_t launches;
     int num_sms;
     mutable std::string err;
@@ -257,12 +260,16 @@ struct WilsonArgs {
     Reduce red;
     HaloIn halo;     // MULTI kernels only
     HaloOut hout;    // MULTI == 2 (self-packing) only
+    const cplx *clover;   // CLOVER kernels only: packed clover blocks, 36 complex per site (wilson_kernel.cuh); keep LAST
 };
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                          const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                             const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
+// clover.cu: (re)builds ctx->clover for kappa*csw of `op` if the cached one is stale
+int ensure_clover(lqcd_ctx *ctx, const lqcd_op *op);
+int launch_wilson_clover(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, int multi, int lh, int grid, int bs, cudaStream_t s);   // wilson_clover.cu
 int apply_op(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
              lqcd_fermion *tmp, const DslashFuse *fuse_last);
 

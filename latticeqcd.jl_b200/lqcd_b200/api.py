@@ -47,6 +47,7 @@ class Context:
         self.call("lqcd_local_dims", ld, og)
         self.local_dims, self.origin = tuple(ld), tuple(og)
         self.gauge_epoch = None
+        self.dist = None              # torch.distributed module once connect_ranks ran (multi-rank host barriers)
         self._fin = weakref.finalize(self, self.lib.lqcd_ctx_destroy, h)
 
     def call(self, name, *args):
@@ -59,6 +60,12 @@ class Context:
 
     def synchronize(self):
         self.call("lqcd_synchronize")
+
+    def barrier(self):
+        """host barrier over the ranks of the job (no-op on a single rank)"""
+        if self.dist is not None:
+            self.synchronize()
+            self.dist.barrier()
 
     def stream(self) -> int:
         s = C.c_void_p()
@@ -101,6 +108,7 @@ def connect_ranks(ctx: Context, dist):
     ctx.call("lqcd_comm_export", buf)
     allh = exchange_handles(buf.raw, dist)
     ctx.call("lqcd_comm_connect", C.c_char_p(allh))
+    ctx.dist = dist
     dist.barrier()
 
 
@@ -263,10 +271,12 @@ class DiracOperator:
         self.params = dict(params)
         name = params["Dirac_operator"]
         self.op = L.LqcdOp()
-        if name == "Wilson":
+        if name in ("Wilson", "WilsonClover"):
             self.op.kind = L.WILSON
             self.op.kappa = float(params["κ"])
             self.op.r = float(params.get("r", 1.0))
+            if name == "WilsonClover":      # new capability (the surveyed wrapper stops at parameter_structs.jl:125)
+                self.op.csw = float(params.get("Clover_coefficient", 1.5612))
         elif name in ("staggered", "Staggered"):
             self.op.kind = L.STAGGERED
             self.op.mass = float(params["mass"])
@@ -288,6 +298,19 @@ class DiracOperator:
         self.U = U
         ptrs = (C.c_void_p * 4)(*[U.data[mu].ctypes.data for mu in range(4)])
         self.ctx.call("lqcd_gauge_upload", ptrs, 3, 0)
+        if self.op.kind == L.WILSON and self.op.csw != 0.0:
+            # the clover term depends on the links only: build it at the D(U) rebinding.  Its leaves reach one site into
+            # the neighbouring ranks' links, so all ranks must have uploaded first and nobody may re-upload while a peer reads.
+            self.ctx.barrier()
+            self.ctx.call("lqcd_clover_term", C.byref(self.op), None)
+            self.ctx.barrier()
+
+    def clover_term(self) -> np.ndarray:
+        """dense clover blocks [V_local, 2, 6(j), 6(i)] (oracle layout), for inspection / tests"""
+        V = int(np.prod(self.ctx.local_dims))
+        out = np.zeros((V, 2, 6, 6), dtype=np.complex128)
+        self.ctx.call("lqcd_clover_term", C.byref(self.op), out.ctypes.data_as(C.c_void_p))
+        return out
 
     def __call__(self, U: Gaugefields):
         self._bind(U)

@@ -116,3 +116,39 @@ def test_cg_true_residual_with_clover():
     assert res["converged"]
     r = b - orc.apply(op, orc.WILSON, orc.DDAGD, U, res["x"])
     assert np.vdot(r, r).real < 1e-18
+
+
+def test_device_packing_and_apply_emulation():
+    """Mirrors, in numpy, the packed storage written by clover_build_kernel (csrc/clover.cu) and the arithmetic of
+    clover_apply (csrc/wilson_kernel.cuh): e = 0..2 diagonal pairs, e = 3 + i(i-1)/2 + j -> A_ij (i > j);
+    y_i += A_ij x_j, y_j += conj(A_ij) x_i.  Checks the index algebra against the dense oracle blocks."""
+    U, psi = fields(seed=41)
+    op = orc.make_op(DIMS, kappa=KAPPA, csw=CSW)
+    clov = orc.clover_build(op, U)                         # [V, blk, j, i]
+    A = np.swapaxes(clov, -1, -2)                          # [V, blk, i, j]
+    V = A.shape[0]
+    packed = np.zeros((V, 2, 18), dtype=complex)
+    for b in range(2):
+        for h in range(3):
+            packed[:, b, h] = A[:, b, 2 * h, 2 * h].real + 1j * A[:, b, 2 * h + 1, 2 * h + 1].real
+        for i in range(1, 6):
+            for j in range(i):
+                packed[:, b, 3 + i * (i - 1) // 2 + j] = A[:, b, i, j]
+    x = psi.reshape(4, V, 3)                                # [alpha, site, c]
+    out = np.zeros_like(x)
+    for b in range(2):
+        xv = [x[2 * b + i // 3, :, i % 3] for i in range(6)]
+        yv = [None] * 6
+        for h in range(3):
+            d = packed[:, b, h]
+            yv[2 * h] = d.real * xv[2 * h]
+            yv[2 * h + 1] = d.imag * xv[2 * h + 1]
+        for i in range(1, 6):
+            for j in range(i):
+                c = packed[:, b, 3 + i * (i - 1) // 2 + j]
+                yv[i] = yv[i] + c * xv[j]
+                yv[j] = yv[j] + np.conj(c) * xv[i]
+        for i in range(6):
+            out[2 * b + i // 3, :, i % 3] = yv[i]
+    want = psi + np_ref.clover_term(U, psi, KAPPA, CSW)
+    assert np.abs(out.reshape(psi.shape) - want).max() < 1e-13

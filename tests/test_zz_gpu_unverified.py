@@ -1,0 +1,64 @@
+"""
+GPU parity tests of device code that was written AFTER the round's GPU budget was spent: compiled for sm_100a and checked
+on the CPU side (oracle, numpy restatements, emulations) but never executed on hardware.  They run last (file name) and are
+marked xfail(strict=False): a failure is reported as "xfailed" and does not hide the verified suite, a pass shows up as
+"xpassed".  Remove the marker once a B200 run has confirmed them.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on hardware (written after the round's GPU budget was spent)", strict=False)]
+
+CSW = 1.5612        # src/system/parameter_structs.jl:125
+
+
+def _clover_setup(dims, kappa, seed=7):
+    import lqcd_b200 as q
+    Uh = orc.random_su3(dims, seed=seed, eps=0.35)
+    U = q.gaugefields_from_array(Uh)
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "WilsonClover", "κ": kappa, "r": 1.0, "Clover_coefficient": CSW,
+                                "boundarycondition": [1, 1, 1, -1], "eps_CG": 1e-20, "MaxCGstep": 3000})
+    op = orc.make_op(dims, kappa=kappa, csw=CSW)
+    clov = orc.clover_build(op, Uh)
+    return q, Uh, U, x, D, op, clov
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (32, 4, 4, 4)])
+def test_clover_term_matches_oracle(dims):
+    q, Uh, U, x, D, op, clov = _clover_setup(dims, 0.125)
+    got = D.clover_term()
+    assert np.abs(got - clov).max() < 1e-13
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (16, 8, 4, 8)])
+def test_clover_dslash_matches_oracle(dims):
+    q, Uh, U, x, D, op, clov = _clover_setup(dims, 0.125)
+    src = orc.gaussian_field(dims, orc.WILSON, seed=19)
+    x.from_host(src)
+    y = q.similar(x)
+    for A, mode in ((D, orc.D), (q.adjoint(D), orc.DDAG), (q.DdagD(D), orc.DDAGD)):
+        q.mul_(y, A, x)
+        want = orc.apply(op, orc.WILSON, mode, Uh, src)
+        assert np.abs(y.to_host() - want).max() / np.abs(want).max() < 1e-13
+
+
+def test_clover_cg_iterations_and_solution():
+    dims = (8, 8, 8, 8)
+    q, Uh, U, x, D, op, clov = _clover_setup(dims, 0.12)
+    b = orc.gaussian_field(dims, orc.WILSON, seed=23)
+    x.from_host(b)
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    ref = orc.cg(op, orc.WILSON, Uh, b, eps=1e-20)
+    assert ref["converged"] and info["iters"] == ref["iters"]
+    assert np.abs(sol.to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+    # plain Wilson on the same context still works after the clover operator (cache keyed on kappa*csw)
+    D0 = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": 0.12, "boundarycondition": [1, 1, 1, -1]})
+    y = q.similar(x)
+    q.mul_(y, D0, x)
+    want = orc.apply(orc.make_op(dims, kappa=0.12), orc.WILSON, orc.D, Uh, b)
+    assert np.abs(y.to_host() - want).max() < 1e-13
