@@ -70,18 +70,33 @@ static inline int64_t nbr(const geom *g, int64_t s, const int c[4], int mu, int 
  *      acc  += kappa*temp1 + kappa*temp2;   finally y = x - acc.
  *  dagger swaps (r-gamma) <-> (r+gamma)  (upstream Wdagx!).  Boundary phase bc[nu] multiplies the shifted
  *  spinor when the shift wraps (upstream applies it when filling the fermion "wing").                    */
+/* parity < 0: all sites, y = [A] x - kappa H x.  parity = 0/1: only sites of that parity are computed and the result is
+ * the bare hopping sum y = H x there (kappa not applied), zero on the other parity (even-odd building block). */
+static void wilson_apply_p(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x, int parity);
 static void wilson_apply(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x) {
+    wilson_apply_p(op, dagger, y, u, x, -1);
+}
+void orc_wilson_hop_parity(const orc_op *op, int dagger, int parity, zc *y, const zc *const u[4], const zc *x) {
+    wilson_apply_p(op, dagger, y, u, x, parity & 1);
+}
+static void wilson_apply_p(const orc_op *op, int dagger, zc *y, const zc *const u[4], const zc *x, int parity) {
     geom g = mkgeom(op->dims);
     if (op->csw != 0.0 && !op->clov) abort();      /* orc_clover_build first */
     const int64_t V = g.V;
     const zc (*Gf)[4][4] = dagger ? op->rplusg : op->rminusg;   /* multiplies the forward hop */
     const zc (*Gb)[4][4] = dagger ? op->rminusg : op->rplusg;   /* multiplies the backward hop */
-    const double kappa = op->kappa;
+    const double kappa = parity < 0 ? op->kappa : 1.0;
 #pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < V; s++) {
         int c[4]; site_coords(&g, s, c);
         zc acc[4][3];
         memset(acc, 0, sizeof acc);
+        if (parity >= 0) {
+            if (((c[0] + c[1] + c[2] + c[3]) & 1) != parity) {
+                for (int al = 0; al < 4; al++) for (int a = 0; a < 3; a++) y[a + 3 * (s + V * al)] = 0;
+                continue;
+            }
+        }
         for (int nu = 0; nu < 4; nu++) {
             int wf, wb;
             int64_t sf = nbr(&g, s, c, nu, +1, &wf);
@@ -115,6 +130,9 @@ static void wilson_apply(const orc_op *op, int dagger, zc *y, const zc *const u[
                     acc[al][a] += kappa * t1 + kappa * t2;
                 }
         }
+        if (parity >= 0) {
+            for (int al = 0; al < 4; al++) for (int a = 0; a < 3; a++) y[a + 3 * (s + V * al)] = acc[al][a];
+        } else
         if (op->csw != 0.0) {       /* Wilson-clover: y = A(n) x(n) - acc, A block diagonal in chirality (spins 01 | 23) */
             const zc *A = op->clov + 72 * s;
             for (int blk = 0; blk < 2; blk++)
@@ -166,7 +184,7 @@ static void staggered_apply(const orc_op *op, int dagger, zc *y, const zc *const
 
 static int64_t field_len(const orc_op *op, int kind) {
     int64_t V = (int64_t)op->dims[0] * op->dims[1] * op->dims[2] * op->dims[3];
-    return kind == ORC_WILSON ? 12 * V : 3 * V;
+    return kind == ORC_STAGGERED ? 3 * V : 12 * V;
 }
 
 void orc_apply(const orc_op *op, int kind, int mode, zc *y, const zc *const u[4], const zc *x, zc *scratch) {
@@ -178,6 +196,24 @@ void orc_apply(const orc_op *op, int kind, int mode, zc *y, const zc *const u[4]
         return;
     }
     if (kind == ORC_WILSON) wilson_apply(op, mode == ORC_DDAG, y, u, x);
+    else if (kind == ORC_WILSON_EO) {   /* y_e = x_e - kappa^2 H_eo (H_oe x_e)  (dagger: H^dag in both hops) */
+        const int64_t n = field_len(op, kind);
+        zc *t = malloc(sizeof(zc) * n);
+        wilson_apply_p(op, mode == ORC_DDAG, t, u, x, 1);
+        wilson_apply_p(op, mode == ORC_DDAG, y, u, t, 0);
+        const double k2 = op->kappa * op->kappa;
+        geom g = mkgeom(op->dims);
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < g.V; s++) {
+            int c[4]; site_coords(&g, s, c);
+            const int even = ((c[0] + c[1] + c[2] + c[3]) & 1) == 0;
+            for (int al = 0; al < 4; al++) for (int a = 0; a < 3; a++) {
+                int64_t i = a + 3 * (s + g.V * al);
+                y[i] = even ? x[i] - k2 * y[i] : 0;
+            }
+        }
+        free(t);
+    }
     else                    staggered_apply(op, mode == ORC_DDAG, y, u, x);
 }
 
@@ -566,4 +602,46 @@ void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4
                 A[36 * blk + i + 6 * j] = sum;
             }
     }
+}
+
+/* ---- even-odd preconditioned Wilson solve (see lqcd_oracle.h) ---- */
+int orc_eo_solve(const orc_op *op, int method, int dagger, zc *x, const zc *const u[4], const zc *b,
+                 double eps, int maxsteps, double *resid_sq, double *hist) {
+    if (op->csw != 0.0) abort();      /* Mhat below assumes M_ee = M_oo = 1 */
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V, n = 12 * V;
+    zc *bh = malloc(sizeof(zc) * n), *xe = malloc(sizeof(zc) * n), *t = malloc(sizeof(zc) * n);
+    const double kappa = op->kappa;
+    /* bhat_e = b_e + kappa H_eo b_o ; xe = even part of the initial guess */
+    wilson_apply_p(op, dagger, t, u, b, 0);                  /* reads the odd part of b only */
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        const int even = ((c[0] + c[1] + c[2] + c[3]) & 1) == 0;
+        for (int al = 0; al < 4; al++) for (int a = 0; a < 3; a++) {
+            int64_t i = a + 3 * (s + V * al);
+            bh[i] = even ? b[i] + kappa * t[i] : 0;
+            xe[i] = even ? x[i] : 0;
+        }
+    }
+    orc_op hop = *op;
+    int it;
+    /* the Krylov routines solve A x = b with A = orc_apply(.., ORC_D ..); for the dagger system hand them Mhat^dag as "D" by
+     * swapping the projector tables (dagger swaps (r-g) <-> (r+g), nothing else) */
+    if (dagger) { memcpy(hop.rplusg, op->rminusg, sizeof hop.rplusg); memcpy(hop.rminusg, op->rplusg, sizeof hop.rminusg); }
+    if (method == 0) it = orc_cgnr(&hop, ORC_WILSON_EO, xe, u, bh, eps, maxsteps, resid_sq, hist);
+    else             it = orc_bicgstab(&hop, ORC_WILSON_EO, xe, u, bh, eps, maxsteps, resid_sq, hist);
+    /* x_o = b_o + kappa H_oe x_e */
+    wilson_apply_p(op, dagger, t, u, xe, 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < V; s++) {
+        int c[4]; site_coords(&g, s, c);
+        const int even = ((c[0] + c[1] + c[2] + c[3]) & 1) == 0;
+        for (int al = 0; al < 4; al++) for (int a = 0; a < 3; a++) {
+            int64_t i = a + 3 * (s + V * al);
+            x[i] = even ? xe[i] : b[i] + kappa * t[i];
+        }
+    }
+    free(bh); free(xe); free(t);
+    return it;
 }

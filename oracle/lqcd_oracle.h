@@ -48,7 +48,9 @@ typedef struct {
                                filled by orc_clover_build; must be set when csw != 0 */
 } orc_op;
 
-enum { ORC_WILSON = 0, ORC_STAGGERED = 1 };
+enum { ORC_WILSON = 0, ORC_STAGGERED = 1,
+       ORC_WILSON_EO = 2 /* even-odd (Schur) preconditioned Wilson operator Mhat = 1 - kappa^2 H_eo H_oe acting on the EVEN
+                            sites of full-size arrays (odd entries are kept zero); see orc_eo_solve */ };
 enum { ORC_D = 0, ORC_DDAG = 1, ORC_DDAGD = 2 };
 
 /* fill gamma tables (LTK / upstream basis) for a given r */
@@ -75,6 +77,18 @@ int orc_bicgstab(const orc_op *op, int kind, zc *x, const zc *const u[4], const 
  * by the caller: shifts[0] must be the smallest) residual */
 int orc_mscg (const orc_op *op, int kind, zc *const xs[], const zc *const u[4], const zc *b,
               const double *shifts, int nshift, double eps, int maxsteps, double *resid_sq);
+
+/* Even-odd preconditioned solve of M x = b (dagger = 0) or M^dag x = b (dagger = 1), Wilson without clover
+ * (BASELINE.json configs[1] "even-odd CG"; new capability: the wrapper's `isevenodd` is a heatbath flag only,
+ * src/updates/AbstractUpdate.jl:97).  With M = 1 - kappa H and H connecting opposite parities:
+ *     bhat_e = b_e + kappa H_eo b_o;   Mhat x_e = bhat_e, Mhat = 1 - kappa^2 H_eo H_oe;   x_o = b_o + kappa H_oe x_e.
+ * The even part of x on entry is the initial guess.  method: 0 = CGNR ("bicg"), 1 = BiCGStab, on Mhat with the
+ * reference's stopping rule |bhat - Mhat x_e|^2 < eps, which equals the true residual |b - M x|^2 of the full system.
+ * Returns the iteration count or -1. */
+int orc_eo_solve(const orc_op *op, int method, int dagger, zc *x, const zc *const u[4], const zc *b,
+                 double eps, int maxsteps, double *resid_sq, double *hist);
+/* y(n) = sum of the eight hopping terms H x at sites n of parity `parity` (0 even, 1 odd), zero elsewhere */
+void orc_wilson_hop_parity(const orc_op *op, int dagger, int parity, zc *y, const zc *const u[4], const zc *x);
 
 /* average plaquette  (1/(6 V NC)) sum Re tr U_mu(n) U_nu(n+mu) U_mu(n+nu)^dag U_nu(n)^dag */
 double orc_plaquette(const int dims[4], const zc *const u[4]);

@@ -21,7 +21,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB = None
 
-WILSON, STAGGERED = 0, 1
+WILSON, STAGGERED, WILSON_EO = 0, 1, 2
 D, DDAG, DDAGD = 0, 1, 2
 
 
@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
         L.orc_wilson_force.argtypes = [op, pp, pp, vp, vp]
         L.orc_staggered_force.argtypes = [op, pp, pp, vp, vp]
         L.orc_clover_build.argtypes = [op, vp, vp, pp]
+        L.orc_eo_solve.argtypes = [op, ci, ci, vp, pp, vp, dbl, ci, C.POINTER(dbl), vp]
+        L.orc_eo_solve.restype = ci
+        L.orc_wilson_hop_parity.argtypes = [op, ci, ci, vp, pp, vp]
         _LIB = L
     return _LIB
 
@@ -161,6 +164,19 @@ def mscg(op, kind, U, b, shifts, eps=1e-19, maxsteps=3000):
                         shifts.ctypes.data_as(C.POINTER(C.c_double)), len(xs), float(eps), int(maxsteps),
                         C.byref(rs))
     return {"xs": xs, "iters": it, "resid_sq": rs.value, "converged": it >= 0}
+
+
+def eo_solve(op, U, b, method="bicg", dagger=False, x0=None, eps=1e-19, maxsteps=3000, hist=False):
+    """even-odd (Schur) preconditioned solve of M x = b / M^dag x = b; method "bicg" (= CGNR) or "bicgstab" on Mhat."""
+    m = {"bicg": 0, "cgnr": 0, "bicgstab": 1}[method]
+    fn = lambda opp, kind, x, u, bb, e, ms, rs, h: lib().orc_eo_solve(opp, m, int(bool(dagger)), x, u, bb, e, ms, rs, h)
+    return _solve(fn, op, WILSON, U, b, x0, eps, maxsteps, hist)
+
+
+def hop_parity(op, U, x, parity, dagger=False):
+    y = np.empty_like(x)
+    lib().orc_wilson_hop_parity(C.byref(op), int(bool(dagger)), int(parity), _chk(y), _uptrs(U), _chk(x))
+    return y
 
 
 def clover_build(op: OrcOp, U: np.ndarray, want_f=False):
