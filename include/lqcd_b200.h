@@ -135,6 +135,16 @@ int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fer
 int lqcd_multishift_cg(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *x,
                        const double *shifts, int nshift, double eps, int maxsteps, int *iters, double *resid_sq);
 
+/* even-odd (Schur complement) preconditioned solve of D y = x (target LQCD_OP_D) or D^dag y = x (LQCD_OP_DDAG) for the
+ * Wilson operator without clover, r = 1, single rank, even extents (BASELINE.json configs[1]; NEW capability: the wrapper's
+ * `isevenodd` is a heatbath flag only, src/updates/AbstractUpdate.jl:97):
+ *     xhat_e = x_e + kappa H_eo x_o;   (1 - kappa^2 H_eo H_oe) y_e = xhat_e;   y_o = x_o + kappa H_oe y_e
+ * on checkerboarded half-lattice fields.  method = LQCD_SOLVER_CGNR (upstream "bicg") or LQCD_SOLVER_BICGSTAB, applied to
+ * the preconditioned operator; the even part of y is the initial guess; eps / maxsteps / hist as in lqcd_solve -- the
+ * preconditioned residual equals the true residual |x - D y|^2 of the full system. */
+int lqcd_solve_eo(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int method, int target,
+                  double eps, int maxsteps, int *iters, double *resid_sq, double *hist);
+
 /* ---- fermion force: calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129) ---------------
  * Given eta: X = (DdagD)^-1 eta by CG, Y = D X, then the 4 link-shaped outer-product fields are written
  * to the host arrays out_mu (same layout as the links, wing width ndw; the halo is zero-filled).

@@ -29,7 +29,7 @@ extern "C" const char *lqcd_last_error(const lqcd_ctx *ctx) {
 extern "C" int lqcd_abi_version(void) { return LQCD_ABI_VERSION; }
 
 // ---- tiling ------------------------------------------------------------------------------------------
-static void make_tiling(Geom &g) {
+void make_tiling(Geom &g) {
     const int d[4] = {g.X, g.Y, g.Z, g.T};
     int rem = 32;
     g.regular = 1;
@@ -95,6 +95,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr;
+    ctx->eo = nullptr; ctx->eo_active = 0;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -133,12 +134,14 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
 }
 
 int comm_destroy(lqcd_ctx *ctx);
+void eo_destroy(lqcd_ctx *ctx);       // wilson_eo.cu
 
 extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     if (!ctx) return LQCD_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     comm_destroy(ctx);
+    eo_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->clover);

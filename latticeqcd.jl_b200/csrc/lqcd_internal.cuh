@@ -166,6 +166,9 @@ struct lqcd_ctx {
     mutable std::string err;
     // comm (multi-GPU) -- see comm.cu
     struct CommState *comm;
+    // even-odd preconditioned solve -- see wilson_eo.cu
+    struct EoState *eo;
+    int eo_active;             // 1 while lqcd_solve_eo runs the Krylov loop: the solver's operator is Mhat on even half fields
 };
 
 int lqcd_fail(const lqcd_ctx *ctx, int code, const char *fmt, ...);

@@ -37,7 +37,10 @@ static int check_op(const lqcd_ctx *ctx, const lqcd_op *op) {
     return LQCD_OK;
 }
 
+int eo_mhat(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse);   // wilson_eo.cu
+
 static int one_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
+    if (ctx->eo_active) return eo_mhat(ctx, op, y, x, dagger, fuse);      // lqcd_solve_eo: the "operator" is Mhat on even half fields
     if (ctx->nranks > 1) return comm_dslash(ctx, op, y, x, dagger, fuse);
     if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream);
     return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream);
@@ -139,6 +142,9 @@ static int run_loop(lqcd_ctx *ctx, int maxsteps, Body body, int *iters, double *
 
 static inline size_t flen(const lqcd_ctx *ctx, const lqcd_fermion *f) { return (size_t)ctx->g.nblk * f->ncomp * 32; }
 
+int solve_impl(lqcd_ctx *ctx, const lqcd_op *op, cplx *x, const cplx *bb, size_t n, int method, int target,
+               double eps, int maxsteps, int *iters, double *resid_sq, double *hist);
+
 extern "C" int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *b, int method, int target,
                           double eps, int maxsteps, int *iters, double *resid_sq, double *hist) {
     if (!ctx || !y || !b) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
@@ -150,13 +156,17 @@ extern "C" int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, con
     if (method == LQCD_SOLVER_CG && target != LQCD_OP_DDAGD) return lqcd_fail(ctx, LQCD_ERR_ARG, "CG needs the Hermitian target DdagD");
     if (method != LQCD_SOLVER_CG && target != LQCD_OP_D && target != LQCD_OP_DDAG) return lqcd_fail(ctx, LQCD_ERR_ARG, "CGNR/BiCGStab solve D or D^dag");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return solve_impl(ctx, op, y->d, b->d, flen(ctx, y), method, target, eps, maxsteps, iters, resid_sq, hist);
+}
+
+// The Krylov loops on raw device vectors of n complex numbers (full fields from lqcd_solve, even half fields from
+// lqcd_solve_eo, where apply_async applies Mhat).
+int solve_impl(lqcd_ctx *ctx, const lqcd_op *op, cplx *x, const cplx *bb, size_t n, int method, int target,
+               double eps, int maxsteps, int *iters, double *resid_sq, double *hist) {
     const int kind = op->kind;
-    const size_t n = flen(ctx, y);
     double *hd = nullptr;
     LQCD_TRY(state_init(ctx, eps, maxsteps, nullptr, 0, hist ? &hd : nullptr));
     ctx->red.hist = hd;
-    cplx *x = y->d;
-    const cplx *bb = b->d;
     DslashFuse plain = DslashFuse(); plain.use_state = 1;
     int rc = LQCD_OK;
 

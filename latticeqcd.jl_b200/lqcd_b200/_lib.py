@@ -72,6 +72,7 @@ SIGNATURES = {
     "lqcd_dslash": (i32, [vp, pop, vp, vp, i32]),
     "lqcd_clover_term": (i32, [vp, pop, vp]),
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
+    "lqcd_solve_eo": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_multishift_cg": (i32, [vp, pop, pvp, vp, pdbl, i32, dbl, i32, pi32, pdbl]),
     "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, i32, pi32, pdbl]),
     "lqcd_comm_export": (i32, [vp, vp]),

@@ -356,7 +356,9 @@ def solve_DinvX_(y: FermionField, A, x: FermionField, history=False):
     hist = np.full(D.maxsteps + 1, np.nan) if (history or D.verbose >= 3) else None
     hp = hist.ctypes.data_as(L.pdbl) if hist is not None else None
     try:
-        D.ctx.call("lqcd_solve", C.byref(D.op), y.h, x.h, method, mode, D.eps, D.maxsteps, C.byref(it), C.byref(rs), hp)
+        # params["evenodd"] = True (new key): Schur-preconditioned solve for D / D' systems of the plain Wilson operator
+        fn = "lqcd_solve_eo" if (D.params.get("evenodd") and mode != L.OP_DDAGD) else "lqcd_solve"
+        D.ctx.call(fn, C.byref(D.op), y.h, x.h, method, mode, D.eps, D.maxsteps, C.byref(it), C.byref(rs), hp)
     finally:
         D.last = {"iters": it.value, "resid_sq": rs.value,
                   "hist": None if hist is None else hist[: it.value + 1]}

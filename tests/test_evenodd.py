@@ -59,3 +59,59 @@ def test_evenodd_initial_guess_and_point_source():
     first = orc.eo_solve(op, U, b, method="bicg", eps=1e-20)
     again = orc.eo_solve(op, U, b, method="bicg", eps=1e-20, x0=first["x"])
     assert first["converged"] and again["iters"] == 0
+
+
+@pytest.mark.parametrize("dims", [(8, 4, 4, 2), (4, 4, 2, 8), (16, 2, 4, 4)])
+@pytest.mark.parametrize("dagger", [False, True])
+def test_checkerboard_index_emulation(dims, dagger):
+    """numpy mirror of the index algebra of csrc/wilson_eo.cu (eo_convert_kernel, wilson_eo_hop_kernel): half index
+    h = (x>>1) + X/2*(y + Y*(z + Z*t)), x = 2*xh + ((y+z+t+p)&1); the +-x neighbour of the other parity is h or h+-1
+    depending on the row parity; forward links from the output parity's array at h, backward links from the input
+    parity's array at the neighbour index; boundary phases on wrap.  Compared with the oracle's parity hop."""
+    import np_ref
+    X, Y, Z, T = dims
+    Xh, V, Vh = X // 2, X * Y * Z * T, X * Y * Z * T // 2
+    bc = (1, 1, 1, -1)
+    U = orc.random_su3(dims, seed=5)
+    psi = orc.gaussian_field(dims, orc.WILSON, seed=6)
+    op = orc.make_op(dims, kappa=0.13, bc=bc)
+    M = np_ref.links_mat(U).reshape(4, V, 3, 3)                  # [mu, site, a, b]
+    f = psi.reshape(4, V, 3).transpose(1, 0, 2)                  # [site, alpha, c]
+    h = np.arange(Vh)
+    xh, y, z, t = h % Xh, (h // Xh) % Y, (h // (Xh * Y)) % Z, h // (Xh * Y * Z)
+    site_of = {}
+    for p in (0, 1):
+        x = 2 * xh + ((y + z + t + p) & 1)
+        assert np.all(((x + y + z + t) & 1) == p)
+        site_of[p] = x + X * (y + Y * (z + Z * t))               # eo_convert_kernel
+    assert sorted(np.concatenate([site_of[0], site_of[1]])) == list(range(V))
+    half_f = {p: f[site_of[p]] for p in (0, 1)}
+    half_U = {p: M[:, site_of[p]] for p in (0, 1)}
+    for p in (0, 1):
+        odd_row = (y + z + t + p) & 1
+        fin, g_out, g_in = half_f[1 - p], half_U[p], half_U[1 - p]
+        acc = np.zeros((Vh, 4, 3), dtype=complex)
+        coords = (None, y, z, t)
+        strides = (None, Xh, Xh * Y, Xh * Y * Z)
+        ext = (X, Y, Z, T)
+        for mu in range(4):
+            if mu == 0:
+                wf = (odd_row == 1) & (xh == Xh - 1)
+                nf = np.where(odd_row == 1, np.where(wf, h - (Xh - 1), h + 1), h)
+                wb = (odd_row == 0) & (xh == 0)
+                nb = np.where(odd_row == 1, h, np.where(wb, h + (Xh - 1), h - 1))
+            else:
+                c, st, d = coords[mu], strides[mu], ext[mu]
+                wf, wb = c == d - 1, c == 0
+                nf = np.where(wf, h - (d - 1) * st, h + st)
+                nb = np.where(wb, h + (d - 1) * st, h - st)
+            sgn = -1 if dagger else 1
+            Pf = np.eye(4) - sgn * np_ref.G[mu]                  # D: forward (1 - g), backward (1 + g)
+            Pb = np.eye(4) + sgn * np_ref.G[mu]
+            phf = np.where(wf, bc[mu], 1.0)[:, None, None]
+            phb = np.where(wb, bc[mu], 1.0)[:, None, None]
+            fw = np.einsum("hab,hsb->hsa", g_out[mu][h], phf * fin[nf])
+            bw = np.einsum("hba,hsb->hsa", np.conj(g_in[mu][nb]), phb * fin[nb])
+            acc += np.einsum("sr,hra->hsa", Pf, fw) + np.einsum("sr,hra->hsa", Pb, bw)
+        want = orc.hop_parity(op, U, psi, p, dagger=dagger).reshape(4, V, 3).transpose(1, 0, 2)[site_of[p]]
+        assert np.abs(acc - want).max() < 1e-13
