@@ -37,9 +37,44 @@ void die(const char *fmt, ...) {
     abort();
 }
 
+// Context switch: a six-register x86-64 stack switch (swapcontext costs two sigprocmask system calls per switch, which
+// dominated the run time); AddressSanitizer builds keep ucontext, which ASan intercepts and understands.
+#if defined(__x86_64__) && !defined(__SANITIZE_ADDRESS__)
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_switch(void **save_sp, void *new_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#define EMU_FAST_SWITCH 0
+#endif
+
 enum Wait { RUN = 0, WAIT_CTA = 1, WAIT_WARP = 2, DONE = 3 };
 struct Fiber {
+#if EMU_FAST_SWITCH
+    void *sp;
+#else
     ucontext_t ctx;
+#endif
     int state;
     unsigned gen;       // generation of the barrier it waits on
 };
@@ -50,7 +85,11 @@ struct Cta {
     unsigned warp_gen[32], warp_count[32], warp_alive[32];
     uint64_t warp_buf[32][32];
     int cur;
+#if EMU_FAST_SWITCH
+    void *sched_sp;
+#else
     ucontext_t sched;
+#endif
     const std::function<void()> *body;
 };
 Cta *C = nullptr;
@@ -65,18 +104,33 @@ void set_tid(int t) {
     threadIdx.z = t / (blockDim.x * blockDim.y);
 }
 
+void to_sched(Fiber &f) {
+#if EMU_FAST_SWITCH
+    emu_switch(&f.sp, C->sched_sp);
+#else
+    swapcontext(&f.ctx, &C->sched);
+#endif
+}
+void to_fiber(Fiber &f) {
+#if EMU_FAST_SWITCH
+    emu_switch(&C->sched_sp, f.sp);
+#else
+    swapcontext(&C->sched, &f.ctx);
+#endif
+}
+
 void trampoline() {
     (*C->body)();
     Fiber &f = C->fib[C->cur];
     f.state = DONE;
-    swapcontext(&f.ctx, &C->sched);
+    to_sched(f);
     die("resumed a finished fiber");
 }
 
 void yield_fiber() {
     Fiber &f = C->fib[C->cur];
     const int me = C->cur;
-    swapcontext(&f.ctx, &C->sched);
+    to_sched(f);
     C->cur = me;
     set_tid(me);
 }
@@ -95,11 +149,23 @@ void run_cta() {
     for (int w = 0; w < 32; w++) { C->warp_gen[w] = 0; C->warp_count[w] = 0; C->warp_alive[w] = 0; }
     for (int t = 0; t < n; t++) {
         Fiber &f = C->fib[t];
+#if EMU_FAST_SWITCH
+        {   // initial frame: six callee-saved registers, then the entry address that emu_switch's `ret` jumps to; the
+            // stack pointer at entry is 8 mod 16 as after a call
+            uintptr_t top = ((uintptr_t)(stacks + (size_t)(t + 1) * STACK_BYTES)) & ~(uintptr_t)15;
+            void **sp = (void **)top;
+            *--sp = nullptr;                       // fake return address of trampoline()
+            *--sp = (void *)&trampoline;
+            for (int k = 0; k < 6; k++) *--sp = nullptr;
+            f.sp = sp;
+        }
+#else
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = stacks + (size_t)t * STACK_BYTES;
         f.ctx.uc_stack.ss_size = STACK_BYTES;
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, trampoline, 0);
+#endif
         f.state = RUN; f.gen = 0;
         C->warp_alive[t >> 5]++;
     }
@@ -112,7 +178,7 @@ void run_cta() {
             if (f.state == WAIT_WARP) { if (f.gen == C->warp_gen[t >> 5]) continue; f.state = RUN; }
             C->cur = t;
             set_tid(t);
-            swapcontext(&C->sched, &f.ctx);
+            to_fiber(f);
             progress = true;
             if (f.state == DONE) { C->alive--; C->warp_alive[t >> 5]--; }
             release_barriers();
@@ -238,8 +304,15 @@ void check_redzones() {
 }
 double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
+void unlink_all_shm() {
+    for (auto &kv : allocs)
+        if (!kv.second.shm.empty()) shm_unlink(kv.second.shm.c_str());
+}
+
 cudaError_t alloc_common(void **p, size_t bytes, bool host) {
     if (!p) return cudaErrorInvalidValue;
+    static bool registered = false;
+    if (!registered) { registered = true; atexit(unlink_all_shm); }
     const size_t raw_bytes = ((bytes + 255) & ~(size_t)255) + 2 * REDZONE + 256;
     Alloc a; a.bytes = bytes; a.raw_bytes = raw_bytes; a.host = host;
     if (use_shm() && !host) {

@@ -29,7 +29,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     assert world == int(np.prod(pg)), f"procgrid {pg} needs {int(np.prod(pg))} ranks, got {world}"
     ndev = torch.cuda.device_count()
-    dev = int(os.environ.get("LOCAL_RANK", rank)) % ndev
+    dev = int(os.environ.get("LOCAL_RANK", rank)) % max(ndev, 1)     # ndev = 0 only under tests/emu (no CUDA device)
     kind = orc.WILSON if kind_name == "Wilson" else orc.STAGGERED
     Ug = orc.random_su3(dims, seed=17, eps=0.4)
     src = orc.gaussian_field(dims, kind, seed=23)
