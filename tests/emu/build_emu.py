@@ -191,7 +191,8 @@ def translate_launches(src: str) -> str:
         close = _match_close(src, p, "(", ")")
         args = src[p + 1:close]
         out.append(src[i:j0])
-        out.append(f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), {cfg[2]}, {cfg[3]}, [&]() {{ {kernel}({args}); }})")
+        name = kernel.split("<")[0]
+        out.append(f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), {cfg[2]}, {cfg[3]}, [&]() {{ {kernel}({args}); }}, \"{name}\")")
         i = close + 1
     return "".join(out)
 

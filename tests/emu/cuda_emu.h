@@ -89,7 +89,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 
 // ---- launch + SIMT intrinsics -------------------------------------------------------------------------------------------
 namespace emu {
-void launch(dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t s, const std::function<void()> &thread_body);
+void launch(dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t s, const std::function<void()> &thread_body, const char *name = "?");
 void cta_barrier();
 void warp_barrier();
 void yield_now();

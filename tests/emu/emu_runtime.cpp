@@ -191,7 +191,15 @@ void run_cta() {
 }   // namespace
 
 namespace emu {
-void launch(dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t, const std::function<void()> &body) {
+// LQCD_EMU_TRACE=1: per-kernel launch histogram on stderr at exit (which kernels a test really exercised)
+static std::map<std::string, long> launch_hist;
+static void dump_hist() {
+    for (auto &kv : launch_hist) fprintf(stderr, "[cuda_emu] launches %-40s %ld\n", kv.first.c_str(), kv.second);
+}
+void launch(dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t, const std::function<void()> &body, const char *name) {
+    static int trace = -1;
+    if (trace < 0) { const char *e = getenv("LQCD_EMU_TRACE"); trace = e && atoi(e) != 0; if (trace) atexit(dump_hist); }
+    if (trace) launch_hist[name]++;
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > (size_t)MAX_THREADS || grid.x == 0 || dyn_smem > (227u << 10)) { last_error = cudaErrorInvalidValue; return; }
     if (C && C->body) die("nested kernel launch");

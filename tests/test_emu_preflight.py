@@ -43,7 +43,7 @@ def test_translation_rejects_unknown_constructs():
     with pytest.raises(build_emu.TranslateError):
         build_emu.translate('__device__ void f() { asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1;" :: "r"(0), "l"(0ull)); }')
     out = build_emu.translate("void g(int n) { k<1, 2><<<n, 128, 0, s>>>(a, f(b, c)); }")
-    assert "emu::launch(dim3(n), dim3(128), 0, s, [&]() { k<1, 2>(a, f(b, c)); })" in out
+    assert 'emu::launch(dim3(n), dim3(128), 0, s, [&]() { k<1, 2>(a, f(b, c)); }, "k")' in out
 
 
 def test_gpu_suite_under_emulation(emu_lib):
@@ -58,14 +58,27 @@ def test_gpu_suite_under_emulation(emu_lib):
     assert m and int(m.group(1)) >= 56, tail
 
 
-@pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson"), ("4x4x4x4", "1x1x2x2", "staggered")])
+@pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson"), ("4x4x4x4", "1x1x2x2", "staggered"),
+                                          ("4x4x8x4", "1x1x2x2", "Wilson clover")])
 def test_multirank_under_emulation(emu_lib, dims, pg, kind):
     """tests/mp_worker.py as separate processes: peer-mapped halo slots, sequence flags, in-kernel all-reduce (POSIX shm IPC)"""
     n = 1
     for v in pg.split("x"):
         n *= int(v)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(31500 + (os.getpid() % 2000)), "tests/mp_worker.py", dims, pg, kind]
+           "--master-port", str(31500 + (os.getpid() % 2000)), "tests/mp_worker.py", dims, pg, *kind.split()]
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120"), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "FAILED" not in r.stdout
+
+
+@pytest.mark.parametrize("bulk", ["early", "late"])
+def test_tmarch_kernel_under_emulation(emu_lib, bulk):
+    """experimental t-marching kernel (cp.async.bulk window + mbarriers, modelled by tests/emu): bulk copies completing at
+    issue (earliest) and only when somebody waits on their mbarrier (latest) -- a missing wait or a premature slot refill
+    shows up as NaNs / mismatches in one of the two"""
+    r = subprocess.run([sys.executable, "tests/k3_worker.py"], cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=_env(emu_lib, LQCD_WILSON_KERNEL="3", LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1"))
+    assert r.returncode == 0 and "K3 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"launches wilson_dslash3_kernel\s+(\d+)", r.stderr)
+    assert m and int(m.group(1)) > 500 and "launches wilson_dslash_kernel" not in r.stderr, r.stderr[-2000:]

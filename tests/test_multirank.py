@@ -74,3 +74,14 @@ def test_multirank_parity(dims, pg, kind):
     res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, kind, timeout=900)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="multi-rank Wilson-clover: verified under tests/emu only, not yet run on hardware", strict=False)
+@pytest.mark.parametrize("dims,pg", [("8x8x8x16", "1x1x1x2"), ("8x8x8x8", "1x1x2x2")])
+def test_multirank_clover_parity(dims, pg):
+    """Wilson-clover across ranks: the clover leaves read the neighbours' links through peer-mapped link arrays (clover.cu)"""
+    n = int(np.prod([int(v) for v in pg.split("x")]))
+    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, "Wilson", "clover", timeout=900)
+    sys.stdout.write(res.stdout[-3000:])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

@@ -110,3 +110,15 @@ def test_evenodd_beats_full_solve_and_keeps_plain_path():
         out[eo] = (q.solve_DinvX_(sol, D, x)["iters"], sol.to_host())
     assert out[True][0] < out[False][0]
     assert np.abs(out[True][1] - out[False][1]).max() < 1e-8
+
+
+# ---- experimental t-marching Wilson kernel (csrc/wilson_dslash3.cu, off by default) ------------------------------------
+def test_tmarch_kernel_matches_oracle():
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "tests/k3_worker.py"], cwd=root, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LQCD_WILSON_KERNEL="3", LQCD_COMM_TIMEOUT_S="5"))
+    assert r.returncode == 0 and "K3 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
