@@ -69,6 +69,8 @@ struct CommState {
     bool opened[LQCD_MAX_RANKS];
     bool connected;
     size_t off_red_flags, off_red_vals, off_halo_flags, off_seq, off_err, off_ticket, off_halo;
+    size_t off_force_flags, force_off[4];   // fermion-force halo (force.cu): one flag + one 12-complex-per-face-site slot per direction
+    unsigned long long force_seq;
     size_t halo_slot_bytes[4];        // per direction, one (side, slot) buffer
     size_t halo_off[4][2][2];         // [mu][side: 0 = arrives from lower nbr, 1 = from upper nbr][slot]
     int face[4];                      // face sites per direction
@@ -101,6 +103,7 @@ static int comm_alloc(lqcd_ctx *ctx) {
     c->off_seq = take(sizeof(unsigned long long));
     c->off_err = take(sizeof(int));
     c->off_ticket = take(sizeof(unsigned int));
+    c->off_force_flags = take(sizeof(unsigned long long) * 4);
     for (int mu = 0; mu < 4; mu++) {
         c->face[mu] = g.V / d[mu];
         int pc[4] = {ctx->pcoord[0], ctx->pcoord[1], ctx->pcoord[2], ctx->pcoord[3]};
@@ -111,6 +114,7 @@ static int comm_alloc(lqcd_ctx *ctx) {
         c->halo_slot_bytes[mu] = fb;
         for (int side = 0; side < 2; side++)
             for (int slot = 0; slot < 2; slot++) c->halo_off[mu][side][slot] = take(fb);
+        c->force_off[mu] = take(2 * fb);
     }
     c->bytes = off;
     cudaError_t e = cudaMalloc(&c->base, c->bytes);
@@ -256,13 +260,38 @@ int comm_link_view(lqcd_ctx *ctx, const cplx **bases) {
     return LQCD_OK;
 }
 
+// fermion-force halo descriptors for force call number ++force_seq (see ForceHalo in lqcd_internal.cuh / force.cu)
+int comm_force_halo(lqcd_ctx *ctx, ForceHalo *F) {
+    CommState *c = ctx->comm;
+    if (!c || !c->connected) return lqcd_fail(ctx, LQCD_ERR_COMM, "multi-rank context is not connected (lqcd_comm_export / lqcd_comm_connect)");
+    memset(F, 0, sizeof *F);
+    F->seq = ++c->force_seq;
+    F->ticket = (unsigned int *)(c->base + c->off_ticket);
+    F->err = (int *)(c->base + c->off_err);
+    F->timeout_cycles = ctx->red.cr.timeout_cycles;
+    int n = 0;
+    for (int mu = 0; mu < 4; mu++) {
+        F->start[mu] = n;
+        F->plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
+        if (!ctx->g.part[mu]) continue;
+        n += c->face[mu];
+        const int lo = c->nbr[mu][0];
+        F->send[mu] = (cplx *)(c->peer[lo] + c->force_off[mu]);
+        F->send_flag[mu] = (unsigned long long *)(c->peer[lo] + c->off_force_flags) + mu;
+        F->recv[mu] = (const cplx *)(c->base + c->force_off[mu]);
+        F->recv_flag[mu] = (const unsigned long long *)(c->base + c->off_force_flags) + mu;
+    }
+    F->start[4] = n;
+    return LQCD_OK;
+}
+
 int comm_allreduce_sum(lqcd_ctx *, double *, int) { return LQCD_OK; }   // reductions are already global (in-kernel)
 
 int comm_check_error(lqcd_ctx *ctx) {
     if (ctx->nranks == 1 || !ctx->comm) return LQCD_OK;
     int err = 0;
     CUDA_TRY(ctx, cudaMemcpy(&err, ctx->comm->base + ctx->comm->off_err, sizeof err, cudaMemcpyDeviceToHost));
-    if (err) return lqcd_fail(ctx, LQCD_ERR_COMM, "peer wait timed out on the device (code %d: 1xxxxxx = halo flag [dir*2+side][seq], 2xxxxxx = all-reduce [seq]; host halo_seq = %llu)", err, ctx->comm->halo_seq);
+    if (err) return lqcd_fail(ctx, LQCD_ERR_COMM, "peer wait timed out on the device (code %d: 1xxxxxx = halo flag [dir*2+side][seq], 2xxxxxx = all-reduce [seq], 3xxxxxx = force halo [dir][seq]; host halo_seq = %llu)", err, ctx->comm->halo_seq);
     return LQCD_OK;
 }
 

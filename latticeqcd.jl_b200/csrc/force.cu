@@ -11,9 +11,20 @@
 // rank-2 structure of the projectors: tr_spin[(1-g) v w^dag] = sum_{s=0,1} (P v)_s conj((P w)_s).
 // The reference then applies p_mu += -eps dtau * Traceless_antihermitian(F_mu) on the CPU (AbstractMD.jl:131-133),
 // so the result is returned in the host link layout.
+//
+// Multi-GPU (one process per GPU): the CG and Y = D X run through comm.cu as usual; the outer products need X(n+mu) and
+// Y(n+mu) of the upper neighbour rank for the sites of the HIGH faces.  force_pack_kernel stores the spin-projected halves
+// of this rank's LOW faces (Wilson: P- X | P+ Y = 12 complex per face site; staggered: X | Y) straight into the lower
+// neighbours' force slots over NVLink and raises one sequence flag per direction; the MULTI force kernels wait for their own
+// flags (clock64 timeout -> LQCD_ERR_COMM) and read the slots with ld.global.cg.  Slot reuse is ordered by the global
+// <eta, X> reduction that closes every call: its in-kernel all-reduce completes on a rank only after EVERY rank has posted
+// its contribution, which each rank does after its own force kernel (stream order), so the next call's pack can never
+// overwrite a slot that a neighbour is still reading.
 #include "lqcd_internal.cuh"
 #include "wilson_spin.cuh"
 #include "site_map.cuh"
+#include "halo_pack.cuh"
+#include <cstring>
 
 struct ForceArgs {
     cplx *out;               // device link layout [((blk*4+mu)*9 + a*3+b)*32 + lane]
@@ -21,7 +32,22 @@ struct ForceArgs {
     Geom g;
     double kappa;
     double bc[4];
+    ForceHalo fh;            // MULTI kernels only
 };
+
+// all threads of a MULTI force CTA: wait until the upper neighbours' low faces of this call have landed
+__device__ __forceinline__ void wait_force_flags(const ForceArgs &A) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        bool good = true;
+        for (int m = 0; m < 4 && good; m++) {
+            if (!A.g.part[m]) continue;
+            while (ld_acquire_sys(A.fh.recv_flag[m]) < A.fh.seq)
+                if (clock64() - t0 > A.fh.timeout_cycles) { good = false; *A.fh.err = 3000000 + m * 100000 + (int)(A.fh.seq % 100000); break; }
+        }
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ void load_spinor(cplx (&p)[12], const cplx *f, int s) {
     const cplx *sp = f + (size_t)(s >> 5) * (12 * 32) + (s & 31);
@@ -29,20 +55,35 @@ __device__ __forceinline__ void load_spinor(cplx (&p)[12], const cplx *f, int s)
     for (int k = 0; k < 12; k++) p[k] = ldg128(sp + k * 32);
 }
 
-template <int MU>
+template <int MU, int MULTI>
 __device__ __forceinline__ void wilson_force_dir(const ForceArgs &A, int s, int coord, int dim, int stride,
-                                                 const cplx (&Xn)[12], const cplx (&Yn)[12]) {
+                                                 const cplx (&Xn)[12], const cplx (&Yn)[12], int x, int y, int z, int t) {
     const bool w = (coord == dim - 1);
     const int ns = w ? s - (dim - 1) * stride : s + stride;
-    const double phase = w ? A.bc[MU] : 1.0;
-    cplx Xf[12], Yf[12];
-    load_spinor(Xf, A.X, ns);
-    load_spinor(Yf, A.Y, ns);
     cplx hx0[3], hx1[3], hy0[3], hy1[3], px0[3], px1[3], py0[3], py1[3];
+    double phase;
+    if (MULTI && w && A.g.part[MU]) {          // neighbour is on the upper rank: projected halves from the force slot
+        const int f = face_index<MU>(A.g, x, y, z, t);
+        const cplx *src = A.fh.recv[MU] + (size_t)(f >> 5) * (12 * 32) + (f & 31);
+        phase = A.fh.plast[MU] ? A.bc[MU] : 1.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            hx0[c] = __ldcg(src + c * 32);       hx1[c] = __ldcg(src + (3 + c) * 32);
+            hy0[c] = __ldcg(src + (6 + c) * 32); hy1[c] = __ldcg(src + (9 + c) * 32);
+        }
+    } else {
+        phase = w ? A.bc[MU] : 1.0;
+        cplx Xf[12], Yf[12];
+        load_spinor(Xf, A.X, ns);
+        load_spinor(Yf, A.Y, ns);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            project<MU, -1>(hx0[c], hx1[c], Xf[c], Xf[3 + c], Xf[6 + c], Xf[9 + c]);      // P- X(n+mu)
+            project<MU, +1>(hy0[c], hy1[c], Yf[c], Yf[3 + c], Yf[6 + c], Yf[9 + c]);      // P+ Y(n+mu)
+        }
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        project<MU, -1>(hx0[c], hx1[c], Xf[c], Xf[3 + c], Xf[6 + c], Xf[9 + c]);      // P- X(n+mu)
-        project<MU, +1>(hy0[c], hy1[c], Yf[c], Yf[3 + c], Yf[6 + c], Yf[9 + c]);      // P+ Y(n+mu)
         project<MU, -1>(py0[c], py1[c], Yn[c], Yn[3 + c], Yn[6 + c], Yn[9 + c]);      // P- Y(n)
         project<MU, +1>(px0[c], px1[c], Xn[c], Xn[3 + c], Xn[6 + c], Xn[9 + c]);      // P+ X(n)
         hx0[c] = cscale(phase, hx0[c]); hx1[c] = cscale(phase, hx1[c]);
@@ -73,7 +114,9 @@ __device__ __forceinline__ void wilson_force_dir(const ForceArgs &A, int s, int 
         }
 }
 
+template <int MULTI>
 __global__ void __launch_bounds__(128) wilson_force_kernel(const ForceArgs A) {
+    if (MULTI) wait_force_flags(A);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.g.V) return;
     int x, y, z, t;
@@ -81,22 +124,30 @@ __global__ void __launch_bounds__(128) wilson_force_kernel(const ForceArgs A) {
     cplx Xn[12], Yn[12];
     load_spinor(Xn, A.X, s);
     load_spinor(Yn, A.Y, s);
-    wilson_force_dir<0>(A, s, x, A.g.X, 1, Xn, Yn);
-    wilson_force_dir<1>(A, s, y, A.g.Y, A.g.X, Xn, Yn);
-    wilson_force_dir<2>(A, s, z, A.g.Z, A.g.X * A.g.Y, Xn, Yn);
-    wilson_force_dir<3>(A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, Xn, Yn);
+    wilson_force_dir<0, MULTI>(A, s, x, A.g.X, 1, Xn, Yn, x, y, z, t);
+    wilson_force_dir<1, MULTI>(A, s, y, A.g.Y, A.g.X, Xn, Yn, x, y, z, t);
+    wilson_force_dir<2, MULTI>(A, s, z, A.g.Z, A.g.X * A.g.Y, Xn, Yn, x, y, z, t);
+    wilson_force_dir<3, MULTI>(A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, Xn, Yn, x, y, z, t);
 }
 
-template <int MU>
+template <int MU, int MULTI>
 __device__ __forceinline__ void stag_force_dir(const ForceArgs &A, int s, int coord, int dim, int stride, double eta,
-                                               const cplx (&Xn)[3], const cplx (&Yn)[3]) {
+                                               const cplx (&Xn)[3], const cplx (&Yn)[3], int x, int y, int z, int t) {
     const bool w = (coord == dim - 1);
     const int ns = w ? s - (dim - 1) * stride : s + stride;
-    const double phase = w ? A.bc[MU] : 1.0;
-    const cplx *xp = A.X + (size_t)(ns >> 5) * (3 * 32) + (ns & 31), *yp = A.Y + (size_t)(ns >> 5) * (3 * 32) + (ns & 31);
     cplx xf[3], yf[3], hx[3], hy[3];
+    if (MULTI && w && A.g.part[MU]) {
+        const int f = face_index<MU>(A.g, x, y, z, t);
+        const cplx *src = A.fh.recv[MU] + (size_t)(f >> 5) * (12 * 32) + (f & 31);
+        const double phase = A.fh.plast[MU] ? A.bc[MU] : 1.0;
 #pragma unroll
-    for (int c = 0; c < 3; c++) { xf[c] = cscale(phase, ldg128(xp + c * 32)); yf[c] = cscale(phase, ldg128(yp + c * 32)); }
+        for (int c = 0; c < 3; c++) { xf[c] = cscale(phase, __ldcg(src + c * 32)); yf[c] = cscale(phase, __ldcg(src + (3 + c) * 32)); }
+    } else {
+        const double phase = w ? A.bc[MU] : 1.0;
+        const cplx *xp = A.X + (size_t)(ns >> 5) * (3 * 32) + (ns & 31), *yp = A.Y + (size_t)(ns >> 5) * (3 * 32) + (ns & 31);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { xf[c] = cscale(phase, ldg128(xp + c * 32)); yf[c] = cscale(phase, ldg128(yp + c * 32)); }
+    }
     const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -120,7 +171,9 @@ __device__ __forceinline__ void stag_force_dir(const ForceArgs &A, int s, int co
         }
 }
 
+template <int MULTI>
 __global__ void __launch_bounds__(128) staggered_force_kernel(const ForceArgs A) {
+    if (MULTI) wait_force_flags(A);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.g.V) return;
     int x, y, z, t;
@@ -130,21 +183,72 @@ __global__ void __launch_bounds__(128) staggered_force_kernel(const ForceArgs A)
 #pragma unroll
     for (int c = 0; c < 3; c++) { Xn[c] = ldg128(xp + c * 32); Yn[c] = ldg128(yp + c * 32); }
     const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
-    stag_force_dir<0>(A, s, x, A.g.X, 1, 1.0, Xn, Yn);
-    stag_force_dir<1>(A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0, Xn, Yn);
-    stag_force_dir<2>(A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, Xn, Yn);
-    stag_force_dir<3>(A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, Xn, Yn);
+    stag_force_dir<0, MULTI>(A, s, x, A.g.X, 1, 1.0, Xn, Yn, x, y, z, t);
+    stag_force_dir<1, MULTI>(A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0, Xn, Yn, x, y, z, t);
+    stag_force_dir<2, MULTI>(A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, Xn, Yn, x, y, z, t);
+    stag_force_dir<3, MULTI>(A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, Xn, Yn, x, y, z, t);
+}
+
+// ---- multi-GPU: ship the projected LOW-face halves of X and Y to the lower neighbours ----------------------------------------
+template <int MU>
+__device__ __forceinline__ void wilson_force_pack_site(const ForceArgs &A, cplx *dst, int s) {
+    cplx Xs[12], Ys[12];
+    load_spinor(Xs, A.X, s);
+    load_spinor(Ys, A.Y, s);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        cplx a0, a1, b0, b1;
+        project<MU, -1>(a0, a1, Xs[c], Xs[3 + c], Xs[6 + c], Xs[9 + c]);      // P- X(m): the receiver's X(n+mu)
+        project<MU, +1>(b0, b1, Ys[c], Ys[3 + c], Ys[6 + c], Ys[9 + c]);      // P+ Y(m)
+        dst[c * 32] = a0; dst[(3 + c) * 32] = a1; dst[(6 + c) * 32] = b0; dst[(9 + c) * 32] = b1;
+    }
+}
+
+__global__ void __launch_bounds__(128) force_pack_kernel(const ForceArgs A, int kind) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.fh.start[4]) {
+        int mu = 0;
+        while (mu < 3 && i >= A.fh.start[mu + 1]) mu++;
+        const int f = i - A.fh.start[mu];
+        const int s = face_site(A.g, mu, f, 0);
+        cplx *dst = A.fh.send[mu] + (size_t)(f >> 5) * (12 * 32) + (f & 31);
+        if (kind == LQCD_WILSON) {
+            switch (mu) {
+            case 0: wilson_force_pack_site<0>(A, dst, s); break;
+            case 1: wilson_force_pack_site<1>(A, dst, s); break;
+            case 2: wilson_force_pack_site<2>(A, dst, s); break;
+            default: wilson_force_pack_site<3>(A, dst, s); break;
+            }
+        } else {
+            const cplx *xp = A.X + (size_t)(s >> 5) * (3 * 32) + (s & 31), *yp = A.Y + (size_t)(s >> 5) * (3 * 32) + (s & 31);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { dst[c * 32] = ldg128(xp + c * 32); dst[(3 + c) * 32] = ldg128(yp + c * 32); }
+        }
+    }
+    // publish (same pattern as halo_pack_cta): CTA barrier, system fence + ticket, the last CTA raises the flags
+    __syncthreads();
+    __shared__ int fpack_last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        fpack_last = (atomicInc(A.fh.ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (fpack_last && threadIdx.x < 4) {
+        __threadfence_system();
+        if (A.g.part[threadIdx.x]) st_release_sys(A.fh.send_flag[threadIdx.x], A.fh.seq);
+    }
 }
 
 int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);     // context.cu
+int comm_check_error(lqcd_ctx *ctx);                                                                // comm.cu
 
 extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
                                   double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action) {
     if (!ctx || !op || !eta || !out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
     if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
-    if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "lqcd_fermion_force: single-rank only in this round");
     if (eta->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "fermion kind does not match the operator");
     if (op->kind == LQCD_WILSON && op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force implements r = 1 only");
+    if (op->kind == LQCD_WILSON && op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: the clover-term derivative is not implemented (csw must be 0)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     lqcd_fermion *X = x_inout, *Y = nullptr;
     if (!X) {
@@ -157,11 +261,6 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
     LQCD_TRY(lqcd_solve(ctx, op, X, eta, LQCD_SOLVER_CG, LQCD_OP_DDAGD, eps, maxsteps, &it, &rs, nullptr));
     if (iters) *iters = it;
     LQCD_TRY(lqcd_dslash(ctx, op, Y, X, LQCD_OP_D));
-    if (action) {
-        double d[2];
-        LQCD_TRY(lqcd_blas_dot(ctx, eta, X, d));
-        *action = d[0];
-    }
     // force field in the device link layout, then the same conversion path as lqcd_gauge_download
     if (!ctx->force_buf) {
         const size_t fbytes = (size_t)ctx->g.nblk * 4 * 9 * 32 * sizeof(cplx);
@@ -172,12 +271,31 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
     A.out = fbuf; A.X = X->d; A.Y = Y->d; A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     const int bs = 128, grid = (ctx->g.V + bs - 1) / bs;
-    if (op->kind == LQCD_WILSON) wilson_force_kernel<<<grid, bs, 0, ctx->stream>>>(A);
-    else                         staggered_force_kernel<<<grid, bs, 0, ctx->stream>>>(A);
+    const bool multi = ctx->nranks > 1;
+    if (multi) {
+        LQCD_TRY(comm_force_halo(ctx, &A.fh));
+        force_pack_kernel<<<(A.fh.start[4] + bs - 1) / bs, bs, 0, ctx->stream>>>(A, op->kind);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        if (op->kind == LQCD_WILSON) wilson_force_kernel<1><<<grid, bs, 0, ctx->stream>>>(A);
+        else                         staggered_force_kernel<1><<<grid, bs, 0, ctx->stream>>>(A);
+    } else {
+        memset(&A.fh, 0, sizeof A.fh);
+        if (op->kind == LQCD_WILSON) wilson_force_kernel<0><<<grid, bs, 0, ctx->stream>>>(A);
+        else                         staggered_force_kernel<0><<<grid, bs, 0, ctx->stream>>>(A);
+    }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     int rc = LQCD_OK;
     if (e != cudaSuccess) rc = lqcd_fail(ctx, LQCD_ERR_CUDA, "force kernel -> %s", cudaGetErrorString(e));
+    // S_f = <eta, X> (global).  Across ranks this reduction also ORDERS the force slots: it is enqueued after the force
+    // kernel and its all-reduce completes only when every rank has got this far, so it runs on every multi-rank call.
+    if (rc == LQCD_OK && (action || multi)) {
+        double d[2];
+        rc = lqcd_blas_dot(ctx, eta, X, d);
+        if (action) *action = d[0];
+    }
     if (rc == LQCD_OK) rc = download_links_from(ctx, fbuf, out_mu, ndw);
+    if (rc == LQCD_OK) rc = comm_check_error(ctx);
     return rc;
 }

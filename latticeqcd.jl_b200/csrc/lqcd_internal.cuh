@@ -266,6 +266,23 @@ struct WilsonArgs {
     const cplx *clover;   // CLOVER kernels only: packed clover blocks, 36 complex per site (wilson_kernel.cuh); keep LAST
 };
 
+// multi-GPU fermion force: the forward neighbours X(n+mu), Y(n+mu) of the HIGH face sites live on the upper neighbour rank,
+// which stores their spin-projected halves (Wilson: P- X | P+ Y, 12 complex per face site; staggered: X | Y, 6) straight
+// into this rank's force slot of direction mu (dedicated slots of the comm buffer, one sequence flag per direction).
+struct ForceHalo {
+    cplx *send[4];                          // LOWER neighbour's slot for direction mu (peer mapped): my low face goes there
+    unsigned long long *send_flag[4];
+    const cplx *recv[4];                    // my slot: data of the upper neighbour's low face
+    const unsigned long long *recv_flag[4];
+    unsigned long long seq;                 // force call number published in the flags
+    unsigned int *ticket;                   // last-pack-CTA detector (shared with the halo pack: same stream, never concurrent)
+    int *err;
+    long long timeout_cycles;
+    int plast[4];                           // this rank touches the global high boundary in mu (boundary phase on the hop)
+    int start[5];                           // pack work items: prefix over partitioned directions of the face sizes
+};
+int comm_force_halo(lqcd_ctx *ctx, ForceHalo *out);      // comm.cu: bumps the force sequence number
+
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                          const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,

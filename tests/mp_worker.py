@@ -25,7 +25,9 @@ def main():
     dims = tuple(int(v) for v in sys.argv[1].split("x"))
     pg = tuple(int(v) for v in sys.argv[2].split("x"))
     kind_name = sys.argv[3]
-    variant = sys.argv[4] if len(sys.argv) > 4 else ""          # "clover": Wilson-clover (peer-mapped links for the leaves)
+    # variant: "" = operator + CG + CGNR (the subset that has run on hardware); "full" = + multi-shift CG + fermion force;
+    # "clover" = Wilson-clover operator (peer-mapped links for the clover leaves) + multi-shift CG
+    variant = sys.argv[4] if len(sys.argv) > 4 else ""
     csw = 1.5612 if variant == "clover" else 0.0
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -120,16 +122,37 @@ def main():
             if not same_iters(info["iters"], ref[key]):
                 fails.append(f"{name} iters")
             check(f"{name} solution", got, ref[key]["x"], 1e-9)
+    if not variant:                                     # the hardware-verified subset stops here (test_multirank_parity)
+        shifts = []
     ys = [q.similar(x) for _ in shifts]                 # multi-shift CG across ranks (zeta recurrences from all-reduced scalars)
-    info = q.shiftedcg_(ys, D, x, shifts)
+    info = q.shiftedcg_(ys, D, x, shifts) if shifts else {"iters": None}
     for j in range(len(shifts)):
         got = gather(ys[j])
         if rank == 0:
             check(f"multishift x[{j}]", got, ref["ms"]["xs"][j], 1e-9)
-    if rank == 0:
+    if rank == 0 and shifts:
         print(f"[mp] multishift iters {info['iters']} (oracle {ref['ms']['iters']})", flush=True)
         if info["iters"] != ref["ms"]["iters"]:
             fails.append("multishift iters")
+    if variant == "full":                               # fermion force across ranks (force halo slots, force.cu)
+        fa = q.FermiAction(D, {"Nf": 8 if kind == orc.STAGGERED else 2})
+        F = np.zeros((4, lt, lz, ly, lx, 3, 3), dtype=complex)
+        finfo = q.calc_UdSfdU_(F, fa, U, x)
+        h = torch.from_numpy(F.view(np.float64))
+        outF = [torch.empty_like(h) for _ in range(world)] if rank == 0 else None
+        dist.gather(h, outF, dst=0)
+        if rank == 0:
+            full = np.zeros((4,) + tuple(dims[::-1]) + (3, 3), dtype=complex)
+            for r in range(world):
+                (ld, og, _, _) = q.decompose(dims, pg, r)
+                s2 = (slice(og[3], og[3] + ld[3]), slice(og[2], og[2] + ld[2]), slice(og[1], og[1] + ld[1]), slice(og[0], og[0] + ld[0]))
+                full[(slice(None),) + s2] = outF[r].numpy().view(np.complex128)
+            Xr = ref["cg"]["x"]
+            Fr = orc.force(op, kind, Ug, Xr, orc.apply(op, kind, orc.D, Ug, Xr))
+            check("fermion force", full, Fr, 1e-8)
+            act = np.vdot(src, Xr).real
+            if abs(finfo["action"] - act) > 1e-9 * abs(act):
+                fails.append("action")
     flag = torch.tensor([len(fails)])
     dist.broadcast(flag, 0)
     dist.barrier()

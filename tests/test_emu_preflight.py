@@ -58,7 +58,7 @@ def test_gpu_suite_under_emulation(emu_lib):
     assert m and int(m.group(1)) >= 56, tail
 
 
-@pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson"), ("4x4x4x4", "1x1x2x2", "staggered"),
+@pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),
                                           ("4x4x8x4", "1x1x2x2", "Wilson clover")])
 def test_multirank_under_emulation(emu_lib, dims, pg, kind):
     """tests/mp_worker.py as separate processes: peer-mapped halo slots, sequence flags, in-kernel all-reduce (POSIX shm IPC)"""

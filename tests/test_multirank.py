@@ -77,6 +77,18 @@ def test_multirank_parity(dims, pg, kind):
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(reason="multi-rank fermion force + multi-shift (force halo slots): verified under tests/emu only, not yet run on hardware", strict=False)
+@pytest.mark.parametrize("dims,pg,kind", [("8x8x8x16", "1x1x1x2", "Wilson"), ("8x8x8x8", "1x1x2x2", "staggered")])
+def test_multirank_force_parity(dims, pg, kind):
+    """same worker as test_multirank_parity; kept as a separate staged test because the worker now also checks the multi-rank
+    fermion force and multi-shift CG, which have not run on hardware yet (tests/mp_worker.py "full")"""
+    n = int(np.prod([int(v) for v in pg.split("x")]))
+    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, kind, "full", timeout=900)
+    sys.stdout.write(res.stdout[-3000:])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.xfail(reason="multi-rank Wilson-clover: verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("dims,pg", [("8x8x8x16", "1x1x1x2"), ("8x8x8x8", "1x1x2x2")])
 def test_multirank_clover_parity(dims, pg):
