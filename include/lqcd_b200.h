@@ -151,6 +151,12 @@ int lqcd_solve_eo(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_
  * x_inout (nullable) is X (initial guess / result). */
 int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
                        double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action);
+/* The bilinear part alone, for rational actions (RHMC, staggered Nf not in {4, 8}: README.md:132, test/test_Nf2.toml):
+ * calc_UdSfdU! = sum_j alpha_j force(X_j, Y_j) with X_j = (DdagD + beta_j)^-1 phi from lqcd_multishift_cg and Y_j = D X_j.
+ * F <- coef * force(X, Y) (accumulate = 0) or F += coef * force(X, Y) in a link-shaped DEVICE buffer owned by the context;
+ * lqcd_fermion_force_download copies it to the four host arrays (link layout, wing ndw).  Collective across ranks. */
+int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate);
+int lqcd_fermion_force_download(lqcd_ctx *ctx, double *const out_mu[4], int ndw);
 
 /* ---- multi-GPU plumbing (one process per GPU; handles are exchanged by the host: MPI.jl Allgather in
  *      Julia, torch.distributed.all_gather in the Python mirror) ---------------------------------- */

@@ -32,6 +32,8 @@ struct ForceArgs {
     Geom g;
     double kappa;
     double bc[4];
+    double coef;             // out = [out +] coef * force
+    int accumulate;
     ForceHalo fh;            // MULTI kernels only
 };
 
@@ -110,7 +112,10 @@ __device__ __forceinline__ void wilson_force_dir(const ForceArgs &A, int s, int 
             cplx t1 = cmake(0, 0), t2 = cmake(0, 0);
             cfmac(t1, py0[b], gx0[a]); cfmac(t1, py1[b], gx1[a]);
             cfmac(t2, gy0[b], px0[a]); cfmac(t2, gy1[b], px1[a]);
-            o[(a * 3 + b) * 32] = cmake(A.kappa * (t2.x - t1.x), A.kappa * (t2.y - t1.y));
+            const double ck = A.coef * A.kappa;
+            cplx v = cmake(ck * (t2.x - t1.x), ck * (t2.y - t1.y));
+            if (A.accumulate) v = cadd(v, o[(a * 3 + b) * 32]);
+            o[(a * 3 + b) * 32] = v;
         }
 }
 
@@ -159,7 +164,7 @@ __device__ __forceinline__ void stag_force_dir(const ForceArgs &A, int s, int co
         }
     }
     cplx *o = A.out + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
-    const double cf = 0.5 * eta;
+    const double cf = 0.5 * eta * A.coef;
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -167,7 +172,9 @@ __device__ __forceinline__ void stag_force_dir(const ForceArgs &A, int s, int co
             cplx t = cmake(0, 0);
             cfmac(t, Yn[b], hx[a]);
             cfmac(t, hy[b], Xn[a]);
-            o[(a * 3 + b) * 32] = cscale(cf, t);
+            cplx v = cscale(cf, t);
+            if (A.accumulate) v = cadd(v, o[(a * 3 + b) * 32]);
+            o[(a * 3 + b) * 32] = v;
         }
 }
 
@@ -242,33 +249,19 @@ __global__ void __launch_bounds__(128) force_pack_kernel(const ForceArgs A, int 
 int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);     // context.cu
 int comm_check_error(lqcd_ctx *ctx);                                                                // comm.cu
 
-extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
-                                  double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action) {
-    if (!ctx || !op || !eta || !out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
-    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
-    if (eta->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "fermion kind does not match the operator");
-    if (op->kind == LQCD_WILSON && op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force implements r = 1 only");
-    if (op->kind == LQCD_WILSON && op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: the clover-term derivative is not implemented (csw must be 0)");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    lqcd_fermion *X = x_inout, *Y = nullptr;
-    if (!X) {
-        LQCD_TRY(get_scratch(ctx, op->kind, 8, &X));
-        CUDA_TRY(ctx, cudaMemsetAsync(X->d, 0, X->bytes, ctx->stream));
-    }
-    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
-    int it = 0;
-    double rs = 0.0;
-    LQCD_TRY(lqcd_solve(ctx, op, X, eta, LQCD_SOLVER_CG, LQCD_OP_DDAGD, eps, maxsteps, &it, &rs, nullptr));
-    if (iters) *iters = it;
-    LQCD_TRY(lqcd_dslash(ctx, op, Y, X, LQCD_OP_D));
-    // force field in the device link layout, then the same conversion path as lqcd_gauge_download
+// F <- [F +] coef * force(X, Y) into the device-resident link-shaped buffer (RHMC: sum_j alpha_j force(X_j, Y_j) without
+// leaving the GPU).  Collective across ranks.  `barrier_with`: field whose <.,X> reduction closes the call (see header).
+static int force_outer(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate,
+                       const lqcd_fermion *dot_with, double *dot_out) {
     if (!ctx->force_buf) {
         const size_t fbytes = (size_t)ctx->g.nblk * 4 * 9 * 32 * sizeof(cplx);
         CUDA_TRY(ctx, cudaMalloc(&ctx->force_buf, fbytes));
+        ctx->force_valid = false;
     }
-    cplx *fbuf = ctx->force_buf;
+    if (accumulate && !ctx->force_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "force: accumulate requested but no force has been computed yet");
     ForceArgs A;
-    A.out = fbuf; A.X = X->d; A.Y = Y->d; A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa;
+    A.out = ctx->force_buf; A.X = X->d; A.Y = Y->d; A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa;
+    A.coef = coef; A.accumulate = accumulate;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     const int bs = 128, grid = (ctx->g.V + bs - 1) / bs;
     const bool multi = ctx->nranks > 1;
@@ -285,17 +278,61 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
         else                         staggered_force_kernel<0><<<grid, bs, 0, ctx->stream>>>(A);
     }
     ctx->launches++;
-    cudaError_t e = cudaGetLastError();
-    int rc = LQCD_OK;
-    if (e != cudaSuccess) rc = lqcd_fail(ctx, LQCD_ERR_CUDA, "force kernel -> %s", cudaGetErrorString(e));
-    // S_f = <eta, X> (global).  Across ranks this reduction also ORDERS the force slots: it is enqueued after the force
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->force_valid = true;
+    // <dot_with, X> (global).  Across ranks this reduction also ORDERS the force slots: it is enqueued after the force
     // kernel and its all-reduce completes only when every rank has got this far, so it runs on every multi-rank call.
-    if (rc == LQCD_OK && (action || multi)) {
+    if (dot_out || multi) {
         double d[2];
-        rc = lqcd_blas_dot(ctx, eta, X, d);
-        if (action) *action = d[0];
+        LQCD_TRY(lqcd_blas_dot(ctx, dot_with ? dot_with : X, X, d));
+        if (dot_out) *dot_out = d[0];
     }
-    if (rc == LQCD_OK) rc = download_links_from(ctx, fbuf, out_mu, ndw);
-    if (rc == LQCD_OK) rc = comm_check_error(ctx);
-    return rc;
+    return comm_check_error(ctx);
+}
+
+static int check_force_args(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *a, const lqcd_fermion *b) {
+    if (!ctx || !op || !a || !b) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (op->kind != LQCD_WILSON && op->kind != LQCD_STAGGERED) return lqcd_fail(ctx, LQCD_ERR_ARG, "unknown operator kind %d", op->kind);
+    if (a->owner != ctx || b->owner != ctx) return lqcd_fail(ctx, LQCD_ERR_ARG, "field belongs to another context");
+    if (a->kind != op->kind || b->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "fermion kind does not match the operator");
+    if (op->kind == LQCD_WILSON && op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force implements r = 1 only");
+    if (op->kind == LQCD_WILSON && op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: the clover-term derivative is not implemented (csw must be 0)");
+    if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "force requested before lqcd_gauge_upload");
+    return LQCD_OK;
+}
+
+extern "C" int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate) {
+    LQCD_TRY(check_force_args(ctx, op, X, Y));
+    if (X == Y) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: X aliases Y");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return force_outer(ctx, op, X, Y, coef, accumulate, nullptr, nullptr);
+}
+
+extern "C" int lqcd_fermion_force_download(lqcd_ctx *ctx, double *const out_mu[4], int ndw) {
+    if (!ctx || !out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
+    if (!ctx->force_buf || !ctx->force_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "no force on the device");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return download_links_from(ctx, ctx->force_buf, out_mu, ndw);
+}
+
+extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
+                                  double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action) {
+    if (!out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
+    LQCD_TRY(check_force_args(ctx, op, eta, eta));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    lqcd_fermion *X = x_inout, *Y = nullptr;
+    if (!X) {
+        LQCD_TRY(get_scratch(ctx, op->kind, 8, &X));
+        CUDA_TRY(ctx, cudaMemsetAsync(X->d, 0, X->bytes, ctx->stream));
+    }
+    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    int it = 0;
+    double rs = 0.0;
+    LQCD_TRY(lqcd_solve(ctx, op, X, eta, LQCD_SOLVER_CG, LQCD_OP_DDAGD, eps, maxsteps, &it, &rs, nullptr));
+    if (iters) *iters = it;
+    LQCD_TRY(lqcd_dslash(ctx, op, Y, X, LQCD_OP_D));
+    LQCD_TRY(force_outer(ctx, op, X, Y, 1.0, 0, eta, action));          // S_f = <eta, X>
+    return download_links_from(ctx, ctx->force_buf, out_mu, ndw);
 }

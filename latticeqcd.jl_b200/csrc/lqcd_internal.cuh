@@ -158,6 +158,7 @@ struct lqcd_ctx {
     // L2 flush buffer
     void *flush; size_t flush_bytes;
     cplx *force_buf;           // link-shaped output of the force kernel (allocated on first use, reused every MD step)
+    bool force_valid;          // force_buf holds a force (lqcd_fermion_force_xy accumulate / _download)
     uint64_t gauge_epoch;      // bumped by every lqcd_gauge_upload / lqcd_gauge_random
     cplx *clover;              // packed clover term (clover.cu), valid for (clover_epoch, clover_coef)
     uint64_t clover_epoch; double clover_coef;

@@ -169,10 +169,20 @@ struct B200FermiAction
 end
 FermiAction(D::B200Dirac{:D}, parameters_action) = B200FermiAction(D, [similar(D.cpu_template) for _ = 1:4], parameters_action)
 
+# staggered Nf = 4: even-site pseudofermions (odd sites zeroed after the Gaussian sampling and after D^dag) [UPSTREAM-RECALL,
+# SURVEY.md App. C.7]; Nf = 8 and Wilson: all sites.  Other staggered Nf -> B200RHMCAction below.
+even_only(fa::B200FermiAction) = fa.D.op.kind == STAGGERED && get(fa.parameters_action, "Nf", 8) == 4
 "gauss_sampling_in_action!(xi, U, fa) -- src/md/standardMD.jl:95 (host RNG stays the reference's, seeded by Random.seed!, lqcd.jl:61)"
-gauss_sampling_in_action!(ξ, U, fa::B200FermiAction) = LatticeDiracOperators.gauss_distribution_fermion!(ξ)     # [UPSTREAM-RECALL]
+function gauss_sampling_in_action!(ξ, U, fa::B200FermiAction)
+    LatticeDiracOperators.gauss_distribution_fermion!(ξ)                                                        # [UPSTREAM-RECALL]
+    even_only(fa) && LatticeDiracOperators.clear_fermion!(ξ, false)                                             # [UPSTREAM-RECALL] evensite = false
+end
 "sample_pseudofermions!(eta, U, fa, xi): eta = D^dag xi -- src/md/standardMD.jl:96"
-sample_pseudofermions!(η, U, fa::B200FermiAction, ξ) = mul!(η, adjoint(fa.D(U)), ξ)
+function sample_pseudofermions!(η, U, fa::B200FermiAction, ξ)
+    mul!(η, adjoint(fa.D(U)), ξ)
+    even_only(fa) && LatticeDiracOperators.clear_fermion!(η, false)
+    return η
+end
 "evaluate_FermiAction(fa, U, eta) = eta^dag (D^dag D)^-1 eta -- src/updates/standardHMC.jl:69-71"
 function evaluate_FermiAction(fa::B200FermiAction, U, η)
     X = fa._temporary_fermionfields[1]
@@ -192,6 +202,35 @@ function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200FermiA
     GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force, LIB), Cint,
         (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Ptr{ComplexF64}}, Cint, Ref{Cint}, Ref{Cdouble}),
         D.ctx.h, D.op, dη.h, C_NULL, D.eps, D.maxsteps, outs, w, iters, act))
+    return nothing
+end
+
+# ---- rational HMC (staggered Nf not in {4, 8}; README.md:132, test/test_Nf2.toml) -----------------------------------------
+# x^(-Nf/8) ~ a0 + sum_j a[j]/(x + b[j]) (coefficients from AlgRemez_jll as upstream, or any partial-fraction fit): the MD
+# force sum_j a[j] * force(X_j, Y_j) is accumulated on the device, X_j from ONE lqcd_multishift_cg, Y_j = D X_j.
+struct B200RHMCAction
+    D::B200Dirac{:D}
+    a0::Float64; a::Vector{Float64}; b::Vector{Float64}          # action approximation, b ascending
+    _temporary_fermionfields::Vector{Any}
+end
+
+function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200RHMCAction, U, η)
+    D = fa.D(U)
+    n = length(fa.b)
+    dη = D.scratch[1]; upload!(dη, η)
+    X = [B200Field(D.ctx, D.op.kind) for _ = 1:n]; Y = B200Field(D.ctx, D.op.kind)
+    iters = Ref{Cint}(0); rs = Ref{Cdouble}(0.0)
+    check(D.ctx.h, ccall((:lqcd_multishift_cg, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
+        D.ctx.h, D.op, [x.h for x in X], dη.h, fa.b, n, D.eps, D.maxsteps, iters, rs))
+    for j = 1:n
+        check(D.ctx.h, ccall((:lqcd_dslash, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), D.ctx.h, D.op, Y.h, X[j].h, OP_D))
+        check(D.ctx.h, ccall((:lqcd_fermion_force_xy, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                             D.ctx.h, D.op, X[j].h, Y.h, fa.a[j], j > 1 ? 1 : 0))
+    end
+    outs = [pointer(UdSfdU[mu].U) for mu = 1:4]
+    w = hasproperty(UdSfdU[1], :NDW) ? Int(UdSfdU[1].NDW) : 0
+    GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{ComplexF64}}, Cint), D.ctx.h, outs, w))
     return nothing
 end
 

@@ -379,50 +379,97 @@ def shiftedcg_(ys, D: DiracOperator, x: FermionField, shifts, eps=None, maxsteps
 
 
 # ---------------------------------------------------------------------------------------------------
-# fermion action (Wilson 2-flavour / staggered Nf = 8 form: S_f = eta^dag (D^dag D)^-1 eta)
+# fermion actions.  FermiAction(D, parameters_action) (universe.jl:138) picks, like upstream (README.md:132):
+#   Wilson, staggered Nf = 8 : S_f = eta^dag (D^dag D)^-1 eta                                     -> FermiActionB200
+#   staggered Nf = 4         : the same on even-site pseudofermions (D^dag D does not couple parities) -> FermiActionB200(even)
+#   staggered other Nf       : rational HMC, det(D^dag D)^{Nf/8} via multi-shift CG                  -> RHMCFermiAction
 # ---------------------------------------------------------------------------------------------------
 class FermiActionB200:
-    """FermiAction(D, parameters_action) (universe.jl:138)."""
+    """HMC pseudofermion action S_f = eta^dag (D^dag D)^-1 eta."""
 
     def __init__(self, D: DiracOperator, parameters_action: dict):
         self.D = D
         self.Nf = parameters_action.get("Nf", None)
+        # staggered Nf = 4 (SURVEY.md App. C.7, UPSTREAM-RECALL, unverified): pseudofermions live on even sites only, odd
+        # sites are zeroed after the Gaussian sampling and after D^dag.  Kept behind this flag so that a different
+        # upstream convention is a one-line change; with it off the action is the 8-taste one.
+        self.even_only = bool(D.kind == L.STAGGERED and self.Nf == 4 and parameters_action.get("even_site_pseudofermions", True))
         self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]   # standardMD.jl:50
         self.last = {}
 
 
-def FermiAction(D, parameters_action) -> FermiActionB200:
+class RHMCFermiAction:
+    """Rational HMC for staggered Nf not in {4, 8} (test/test_Nf2.toml, test_Nf3.toml): rational approximations of
+    (D^dag D)^{+Nf/16} (heat bath) and (D^dag D)^{-Nf/8} (action, force) evaluated with lqcd_multishift_cg; the force
+    sum_j alpha_j force(X_j, Y_j) is accumulated on the device (lqcd_fermion_force_xy).  Spectral range: the staggered
+    hop is anti-Hermitian with norm <= 4, so spec(D^dag D) lies in [m^2, m^2 + 16]."""
+
+    def __init__(self, D: DiracOperator, parameters_action: dict):
+        from . import rhmc
+        if D.kind != L.STAGGERED:
+            raise ValueError("RHMC is wired for the staggered operator")
+        self.D, self.Nf = D, int(parameters_action["Nf"])
+        m2 = float(D.op.mass) ** 2
+        lo = parameters_action.get("rational_lambda_min", 0.9 * m2)
+        hi = parameters_action.get("rational_lambda_max", 1.05 * (m2 + 16.0))
+        self.rhmc = rhmc.RHMCAction(rhmc.B200Backend(D), self.Nf, lo, hi, order=int(parameters_action.get("rational_order", 12)))
+        self.even_only = False
+        self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]
+        self.last = {}
+
+
+def FermiAction(D, parameters_action):
+    Nf = parameters_action.get("Nf", None)
+    if D.kind == L.STAGGERED and Nf not in (None, 4, 8):
+        return RHMCFermiAction(D, parameters_action)
     return FermiActionB200(D, parameters_action)
 
 
-def gauss_sampling_in_action_(xi: FermionField, U, fa: FermiActionB200, seed=112):     # standardMD.jl:95
+def gauss_sampling_in_action_(xi: FermionField, U, fa, seed=112):     # standardMD.jl:95
     gauss_distribution_fermion_(xi, seed)
+    if fa.even_only:
+        mask_parity_(xi, 0)
 
 
-def sample_pseudofermions_(eta: FermionField, U, fa: FermiActionB200, xi: FermionField):   # standardMD.jl:96
-    """Wilson / staggered Nf=8: eta = D^dag xi.  The staggered Nf=4 even-site variant (App. C.7)
-    is NOT wired: its exact upstream convention (which of xi / eta is restricted, and how S_old = xi.xi is kept exact)
-    cannot be established without the LatticeDiracOperators.jl source; the building block is mask_parity_()."""
+def sample_pseudofermions_(eta: FermionField, U, fa, xi: FermionField):   # standardMD.jl:96
+    """Wilson / staggered Nf = 8: eta = D^dag xi; staggered Nf = 4: odd sites of eta zeroed afterwards
+    (App. C.7); RHMC: eta = (D^dag D)^{Nf/16} xi by the rational approximation."""
     fa.D(U)
+    if isinstance(fa, RHMCFermiAction):
+        substitute_fermion_(eta, fa.rhmc.sample_pseudofermions(xi))
+        return
     mul_(eta, adjoint(fa.D), xi)
+    if fa.even_only:
+        mask_parity_(eta, 0)
 
 
-def evaluate_FermiAction(fa: FermiActionB200, U, eta: FermionField) -> float:           # standardHMC.jl:69-71
-    """S_f = eta^dag (D^dag D)^-1 eta: one CG solve."""
+def evaluate_FermiAction(fa, U, eta: FermionField) -> float:           # standardHMC.jl:69-71
+    """S_f = eta^dag (D^dag D)^-1 eta: one CG solve (RHMC: eta^dag (D^dag D)^{-Nf/8} eta, one multi-shift solve)."""
     D = fa.D(U)
+    if isinstance(fa, RHMCFermiAction):
+        S = fa.rhmc.evaluate(eta)
+        fa.last = {"iters": fa.rhmc.be.last_iters, "action": S}
+        return S
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
     fa.last = solve_DinvX_(X, DdagD(D), eta)
     return dot(eta, X).real
 
 
-def calc_UdSfdU_(UdSfdU: np.ndarray, fa: FermiActionB200, U, eta: FermionField):         # AbstractMD.jl:129
+def calc_UdSfdU_(UdSfdU: np.ndarray, fa, U, eta: FermionField):         # AbstractMD.jl:129
     """Fermion MD force: X = (D^dag D)^-1 eta (CG), Y = D X, per-mu colour outer products.
-    UdSfdU: complex128[4,NT,NZ,NY,NX,3,3] in the link layout, overwritten."""
+    UdSfdU: complex128[4,NT,NZ,NY,NX,3,3] in the link layout, overwritten.  RHMC: sum_j alpha_j force(X_j, Y_j) with the
+    shifted solutions of ONE multi-shift CG, accumulated on the device."""
     D = fa.D(U)
+    out = (C.c_void_p * 4)(*[UdSfdU[mu].ctypes.data for mu in range(4)])
+    if isinstance(fa, RHMCFermiAction):
+        for j, (a, X, Y) in enumerate(fa.rhmc.force_terms(eta)):
+            D.ctx.call("lqcd_fermion_force_xy", C.byref(D.op), X.h, Y.h, float(a), 1 if j else 0)
+        D.ctx.call("lqcd_fermion_force_download", out, 0)
+        fa.last = {"iters": fa.rhmc.be.last_iters}
+        return fa.last
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
-    out = (C.c_void_p * 4)(*[UdSfdU[mu].ctypes.data for mu in range(4)])
     it, act = C.c_int(0), C.c_double(0.0)
     D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, 0, C.byref(it), C.byref(act))
     fa.last = {"iters": it.value, "action": act.value}

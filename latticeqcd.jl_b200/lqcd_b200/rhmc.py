@@ -20,6 +20,7 @@ code runs on the CPU oracle (tests, no GPU) and on the B200 library.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 
 import numpy as np
@@ -41,25 +42,45 @@ class RationalApprox:
 
 
 def rational_approx(power: float, order: int, lo: float, hi: float, npts: int = 400) -> RationalApprox:
-    """x^power ~ alpha0 + sum_j alpha_j/(x + beta_j) on [lo, hi], -1 < power < 1, power != 0."""
+    """x^power ~ alpha0 + sum_j alpha_j/(x + beta_j) on [lo, hi], -1 < power < 1, power != 0 (cached per argument set)."""
+    return _rational_approx(float(power), int(order), float(lo), float(hi), int(npts))
+
+
+@functools.lru_cache(maxsize=64)
+def _rational_approx(power: float, order: int, lo: float, hi: float, npts: int) -> RationalApprox:
+    assert -1.0 < power < 1.0 and power != 0.0 and 0 < lo < hi and order >= 2
+    if power < 0:
+        c0, a, b = _fit_negative_power(power, order, lo, hi, npts, fix_c0=False)
+    else:
+        # x^p = x * x^(p-1): fit the negative power q = p - 1 WITHOUT constant term (its Stieltjes form has none), then
+        # x * sum_j a_j/(x + b_j) = sum_j a_j - sum_j a_j b_j/(x + b_j).  Same relative error as the x^q fit, and the
+        # Levenberg-Marquardt fit of a negative power converges in ~2 s where the direct positive-power fit needed ~30 s.
+        _, a, b = _fit_negative_power(power - 1.0, order, lo, hi, npts, fix_c0=True)
+        c0, a = float(a.sum()), -a * b
+    idx = np.argsort(b)
+    ra = RationalApprox(power, float(c0), a[idx].copy(), b[idx].copy(), lo, hi, 0.0)
+    dense = np.exp(np.linspace(np.log(lo), np.log(hi), 4 * npts))
+    ra.max_rel_err = float(np.abs(ra(dense) / dense ** power - 1.0).max())
+    return ra
+
+
+def _fit_negative_power(power, order, lo, hi, npts, fix_c0):
+    """relative-error least squares (Lawson reweighted towards minimax) of x^power, -1 < power < 0, started from the
+    quadrature of x^-g = (sin(pi g)/pi) int_0^inf t^-g/(x+t) dt on a log grid"""
     from scipy.optimize import least_squares
 
-    assert -1.0 < power < 1.0 and power != 0.0 and 0 < lo < hi and order >= 2
     xs = np.exp(np.linspace(np.log(lo), np.log(hi), npts))
     target = xs ** power
-    g = -power if power < 0 else 1.0 - power          # x^-g = (sin(pi g)/pi) int_0^inf t^-g/(x+t) dt,  0 < g < 1
+    g = -power
     pad = 2.5
     s = np.linspace(np.log(lo) - pad, np.log(hi) + pad, order)
     ds = s[1] - s[0]
     t = np.exp(s)
-    w = np.sin(np.pi * g) / np.pi * t ** (1.0 - g) * ds          # weights of 1/(x+t_j) for x^-g
-    if power < 0:
-        a0, al = 0.0, w
-    else:                                                           # x^p = x * x^-(1-p) = sum w_j (1 - t_j/(x+t_j))
-        a0, al = w.sum(), -w * t
+    al = np.sin(np.pi * g) / np.pi * t ** (1.0 - g) * ds          # weights of 1/(x+t_j)
+    k0 = 0 if fix_c0 else 1
 
     def unpack(p):
-        return p[0], p[1:1 + order], np.exp(p[1 + order:])
+        return (0.0 if fix_c0 else p[0]), p[k0:k0 + order], np.exp(p[k0 + order:])
 
     wts = np.ones_like(xs)
 
@@ -70,18 +91,14 @@ def rational_approx(power: float, order: int, lo: float, hi: float, npts: int = 
     def resid(p):
         return wts * rel(p)
 
-    p = np.concatenate([[a0], al, np.log(t)])
+    p = np.concatenate([[] if fix_c0 else [0.0], al, np.log(t)])
     for _ in range(5):           # Lawson-type reweighting: pushes the least-squares fit towards the minimax (Remez) one
-        p = least_squares(resid, p, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=4000).x
+        p = least_squares(resid, p, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=800).x
         e = np.abs(rel(p))
         wts = wts * (0.5 + e / e.mean())
         wts /= wts.mean()
     c0, a, b = unpack(p)
-    idx = np.argsort(b)
-    ra = RationalApprox(power, float(c0), a[idx].copy(), b[idx].copy(), lo, hi, 0.0)
-    dense = np.exp(np.linspace(np.log(lo), np.log(hi), 4 * npts))
-    ra.max_rel_err = float(np.abs(ra(dense) / dense ** power - 1.0).max())
-    return ra
+    return float(c0), np.array(a), np.array(b)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -167,8 +184,17 @@ class RHMCAction:
         if Nf in (4, 8):
             raise ValueError("Nf = 4, 8 use the plain HMC action (no rational approximation)")
         self.be, self.Nf = backend, Nf
-        self.r_heatbath = rational_approx(+Nf / 16.0, order, lambda_min, lambda_max)
-        self.r_action = rational_approx(-Nf / 8.0, order, lambda_min, lambda_max)
+        self._range = (order, float(lambda_min), float(lambda_max))
+
+    # the fits are computed on first use and cached per (power, order, range): the positive-power (heat-bath) fit is the
+    # slow one (tens of seconds) and is not needed by evaluate / force_terms
+    @property
+    def r_heatbath(self) -> RationalApprox:
+        return rational_approx(+self.Nf / 16.0, *self._range)
+
+    @property
+    def r_action(self) -> RationalApprox:
+        return rational_approx(-self.Nf / 8.0, *self._range)
 
     def _apply_rational(self, ra: RationalApprox, b):
         """alpha0 b + sum_j alpha_j (D^dag D + beta_j)^-1 b with ONE multi-shift solve."""

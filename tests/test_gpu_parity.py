@@ -314,7 +314,7 @@ def test_fermion_force_matches_oracle(Uw, Us, kind):
     U = q.gaugefields_from_array(Uh)
     x = q.Initialize_pseudofermion_fields(U[0], kind)
     D = q.Dirac_operator(U, x, wparams(0.12, eps_CG=1e-24) if kind == "Wilson" else sparams(0.5, eps_CG=1e-24))
-    fa = q.FermiAction(D, {"Nf": 2})
+    fa = q.FermiAction(D, {"Nf": 2 if kind == "Wilson" else 8})       # staggered Nf = 2 would be RHMC (README.md:132)
     eta = q.similar(x)
     phi = orc.gaussian_field(dims, k, seed=41)
     eta.from_host(phi)
