@@ -145,6 +145,15 @@ int lqcd_multishift_cg(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[
 int lqcd_solve_eo(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int method, int target,
                   double eps, int maxsteps, int *iters, double *resid_sq, double *hist);
 
+/* ---- mul!(y, D, x) on HOST fields (the call the Julia shim makes for the reference's CPU pseudofermion types,
+ *      SURVEY.md 8b "Selection" option 1): upload + Dslash + download as one operation, pipelined over slabs of t-slices so
+ *      that the H2D copy, the kernels and the D2H copy overlap (both PCIe directions busy at once).  x_host / y_host: host
+ *      layout of lqcd_fermion_upload / _download with wing ndw (pin them with lqcd_host_register for asynchronous copies);
+ *      x, y: device fields of the operator's kind, left holding the source and the result.  Falls back to the three-call
+ *      sequence where the pipeline does not apply (several ranks, wings, irregular tiling). */
+int lqcd_dslash_host(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, lqcd_fermion *x, double *y_host, const double *x_host,
+                     int mode, int ndw);
+
 /* ---- fermion force: calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129) ---------------
  * Given eta: X = (DdagD)^-1 eta by CG, Y = D X, then the 4 link-shaped outer-product fields are written
  * to the host arrays out_mu (same layout as the links, wing width ndw; the halo is zero-filled).

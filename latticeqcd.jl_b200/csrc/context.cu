@@ -95,7 +95,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false;
-    ctx->eo = nullptr; ctx->eo_active = 0;
+    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -135,6 +135,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
 
 int comm_destroy(lqcd_ctx *ctx);
 void eo_destroy(lqcd_ctx *ctx);       // wilson_eo.cu
+void pipe_destroy(lqcd_ctx *ctx);     // host_pipeline.cu
 
 extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     if (!ctx) return LQCD_OK;
@@ -142,6 +143,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     cudaDeviceSynchronize();
     comm_destroy(ctx);
     eo_destroy(ctx);
+    pipe_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->clover);
@@ -252,6 +254,19 @@ __global__ void convert_fermion_kernel(cplx *dev, cplx *host, Geom g, int w, int
             if (TO_DEVICE) d[c * 32 + lane] = host[hi]; else host[hi] = d[c * 32 + lane];
         }
     }
+}
+
+int convert_fermion_range(lqcd_ctx *ctx, int to_device, cplx *dev, cplx *host_stage, int ncomp, int blk0, int nblk, cudaStream_t s) {
+    const int nspin = ncomp / 3;
+    Geom g = ctx->g;
+    g.nblk = nblk;                                                  // the kernel covers blocks [0, nblk) of the shifted pointers
+    cplx *d = dev + (size_t)blk0 * ncomp * 32, *h = host_stage + (size_t)blk0 * 32 * 3;
+    const int warps = nblk * nspin, bs = 256, grid = (warps * 32 + bs - 1) / bs;
+    if (to_device) convert_fermion_kernel<1><<<grid, bs, 0, s>>>(d, h, g, 0, nspin, (size_t)ctx->g.V);
+    else           convert_fermion_kernel<0><<<grid, bs, 0, s>>>(d, h, g, 0, nspin, (size_t)ctx->g.V);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return LQCD_OK;
 }
 
 static size_t host_volume(const Geom &g, int w) {

@@ -169,6 +169,7 @@ struct lqcd_ctx {
     struct CommState *comm;
     // even-odd preconditioned solve -- see wilson_eo.cu
     struct EoState *eo;
+    struct HostPipe *pipe;     // host-field pipeline (streams, events, two staging buffers) -- see host_pipeline.cu
     int eo_active;             // 1 while lqcd_solve_eo runs the Krylov loop: the solver's operator is Mhat on even half fields
 };
 
@@ -227,6 +228,8 @@ struct DslashFuse {
     const cplx *shift_src;     // field multiplied by `shift` (the input of the first hop of DdagD)
     int interior_only;         // multi-GPU interior pass: reduce over non-boundary sites, deposit partials only
     cplx *axpy_r;              // CG: do not store y; instead r <- r - alpha*y (alpha from SolverState) and reduce |r|^2 in red2
+    int cta_off, cta_count;    // single-rank sub-range launch (host_pipeline.cu): CTAs [cta_off, cta_off + cta_count) of the
+                               // t-slowest tile order = a slab of t-slices; cta_count = 0 -> whole lattice.  No reductions.
 };
 
 // multi-GPU: halo data consumed INSIDE the Dslash kernel (fused exterior).  CTAs are permuted so that tiles
@@ -293,6 +296,10 @@ int ensure_clover(lqcd_ctx *ctx, const lqcd_op *op);
 int launch_wilson_clover(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, int multi, int lh, int grid, int bs, cudaStream_t s);   // wilson_clover.cu
 int apply_op(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, int mode,
              lqcd_fermion *tmp, const DslashFuse *fuse_last);
+
+// context.cu: layout conversion of the 32-site blocks [blk0, blk0 + nblk) between the staged host-layout field and the
+// device AoSoA-32 field (wing 0), enqueued on stream s
+int convert_fermion_range(lqcd_ctx *ctx, int to_device, cplx *dev, cplx *host_stage, int ncomp, int blk0, int nblk, cudaStream_t s);
 
 // blas.cu
 int blas_zero(lqcd_ctx *ctx, cplx *x, size_t n);

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
         if (bid < npack) { halo_pack_cta(A.g, LQCD_STAGGERED, 0, A.in, A.gauge, A.hout, bid); return; }
         bid -= npack;
     }
-    int cta = bid;
+    int cta = bid + A.fuse.cta_off;
     if (MULTI) {
         cta = A.halo.cta_order[bid];
         if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
@@ -163,7 +163,9 @@ int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cpl
     if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
     if (hout) A.hout = *hout; else memset(&A.hout, 0, sizeof A.hout);
     const int bs = 32 * ctx->g.wpc;
-    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
+    const bool sub = A.fuse.cta_count > 0;               // slab launch (host_pipeline.cu): single rank, plain epilogue only
+    if (sub && (halo || A.fuse.dot_with || A.fuse.want_norm || A.fuse.axpy_r)) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range Dslash launch: no halo / reductions");
+    const int grid = sub ? A.fuse.cta_count : (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
     if (halo && hout) staggered_dslash_kernel<2><<<grid, bs, 0, s>>>(A);
     else if (halo) staggered_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
     else      staggered_dslash_kernel<0><<<grid, bs, 0, s>>>(A);

@@ -34,7 +34,9 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     A.clover = nullptr;
     if (op->csw != 0.0) { LQCD_TRY(ensure_clover(ctx, op)); A.clover = ctx->clover; }
     const int bs = 32 * ctx->g.wpc;
-    const int grid = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
+    const bool sub = A.fuse.cta_count > 0;               // slab launch (host_pipeline.cu): single rank, plain epilogue only
+    if (sub && (halo || A.fuse.dot_with || A.fuse.want_norm || A.fuse.axpy_r)) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range Dslash launch: no halo / reductions");
+    const int grid = sub ? A.fuse.cta_count : (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
     // register budget variants (tuning knob LQCD_LB = "maxthreads,minblocks"; default picked by measurement)
     static int lb = -1;
     if (lb < 0) {
@@ -70,11 +72,11 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         ctx->launches++;
         return LQCD_OK;
     }
-    if (family == 3 && !halo) {        // experimental t-marching kernel; falls through when the geometry does not qualify
+    if (family == 3 && !halo && !sub) {        // experimental t-marching kernel; falls through when the geometry does not qualify
         const int rc = launch_wilson_dslash3(ctx, A, dagger, s);
         if (rc != LQCD_ERR_STATE) return rc;
     }
-    if (family == 2 && !halo && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
+    if (family == 2 && !halo && !sub && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
     if (lb == 12804 && bs <= 128) WL(128, 4);

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         if (bid < npack) { halo_pack_cta(A.g, LQCD_WILSON, DAG, A.in, A.gauge, A.hout, bid); return; }
         bid -= npack;
     }
-    int cta = bid;
+    int cta = bid + A.fuse.cta_off;
     if (MULTI) {
         cta = A.halo.cta_order[bid];
         if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);

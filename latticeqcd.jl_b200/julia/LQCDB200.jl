@@ -139,9 +139,12 @@ mode(::B200Dirac{:D}) = OP_D; mode(::B200Dirac{:Ddag}) = OP_DDAG; mode(::B200Dir
 "LinearAlgebra.mul!(y, D, x) -- measure_Pion_correlator.jl:379"
 function mul!(y::AbstractFermionfields, D::B200Dirac, x::AbstractFermionfields)
     dx, dy = D.scratch[1], D.scratch[2]
-    upload!(dx, x)
-    check(D.ctx.h, ccall((:lqcd_dslash, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), D.ctx.h, D.op, dy.h, dx.h, mode(D)))
-    download!(y, dy)
+    # one pipelined upload + Dslash + download (H2D, kernels and D2H overlap over slabs of t-slices); x.f / y.f are the
+    # host arrays [UPSTREAM-RECALL: field name `f`], wing width as in upload!/download!
+    w = hasproperty(x, :NDW) ? Int(x.NDW) : 0
+    GC.@preserve x y check(D.ctx.h, ccall((:lqcd_dslash_host, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
+        D.ctx.h, D.op, dy.h, dx.h, pointer(y.f), pointer(x.f), mode(D), w))
     return y
 end
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "lqcd_blas_dot": (i32, [vp, vp, vp, pdbl]),
     "lqcd_blas_norm2": (i32, [vp, vp, pdbl]),
     "lqcd_dslash": (i32, [vp, pop, vp, vp, i32]),
+    "lqcd_dslash_host": (i32, [vp, pop, vp, vp, vp, vp, i32, i32]),
     "lqcd_clover_term": (i32, [vp, pop, vp]),
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_solve_eo": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),

@@ -344,6 +344,18 @@ def mul_(y: FermionField, A, x: FermionField):
     D.ctx.call("lqcd_dslash", C.byref(D.op), y.h, x.h, mode)
 
 
+def mul_host_(y_host: np.ndarray, A, x_host: np.ndarray, y: FermionField = None, x: FermionField = None):
+    """mul!(y, A, x) for HOST arrays in the Julia layout (what the Julia shim does for the reference's CPU pseudofermion
+    types): one pipelined upload + Dslash + download (lqcd_dslash_host).  y / x: optional device scratch fields."""
+    D, mode = _base(A)
+    x = x or FermionField(D.ctx, D.kind)
+    y = y or FermionField(D.ctx, D.kind)
+    assert x_host.dtype == np.complex128 and y_host.dtype == np.complex128 and x_host.flags.c_contiguous and y_host.flags.c_contiguous
+    assert x_host.shape == x.host_shape and y_host.shape == y.host_shape, (x_host.shape, x.host_shape)
+    D.ctx.call("lqcd_dslash_host", C.byref(D.op), y.h, x.h, y_host.ctypes.data, x_host.ctypes.data, mode, 0)
+    return y_host
+
+
 _METHODS = {"bicg": L.SOLVER_CGNR, "bicgstab": L.SOLVER_BICGSTAB, "preconditiond_bicgstab": L.SOLVER_BICGSTAB}
 
 
