@@ -95,7 +95,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false;
-    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr;
+    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr; ctx->queue = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -123,6 +123,8 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     CT(cudaMalloc(&ctx->red.partials, maxgrid * LQCD_MAX_RED * sizeof(double)));
     CT(cudaMalloc(&ctx->red.ticket, sizeof(unsigned int)));
     CT(cudaMemset(ctx->red.ticket, 0, sizeof(unsigned int)));
+    CT(cudaMalloc(&ctx->queue, sizeof(unsigned int)));
+    CT(cudaMemset(ctx->queue, 0, sizeof(unsigned int)));
     CT(cudaMalloc(&ctx->red.st, sizeof(SolverState)));
     CT(cudaMemset(ctx->red.st, 0, sizeof(SolverState)));
     ctx->red.hist = nullptr;
@@ -147,7 +149,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->clover);
-    cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
+    cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);

@@ -169,6 +169,7 @@ struct lqcd_ctx {
     struct CommState *comm;
     // even-odd preconditioned solve -- see wilson_eo.cu
     struct EoState *eo;
+    unsigned int *queue;       // tile queue of the persistent-CTA Dslash variants (zero between launches)
     struct HostPipe *pipe;     // host-field pipeline (streams, events, two staging buffers) -- see host_pipeline.cu
     int eo_active;             // 1 while lqcd_solve_eo runs the Krylov loop: the solver's operator is Mhat on even half fields
 };
@@ -230,6 +231,8 @@ struct DslashFuse {
     cplx *axpy_r;              // CG: do not store y; instead r <- r - alpha*y (alpha from SolverState) and reduce |r|^2 in red2
     int cta_off, cta_count;    // single-rank sub-range launch (host_pipeline.cu): CTAs [cta_off, cta_off + cta_count) of the
                                // t-slowest tile order = a slab of t-slices; cta_count = 0 -> whole lattice.  No reductions.
+    unsigned int *queue;       // persistent-CTA variants (wilson_kernel.cuh): self-resetting tile queue counter
+    int queue_total;           //   number of tiles (pack + Dslash) drawn from it
 };
 
 // multi-GPU: halo data consumed INSIDE the Dslash kernel (fused exterior).  CTAs are permuted so that tiles

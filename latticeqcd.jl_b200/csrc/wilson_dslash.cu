@@ -57,6 +57,10 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         if (lh) { if (mu_ == 2) WLK(MT, MB, 2, 1); else if (mu_ == 1) WLK(MT, MB, 1, 1); else WLK(MT, MB, 0, 1); } \
         else    { if (mu_ == 2) WLK(MT, MB, 2, 0); else if (mu_ == 1) WLK(MT, MB, 1, 0); else WLK(MT, MB, 0, 0); } \
     } while (0)
+    // experiment (LQCD_PERSIST=1, default off): one wave of persistent CTAs drawing tiles from a queue -- self-packing
+    // multi-GPU launches and plain single-GPU launches of the default register budget only
+    static int persist = -1;
+    if (persist < 0) { const char *e = getenv("LQCD_PERSIST"); persist = (e && atoi(e) == 1) ? 1 : 0; }
     static int lh_env = -2;
     if (lh_env == -2) { const char *e = getenv("LQCD_LINK_HINT"); lh_env = e ? (atoi(e) != 0) : -1; }
     const int lh = lh_env >= 0 ? lh_env : (ctx->g.V <= (1 << 18));
@@ -79,6 +83,21 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     if (family == 2 && !halo && !sub && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
     // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
     // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
+    if (persist && !sub && bs == 128 && lb == 0 && ((halo && hout) || !halo)) {
+        const int pgrid = grid < 3 * ctx->num_sms ? grid : 3 * ctx->num_sms;      // __launch_bounds__(128, 3): 3 CTAs per SM
+        A.fuse.queue = ctx->queue; A.fuse.queue_total = grid;
+#define WLP(MU_, LH_)                                                                           \
+    do {                                                                                        \
+        if (dagger) wilson_dslash_kernel<1, 128, 3, MU_, LH_, 0><<<pgrid, bs, 0, s>>>(A);       \
+        else        wilson_dslash_kernel<0, 128, 3, MU_, LH_, 0><<<pgrid, bs, 0, s>>>(A);       \
+    } while (0)
+        if (halo) { if (lh) WLP(3, 1); else WLP(3, 0); }
+        else      { if (lh) WLP(4, 1); else WLP(4, 0); }
+#undef WLP
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return LQCD_OK;
+    }
     if (lb == 12804 && bs <= 128) WL(128, 4);
     else if (lb == 25602) WL(256, 2);
     else if (lb == 25601 || bs > 128) WL(256, 1);

@@ -82,3 +82,16 @@ def test_tmarch_kernel_under_emulation(emu_lib, bulk):
     assert r.returncode == 0 and "K3 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     m = re.search(r"launches wilson_dslash3_kernel\s+(\d+)", r.stderr)
     assert m and int(m.group(1)) > 500 and "launches wilson_dslash_kernel" not in r.stderr, r.stderr[-2000:]
+
+
+def test_persistent_queue_variant_under_emulation(emu_lib):
+    """LQCD_PERSIST=1 (persistent CTAs drawing tiles from a self-resetting queue): single-rank solver tests + a 2-rank worker"""
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+           "-k", "wilson_dslash_fixture or cg_matches or solve_D or multishift or odd_shapes"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_PERSIST="1"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(33500 + (os.getpid() % 2000)), "tests/mp_worker.py", "4x4x4x8", "1x1x1x2", "Wilson"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120", LQCD_PERSIST="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
