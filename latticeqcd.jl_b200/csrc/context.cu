@@ -5,6 +5,7 @@
 // (universe.jl:107,112) with device-resident AoSoA-32 mirrors (layout: lqcd_internal.cuh).
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
+#include "rng.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -94,7 +95,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     g.V = (int)V; g.nblk = g.V / 32;
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
-    ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false;
+    ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false; ctx->mom = nullptr; ctx->mom_valid = false;
     ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr; ctx->queue = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
@@ -148,7 +149,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     pipe_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
-    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->clover);
+    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover);
     cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);
@@ -275,11 +276,9 @@ static size_t host_volume(const Geom &g, int w) {
     return (size_t)(g.X + 2 * w) * (g.Y + 2 * w) * (g.Z + 2 * w) * (g.T + 2 * w);
 }
 
-extern "C" int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int nc, int ndw) {
-    if (!ctx || !U_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
-    if (nc != 3) return lqcd_fail(ctx, LQCD_ERR_ARG, "only NC = 3 is implemented on the device path (got %d)", nc);
+// the four host arrays (Julia layout, wing ndw) -> a device link-layout field
+int upload_links_to(lqcd_ctx *ctx, cplx *dev_links, const double *const U_mu[4], int ndw) {
     if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t Vh = host_volume(ctx->g, ndw), per = Vh * 9 * sizeof(cplx);
     LQCD_TRY(ensure_stage(ctx, per * 4));
     for (int mu = 0; mu < 4; mu++) {
@@ -287,10 +286,18 @@ extern "C" int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int
         CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->stage + mu * per, U_mu[mu], per, cudaMemcpyHostToDevice, ctx->stream));
     }
     int warps = ctx->g.nblk * 4, bs = 256, grid = (warps * 32 + bs - 1) / bs;
-    convert_links_kernel<1><<<grid, bs, 0, ctx->stream>>>(ctx->gauge, (cplx *)ctx->stage, ctx->g, ndw, Vh * 9);
+    convert_links_kernel<1><<<grid, bs, 0, ctx->stream>>>(dev_links, (cplx *)ctx->stage, ctx->g, ndw, Vh * 9);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LQCD_OK;
+}
+
+extern "C" int lqcd_gauge_upload(lqcd_ctx *ctx, const double *const U_mu[4], int nc, int ndw) {
+    if (!ctx || !U_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (nc != 3) return lqcd_fail(ctx, LQCD_ERR_ARG, "only NC = 3 is implemented on the device path (got %d)", nc);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    LQCD_TRY(upload_links_to(ctx, ctx->gauge, U_mu, ndw));
     ctx->gauge_valid = true; ctx->gauge_epoch++;
     return LQCD_OK;
 }
@@ -426,27 +433,6 @@ extern "C" int lqcd_fermion_copy(lqcd_ctx *ctx, lqcd_fermion *dst, const lqcd_fe
 }
 
 // ---- counter-based generators (identical fields for any process grid) ------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t ctr, double &g0, double &g1) {
-    uint64_t a = splitmix64(seed ^ splitmix64(2 * ctr)), b = splitmix64(seed ^ splitmix64(2 * ctr + 1));
-    double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0);      // (0,1]
-    double u2 = (b >> 11) * (1.0 / 9007199254740992.0);              // [0,1)
-    double rad = sqrt(-2.0 * log(u1)), s, c;
-    sincospi(2.0 * u2, &s, &c);
-    g0 = rad * c; g1 = rad * s;
-}
-__device__ __forceinline__ int global_site(const Geom &g, int s) {
-    int x = s % g.X; s /= g.X;
-    int y = s % g.Y; s /= g.Y;
-    int z = s % g.Z; int t = s / g.Z;
-    return (x + g.o[0]) + g.gX * ((y + g.o[1]) + g.gY * ((z + g.o[2]) + g.gZ * (t + g.o[3])));
-}
-
 __global__ void gauge_random_kernel(cplx *gauge, Geom g, uint64_t seed, double warm_eps) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;    // over V*4, site fastest within mu-major blocks
     if (idx >= g.V * 4) return;

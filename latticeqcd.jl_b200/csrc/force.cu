@@ -301,6 +301,21 @@ static int check_force_args(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion
     return LQCD_OK;
 }
 
+// gauge_md.cu: X = (DdagD)^-1 eta from a zero guess, Y = D X, UdSfdU left in ctx->force_buf (no host transfer)
+int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, int maxsteps, int *iters) {
+    LQCD_TRY(check_force_args(ctx, op, eta, eta));
+    lqcd_fermion *X = nullptr, *Y = nullptr;
+    LQCD_TRY(get_scratch(ctx, op->kind, 8, &X));
+    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    CUDA_TRY(ctx, cudaMemsetAsync(X->d, 0, X->bytes, ctx->stream));
+    int it = 0;
+    double rs = 0.0;
+    LQCD_TRY(lqcd_solve(ctx, op, X, eta, LQCD_SOLVER_CG, LQCD_OP_DDAGD, eps, maxsteps, &it, &rs, nullptr));
+    if (iters) *iters = it;
+    LQCD_TRY(lqcd_dslash(ctx, op, Y, X, LQCD_OP_D));
+    return force_outer(ctx, op, X, Y, 1.0, 0, nullptr, nullptr);
+}
+
 extern "C" int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate) {
     LQCD_TRY(check_force_args(ctx, op, X, Y));
     if (X == Y) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: X aliases Y");

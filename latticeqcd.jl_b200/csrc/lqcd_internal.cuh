@@ -158,6 +158,8 @@ struct lqcd_ctx {
     // L2 flush buffer
     void *flush; size_t flush_bytes;
     cplx *force_buf;           // link-shaped output of the force kernel (allocated on first use, reused every MD step)
+    cplx *mom;                 // MD momenta, link-shaped anti-Hermitian traceless matrices (gauge_md.cu)
+    bool mom_valid;
     bool force_valid;          // force_buf holds a force (lqcd_fermion_force_xy accumulate / _download)
     uint64_t gauge_epoch;      // bumped by every lqcd_gauge_upload / lqcd_gauge_random
     cplx *clover;              // packed clover term (clover.cu), valid for (clover_epoch, clover_coef)

@@ -237,4 +237,31 @@ function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200RHMCAc
     return nothing
 end
 
+# ---- device-resident molecular dynamics (src/md/standardMD.jl:103-165, src/md/AbstractMD.jl:78-135) -------------------------
+# runMD!(U, md) for a StandardMD whose fermi_action is a B200FermiAction (or quenched): the links are uploaded once, momenta
+# are sampled on the device, U_update! / P_update! / P_update_fermion! run as kernels (lqcd_md_trajectory), and U is
+# downloaded at the end.  md.p (host momenta) is bypassed: Sp_old / Sp_new come from lqcd_md_kinetic.
+function runMD_b200!(U::Vector{<:AbstractGaugefields{3,4}}, ctx::B200Context, β, Δτ, MDsteps; fa::Union{Nothing,B200FermiAction}=nothing,
+                     η=nothing, SextonWeingargten=false, Nsw=2, seed=rand(UInt64))
+    upload_links!(ctx, U)
+    check(ctx.h, ccall((:lqcd_md_momenta_gaussian, LIB), Cint, (Ptr{Cvoid}, UInt64), ctx.h, seed))
+    K0 = Ref{Cdouble}(0.0); check(ctx.h, ccall((:lqcd_md_kinetic, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), ctx.h, K0))
+    its = Ref{Clonglong}(0)
+    if fa === nothing
+        check(ctx.h, ccall((:lqcd_md_trajectory, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Ref{Clonglong}),
+            ctx.h, C_NULL, C_NULL, β, Δτ, MDsteps, SextonWeingargten ? Nsw : 0, 0.0, 1, its))
+    else
+        dη = fa.D.scratch[1]; upload!(dη, η)
+        check(ctx.h, ccall((:lqcd_md_trajectory, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Ref{Clonglong}),
+            ctx.h, fa.D.op, dη.h, β, Δτ, MDsteps, SextonWeingargten ? Nsw : 0, fa.D.eps, fa.D.maxsteps, its))
+    end
+    K1 = Ref{Cdouble}(0.0); check(ctx.h, ccall((:lqcd_md_kinetic, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), ctx.h, K1))
+    w = hasproperty(U[1], :NDW) ? Int(U[1].NDW) : 0
+    ptrs = [pointer(U[mu].U) for mu = 1:4]
+    GC.@preserve U check(ctx.h, ccall((:lqcd_gauge_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{ComplexF64}}, Cint, Cint), ctx.h, ptrs, 3, w))
+    return (Sp_old = K0[], Sp_new = K1[], cg_iters = its[])
+end
+
 end # module

@@ -486,3 +486,106 @@ def calc_UdSfdU_(UdSfdU: np.ndarray, fa, U, eta: FermionField):         # Abstra
     D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, 0, C.byref(it), C.byref(act))
     fa.last = {"iters": it.value, "action": act.value}
     return fa.last
+
+
+# ---------------------------------------------------------------------------------------------------
+# gauge-sector molecular dynamics on the device (src/md/AbstractMD.jl:78-135, src/md/standardMD.jl:103-165,
+# src/updates/standardHMC.jl:41-91): links, momenta and pseudofermions stay in HBM for a whole trajectory
+# ---------------------------------------------------------------------------------------------------
+def _link_ptrs(a):
+    return (C.c_void_p * 4)(*[a[mu].ctypes.data for mu in range(4)])
+
+
+def gauss_distribution_momenta_(ctx: Context, seed=113):             # gauss_distribution!(md.p), standardMD.jl:86
+    ctx.call("lqcd_md_momenta_gaussian", int(seed))
+
+
+def set_momenta_(ctx: Context, P: np.ndarray):
+    """P: complex128[4,NT,NZ,NY,NX,3,3] anti-Hermitian traceless matrices in the link layout"""
+    P = np.ascontiguousarray(P, dtype=np.complex128)
+    ctx.call("lqcd_md_momenta_upload", _link_ptrs(P), 0)
+
+
+def get_momenta(ctx: Context) -> np.ndarray:
+    NX, NY, NZ, NT = ctx.local_dims
+    P = np.zeros((4, NT, NZ, NY, NX, 3, 3), dtype=np.complex128)
+    ctx.call("lqcd_md_momenta_download", _link_ptrs(P), 0)
+    return P
+
+
+def get_links(ctx: Context) -> np.ndarray:
+    NX, NY, NZ, NT = ctx.local_dims
+    U = np.zeros((4, NT, NZ, NY, NX, 3, 3), dtype=np.complex128)
+    ctx.call("lqcd_gauge_download", _link_ptrs(U), 3, 0)
+    return U
+
+
+def kinetic_energy(ctx: Context) -> float:                            # md.p * md.p / 2, standardHMC.jl:47
+    out = C.c_double()
+    ctx.call("lqcd_md_kinetic", C.byref(out))
+    return out.value
+
+
+def gauge_action(ctx: Context, beta: float) -> float:                 # -evaluate_GaugeAction(gauge_action, U) / NC, standardHMC.jl:49-50
+    out = C.c_double()
+    ctx.call("lqcd_md_gauge_action", float(beta), C.byref(out))
+    return out.value
+
+
+def U_update_(ctx: Context, eps_dtau: float):                         # U_update!(U, p, eps, md) with eps*md.dtau folded in
+    ctx.call("lqcd_md_update_U", float(eps_dtau))
+
+
+def P_update_(ctx: Context, eps_dtau: float, beta: float):            # P_update!
+    ctx.call("lqcd_md_update_P", float(eps_dtau), float(beta))
+
+
+def P_update_fermion_(D: DiracOperator, eta: FermionField, eps_dtau: float) -> int:      # P_update_fermion!
+    it = C.c_int(0)
+    D.ctx.call("lqcd_md_update_P_fermion", C.byref(D.op), eta.h, float(eps_dtau), D.eps, D.maxsteps, C.byref(it))
+    return it.value
+
+
+def runMD_(ctx: Context, beta, dtau, MDsteps, D: DiracOperator = None, eta: FermionField = None, SextonWeingargten=False, Nsw=2) -> int:
+    """runMD!(U, md) on the device-resident links (standardMD.jl:103-165); returns the CG iterations spent in fermion forces"""
+    its = C.c_longlong(0)
+    nsw = int(Nsw) if SextonWeingargten else 0
+    ctx.call("lqcd_md_trajectory", C.byref(D.op) if D is not None else None, eta.h if eta is not None else None,
+             float(beta), float(dtau), int(MDsteps), nsw, D.eps if D is not None else 0.0, D.maxsteps if D is not None else 1, C.byref(its))
+    return its.value
+
+
+def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=False, Nsw=2, rng=None, seed=1):
+    """update!(updatemethod::StandardHMC, U) (standardHMC.jl:41-91) with the molecular dynamics on the device: upload U once,
+    sample p / xi / eta, S_old, runMD!, S_new, Metropolis test on the host, and U is overwritten only when accepted.
+    Plain-HMC fermion actions (Wilson, staggered Nf = 4, 8); returns (accepted, S_new - S_old, info)."""
+    ctx = U.context()
+    if fa is not None and isinstance(fa, RHMCFermiAction):
+        raise NotImplementedError("device-resident trajectories are wired for the plain HMC actions")
+    rng = rng or np.random.default_rng(seed)
+    if fa is not None:
+        D = fa.D(U)                                                   # uploads the links
+    else:
+        D = None
+        ctx.call("lqcd_gauge_upload", _link_ptrs(U.data), 3, 0)
+    gauss_distribution_momenta_(ctx, int(rng.integers(1 << 62)))
+    S_old = kinetic_energy(ctx) + gauge_action(ctx, beta)
+    eta = None
+    if fa is not None:
+        xi, eta = fa._temporary_fermionfields[1], fa._temporary_fermionfields[2]
+        gauss_sampling_in_action_(xi, U, fa, seed=int(rng.integers(1 << 62)))
+        mul_(eta, adjoint(D), xi)                                     # sample_pseudofermions! without re-uploading U
+        if fa.even_only:
+            mask_parity_(eta, 0)
+        S_old += dot(xi, xi).real                                     # standardHMC.jl:54
+    its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw)
+    S_new = kinetic_energy(ctx) + gauge_action(ctx, beta)
+    if fa is not None:
+        X = fa._temporary_fermionfields[0]
+        clear_fermion_(X)
+        solve_DinvX_(X, DdagD(D), eta)
+        S_new += dot(eta, X).real
+    accept = bool(np.exp(min(0.0, S_old - S_new)) >= rng.random())    # exp(Sold - Snew) >= rand(), standardHMC.jl:79
+    if accept:
+        U.data[...] = get_links(ctx)
+    return accept, S_new - S_old, {"cg_iters": its, "S_old": S_old, "S_new": S_new}

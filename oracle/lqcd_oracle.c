@@ -645,3 +645,119 @@ int orc_eo_solve(const orc_op *op, int method, int dagger, zc *x, const zc *cons
     free(bh); free(xe); free(t);
     return it;
 }
+
+/* ---- gauge-sector molecular dynamics: the steps of src/md/AbstractMD.jl:78-135 -------------------------
+ *  U_update!          U_mu <- exptU(eps*dtau * p_mu) * U_mu                                  (AbstractMD.jl:78-99)
+ *  P_update!          p_mu <- p_mu + (-eps*dtau/NC) * Traceless_antihermitian(U_mu * dSdU_mu)  (AbstractMD.jl:101-118),
+ *                     plaquette action beta/2 * (P + P^dag) (universe.jl:90-93), S_g = -(beta/NC) sum_plaq Re tr U_p
+ *                     (standardHMC.jl:49-50)
+ *  P_update_fermion!  p_mu <- p_mu + (-eps*dtau) * Traceless_antihermitian(UdSfdU_mu)        (AbstractMD.jl:120-135)
+ *  Momenta are kept as anti-Hermitian traceless 3x3 matrices p = sum_a a_a T_a, T_a = i lambda_a / 2 (upstream stores the
+ *  eight real a_a [UPSTREAM-RECALL]); p*p/2 = sum a^2/2 = sum_ij |p_ij|^2.  TA(M) = (M - M^dag)/2 - tr/3.  With these
+ *  conventions Hamilton's equations for H = p*p/2 + S_g + S_f give exactly the factors above (beta/(2 NC) for the plaquette
+ *  term): the known-answer tests are energy conservation at O(dtau^2) and reversibility, not a reference number.      */
+static void ta3(zc *a, const zc *m) {                      /* traceless anti-Hermitian part */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i + 3 * j] = 0.5 * (m[i + 3 * j] - conj(m[j + 3 * i]));
+    zc tr = (a[0] + a[4] + a[8]) / 3.0;
+    a[0] -= tr; a[4] -= tr; a[8] -= tr;
+}
+/* exp of a 3x3 matrix: scaling (Frobenius norm <= 1/4), Taylor order 12 by Horner, squaring.  The device code repeats
+ * the same operations in the same order (csrc/gauge_md.cu: expm3). */
+static void expm3(zc *e, const zc *x0) {
+    double n2 = 0;
+    for (int i = 0; i < 9; i++) n2 += creal(x0[i]) * creal(x0[i]) + cimag(x0[i]) * cimag(x0[i]);
+    double nrm = sqrt(n2), sc = 1.0;
+    int sq = 0;
+    while (nrm > 0.25) { nrm *= 0.5; sc *= 0.5; sq++; }
+    zc x[9], t[9];
+    for (int i = 0; i < 9; i++) x[i] = sc * x0[i];
+    for (int i = 0; i < 9; i++) e[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int k = 12; k >= 1; k--) {                        /* e = 1 + (x/k) e */
+        mm(t, x, e);
+        for (int i = 0; i < 9; i++) e[i] = ((i % 4 == 0) ? 1.0 : 0.0) + t[i] / (double)k;
+    }
+    for (int q = 0; q < sq; q++) { mm(t, e, e); memcpy(e, t, sizeof t); }
+}
+
+void orc_md_update_u(const int dims[4], zc *const u[4], const zc *const p[4], double eps) {
+    geom g = mkgeom(dims);
+    for (int mu = 0; mu < 4; mu++) {
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < g.V; s++) {
+            zc x[9], e[9], w[9];
+            for (int i = 0; i < 9; i++) x[i] = eps * p[mu][9 * s + i];
+            expm3(e, x);
+            mm(w, e, u[mu] + 9 * s);
+            memcpy(u[mu] + 9 * s, w, sizeof w);
+        }
+    }
+}
+
+/* sum of the six staples closing U_mu(n): V such that Re tr[U_mu(n) V] = sum of the six plaquettes through the link */
+static void staple_sum(const geom *g, const zc *const u[4], int64_t s, const int c[4], int mu, zc *v) {
+    memset(v, 0, 9 * sizeof(zc));
+    int w;
+    const int64_t smu = nbr(g, s, c, mu, +1, &w);
+    int cmu[4] = {c[0], c[1], c[2], c[3]};
+    cmu[mu] = (c[mu] + 1) % g->d[mu];
+    for (int nu = 0; nu < 4; nu++) {
+        if (nu == mu) continue;
+        const int64_t snu = nbr(g, s, c, nu, +1, &w), sdn = nbr(g, s, c, nu, -1, &w), smudn = nbr(g, smu, cmu, nu, -1, &w);
+        zc a[9], b[9];
+        mmd(a, u[nu] + 9 * smu, u[mu] + 9 * snu);         /* U_nu(n+mu) U_mu(n+nu)^dag */
+        mmd(b, a, u[nu] + 9 * s);                          /* ... U_nu(n)^dag           */
+        for (int i = 0; i < 9; i++) v[i] += b[i];
+        /* lower staple: U_nu(n+mu-nu)^dag U_mu(n-nu)^dag U_nu(n-nu) */
+        zc t[9];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {      /* t = U_nu(n+mu-nu)^dag U_mu(n-nu)^dag */
+            zc sacc = 0;
+            for (int k = 0; k < 3; k++) sacc += conj(u[nu][9 * smudn + k + 3 * i]) * conj(u[mu][9 * sdn + j + 3 * k]);
+            t[i + 3 * j] = sacc;
+        }
+        mm(b, t, u[nu] + 9 * sdn);
+        for (int i = 0; i < 9; i++) v[i] += b[i];
+    }
+}
+
+void orc_md_update_p_gauge(const int dims[4], zc *const p[4], const zc *const u[4], double eps, double beta) {
+    geom g = mkgeom(dims);
+    const double f = eps * beta / 6.0;                     /* beta / (2 NC) */
+    for (int mu = 0; mu < 4; mu++) {
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < g.V; s++) {
+            int c[4]; site_coords(&g, s, c);
+            zc v[9], m[9], a[9];
+            staple_sum(&g, u, s, c, mu, v);
+            mm(m, u[mu] + 9 * s, v);
+            ta3(a, m);
+            for (int i = 0; i < 9; i++) p[mu][9 * s + i] -= f * a[i];
+        }
+    }
+}
+
+void orc_md_update_p_force(const int dims[4], zc *const p[4], const zc *const F[4], double eps) {
+    geom g = mkgeom(dims);
+    for (int mu = 0; mu < 4; mu++) {
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < g.V; s++) {
+            zc a[9];
+            ta3(a, F[mu] + 9 * s);
+            for (int i = 0; i < 9; i++) p[mu][9 * s + i] -= eps * a[i];
+        }
+    }
+}
+
+double orc_md_kinetic(const int dims[4], const zc *const p[4]) {
+    geom g = mkgeom(dims);
+    double sum = 0;
+    for (int mu = 0; mu < 4; mu++) {
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+        for (int64_t i = 0; i < 9 * g.V; i++) sum += creal(p[mu][i]) * creal(p[mu][i]) + cimag(p[mu][i]) * cimag(p[mu][i]);
+    }
+    return sum;
+}
+
+double orc_md_gauge_action(const int dims[4], const zc *const u[4], double beta) {
+    geom g = mkgeom(dims);
+    return -(beta / 3.0) * orc_plaquette(dims, u) * 18.0 * (double)g.V;
+}

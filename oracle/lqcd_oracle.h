@@ -103,4 +103,12 @@ void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4
  * (0,1),(0,2),(0,3),(1,2),(1,3),(2,3), [a + 3 b]) receives F^_mu_nu for tests. */
 void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4]);
 
+/* gauge-sector molecular dynamics steps (src/md/AbstractMD.jl:78-135): momenta p[mu][a + 3*(b + 3*site)] are anti-Hermitian
+ * traceless matrices; see the block comment in lqcd_oracle.c for the conventions. */
+void   orc_md_update_u(const int dims[4], zc *const u[4], const zc *const p[4], double eps);                 /* U <- exp(eps p) U   */
+void   orc_md_update_p_gauge(const int dims[4], zc *const p[4], const zc *const u[4], double eps, double beta); /* p -= eps beta/6 TA(U V) */
+void   orc_md_update_p_force(const int dims[4], zc *const p[4], const zc *const F[4], double eps);           /* p -= eps TA(F)      */
+double orc_md_kinetic(const int dims[4], const zc *const p[4]);                                             /* p*p/2 = sum |p_ij|^2 */
+double orc_md_gauge_action(const int dims[4], const zc *const u[4], double beta);                           /* -(beta/3) sum Re tr U_p */
+
 #endif

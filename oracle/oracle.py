@@ -77,6 +77,11 @@ def lib() -> C.CDLL:
         L.orc_eo_solve.argtypes = [op, ci, ci, vp, pp, vp, dbl, ci, C.POINTER(dbl), vp]
         L.orc_eo_solve.restype = ci
         L.orc_wilson_hop_parity.argtypes = [op, ci, ci, vp, pp, vp]
+        L.orc_md_update_u.argtypes = [C.POINTER(ci), pp, pp, dbl]
+        L.orc_md_update_p_gauge.argtypes = [C.POINTER(ci), pp, pp, dbl, dbl]
+        L.orc_md_update_p_force.argtypes = [C.POINTER(ci), pp, pp, dbl]
+        L.orc_md_kinetic.argtypes = [C.POINTER(ci), pp]; L.orc_md_kinetic.restype = dbl
+        L.orc_md_gauge_action.argtypes = [C.POINTER(ci), pp, dbl]; L.orc_md_gauge_action.restype = dbl
         _LIB = L
     return _LIB
 
@@ -194,6 +199,43 @@ def clover_build(op: OrcOp, U: np.ndarray, want_f=False):
 def plaquette(dims, U) -> float:
     d = (C.c_int * 4)(*[int(v) for v in dims])
     return lib().orc_plaquette(d, _uptrs(U))
+
+
+# ---- gauge-sector MD steps (src/md/AbstractMD.jl:78-135); U, P: complex128[4,NT,NZ,NY,NX,3,3] link layout, updated in place
+def _dims(dims):
+    return (C.c_int * 4)(*dims)
+
+
+def md_update_u(dims, U, P, eps):
+    lib().orc_md_update_u(_dims(dims), _uptrs(U), _uptrs(P), float(eps))
+
+
+def md_update_p_gauge(dims, P, U, eps, beta):
+    lib().orc_md_update_p_gauge(_dims(dims), _uptrs(P), _uptrs(U), float(eps), float(beta))
+
+
+def md_update_p_force(dims, P, F, eps):
+    lib().orc_md_update_p_force(_dims(dims), _uptrs(P), _uptrs(F), float(eps))
+
+
+def md_kinetic(dims, P) -> float:
+    return lib().orc_md_kinetic(_dims(dims), _uptrs(P))
+
+
+def md_gauge_action(dims, U, beta) -> float:
+    return lib().orc_md_gauge_action(_dims(dims), _uptrs(U), float(beta))
+
+
+def md_momenta(dims, seed=1) -> np.ndarray:
+    """p = sum_a a_a i lambda_a / 2 with a_a ~ N(0,1) (numpy RNG; the device has its own counter-based generator)"""
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((4,) + tuple(dims[::-1]) + (8,))
+    lam = np.zeros((8, 3, 3), dtype=complex)
+    lam[0][0, 1] = lam[0][1, 0] = 1; lam[1][0, 1] = -1j; lam[1][1, 0] = 1j; lam[2][0, 0] = 1; lam[2][1, 1] = -1
+    lam[3][0, 2] = lam[3][2, 0] = 1; lam[4][0, 2] = -1j; lam[4][2, 0] = 1j; lam[5][1, 2] = lam[5][2, 1] = 1
+    lam[6][1, 2] = -1j; lam[6][2, 1] = 1j; lam[7] = np.diag([1, 1, -2]) / np.sqrt(3)
+    P = 0.5j * np.einsum("...a,aij->...ij", a, lam)
+    return np.ascontiguousarray(np.swapaxes(P, -1, -2))          # host layout [.., b, a]
 
 
 def force(op, kind, U, X, Y) -> np.ndarray:

@@ -1,0 +1,190 @@
+"""Gauge-sector molecular dynamics: the steps of src/md/AbstractMD.jl:78-135 and the leapfrog
+integrators of src/md/standardMD.jl:125-165.  CPU: the oracle's restatement is pinned by what an integrator must satisfy
+whatever the generator normalisation -- energy conservation at O(dtau^2) (a wrong force factor breaks the scaling) and
+reversibility.  GPU (staged: written after the round's GPU budget was spent, verified under tests/emu): device steps and a
+whole Sexton-Weingarten trajectory against the oracle composed step by step."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+DIMS = (4, 4, 4, 4)
+BETA = 5.7            # test/test_wilson.toml
+KAPPA = 0.141139
+
+
+@pytest.fixture(scope="module")
+def Uw(golden_dir):
+    return np.load(golden_dir / "wilson_4444.npy")
+
+
+def _traj(U, P, dtau, n, nsw=0, fermion=None):
+    """runMD_QPQ! / runMD_QPQ_sw! (standardMD.jl:125-165) composed from the oracle's steps; fermion = (op, kind, eta)"""
+    U, P = U.copy(), P.copy()
+
+    def pf(eps):
+        op, kind, eta = fermion
+        X = orc.cg(op, kind, U, eta, eps=1e-22)["x"]
+        orc.md_update_p_force(DIMS, P, orc.force(op, kind, U, X, orc.apply(op, kind, orc.D, U, X)), eps)
+
+    for _ in range(n):
+        if nsw == 0:
+            orc.md_update_u(DIMS, U, P, 0.5 * dtau)
+            orc.md_update_p_gauge(DIMS, P, U, dtau, BETA)
+            if fermion:
+                pf(dtau)
+            orc.md_update_u(DIMS, U, P, 0.5 * dtau)
+        else:
+            for half in range(2):
+                for _ in range(nsw // 2):
+                    orc.md_update_u(DIMS, U, P, 0.5 * dtau / nsw)
+                    orc.md_update_p_gauge(DIMS, P, U, dtau / nsw, BETA)
+                    orc.md_update_u(DIMS, U, P, 0.5 * dtau / nsw)
+                if half == 0 and fermion:
+                    pf(dtau)
+    return U, P
+
+
+def _H(U, P, fermion=None):
+    H = orc.md_kinetic(DIMS, P) + orc.md_gauge_action(DIMS, U, BETA)
+    if fermion:
+        op, kind, eta = fermion
+        H += np.vdot(eta, orc.cg(op, kind, U, eta, eps=1e-22)["x"]).real
+    return H
+
+
+def test_momenta_and_kinetic_term():
+    P = orc.md_momenta(DIMS, seed=3)
+    M = np.swapaxes(P, -1, -2)
+    assert np.abs(M + np.conj(np.swapaxes(M, -1, -2))).max() < 1e-15          # anti-Hermitian
+    assert np.abs(np.trace(M, axis1=-2, axis2=-1)).max() < 1e-15              # traceless
+    K = orc.md_kinetic(DIMS, P)                                               # = sum a^2 / 2, 8 real a per link
+    assert abs(K / (4 * 256 * 8 / 2) - 1.0) < 0.05
+
+
+def test_quenched_leapfrog_energy_scaling_and_reversibility(Uw):
+    P0 = orc.md_momenta(DIMS, seed=3)
+    H0 = _H(Uw, P0)
+    dH = []
+    for dtau, n in ((0.1, 10), (0.05, 20), (0.025, 40)):
+        U1, P1 = _traj(Uw, P0, dtau, n)
+        dH.append(_H(U1, P1) - H0)
+    assert abs(dH[0]) < 2.0 and 3.0 < dH[0] / dH[1] < 5.0 and 3.0 < dH[1] / dH[2] < 5.0      # O(dtau^2)
+    U1, P1 = _traj(Uw, P0, 0.05, 20)
+    U2, P2 = _traj(U1, -P1, 0.05, 20)
+    assert np.abs(U2 - Uw).max() < 1e-12 and np.abs(P2 + P0).max() < 1e-12
+    assert np.abs(np.einsum("...ij,...kj->...ik", U1, U1.conj()) - np.eye(3)).max() < 1e-9     # exp keeps SU(3)
+
+
+@pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
+def test_dynamical_leapfrog_energy_scaling(Uw, kind):
+    """with the pseudofermion force (P_update_fermion!): the relative weight of gauge and fermion force must be right"""
+    op = orc.make_op(DIMS, kappa=0.12, mass=0.5)
+    xi = orc.gaussian_field(DIMS, kind, seed=9)
+    eta = orc.apply(op, kind, orc.DDAG, Uw, xi)
+    P0 = orc.md_momenta(DIMS, seed=4)
+    f = (op, kind, eta)
+    H0 = _H(Uw, P0, f)
+    assert abs(H0 - (orc.md_kinetic(DIMS, P0) + orc.md_gauge_action(DIMS, Uw, BETA) + np.vdot(xi, xi).real)) < 1e-8 * abs(H0)
+    dH = []
+    for dtau, n in ((0.05, 10), (0.025, 20), (0.0125, 40)):          # asymptotic regime of the fermion force
+        U1, P1 = _traj(Uw, P0, dtau, n, nsw=0, fermion=f)
+        dH.append(_H(U1, P1, f) - H0)
+    print("dH", dH)
+    assert abs(dH[0]) < 1.0 and 2.5 < dH[0] / dH[1] < 6.0 and 3.0 < dH[1] / dH[2] < 5.0
+    # Sexton-Weingarten nesting integrates the same Hamiltonian
+    U2, P2 = _traj(Uw, P0, 0.05, 10, nsw=4, fermion=f)
+    assert abs(_H(U2, P2, f) - H0) < 1.0
+
+
+# ---- device ----------------------------------------------------------------------------------------------------------------
+staged = pytest.mark.xfail(reason="gauge-sector MD kernels: verified under tests/emu only, not yet run on hardware", strict=False)
+
+
+@pytest.mark.gpu
+@staged
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4)])
+def test_md_steps_match_oracle(dims):
+    import lqcd_b200 as q
+    U0 = orc.random_su3(dims, seed=31, eps=0.4)
+    P0 = orc.md_momenta(dims, seed=32)
+    U = q.gaugefields_from_array(U0.copy())
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": 0.12, "eps_CG": 1e-22, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    ctx = D.ctx
+    q.set_momenta_(ctx, P0)
+    assert np.array_equal(q.get_momenta(ctx), P0)
+    assert abs(q.kinetic_energy(ctx) - orc.md_kinetic(dims, P0)) < 1e-10 * orc.md_kinetic(dims, P0)
+    assert abs(q.gauge_action(ctx, BETA) - orc.md_gauge_action(dims, U0, BETA)) < 1e-10 * abs(orc.md_gauge_action(dims, U0, BETA))
+    Ur, Pr = U0.copy(), P0.copy()
+    q.P_update_(ctx, 0.07, BETA); orc.md_update_p_gauge(dims, Pr, Ur, 0.07, BETA)
+    assert np.abs(q.get_momenta(ctx) - Pr).max() < 1e-13
+    q.U_update_(ctx, 0.11); orc.md_update_u(dims, Ur, Pr, 0.11)
+    assert np.abs(q.get_links(ctx) - Ur).max() < 1e-13
+    op = orc.make_op(dims, kappa=0.12)
+    eta_h = orc.gaussian_field(dims, orc.WILSON, seed=33)
+    eta = q.similar(x).from_host(eta_h)
+    its = q.P_update_fermion_(D, eta, 0.05)
+    ref = orc.cg(op, orc.WILSON, Ur, eta_h, eps=1e-22)
+    orc.md_update_p_force(dims, Pr, orc.force(op, orc.WILSON, Ur, ref["x"], orc.apply(op, orc.WILSON, orc.D, Ur, ref["x"])), 0.05)
+    assert its == ref["iters"]
+    assert np.abs(q.get_momenta(ctx) - Pr).max() < 1e-10
+    # device Gaussian momenta: anti-Hermitian, traceless, <a^2> = 1
+    q.gauss_distribution_momenta_(ctx, 7)
+    M = np.swapaxes(q.get_momenta(ctx), -1, -2)
+    assert np.abs(M + np.conj(np.swapaxes(M, -1, -2))).max() < 1e-15 and np.abs(np.trace(M, axis1=-2, axis2=-1)).max() < 1e-15
+    nl = 4 * int(np.prod(dims))
+    assert abs(q.kinetic_energy(ctx) / (nl * 4) - 1.0) < 0.05
+
+
+
+@pytest.mark.gpu
+@staged
+def test_sw_trajectory_matches_oracle(Uw):
+    """runMD_QPQ_sw! on the device == the oracle's steps composed in the same order (test/test_wilson.toml integrator with a
+    shorter trajectory): links and momenta after the trajectory, and Delta H"""
+    import lqcd_b200 as q
+    U = q.gaugefields_from_array(Uw.copy())
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": KAPPA, "eps_CG": 1e-22, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    ctx = D.ctx
+    op = orc.make_op(DIMS, kappa=KAPPA)
+    xi = orc.gaussian_field(DIMS, orc.WILSON, seed=41)
+    eta_h = orc.apply(op, orc.WILSON, orc.DDAG, Uw, xi)
+    eta = q.similar(x).from_host(eta_h)
+    P0 = orc.md_momenta(DIMS, seed=42)
+    q.set_momenta_(ctx, P0)
+    H0 = q.kinetic_energy(ctx) + q.gauge_action(ctx, BETA) + np.vdot(xi, xi).real
+    its = q.runMD_(ctx, BETA, 0.05, 3, D, eta, SextonWeingargten=True, Nsw=10)
+    assert its > 0
+    Ur, Pr = _traj(Uw, P0, 0.05, 3, nsw=10, fermion=(op, orc.WILSON, eta_h))
+    assert np.abs(q.get_links(ctx) - Ur).max() < 1e-9 and np.abs(q.get_momenta(ctx) - Pr).max() < 1e-9
+    X = q.similar(x)
+    q.clear_fermion_(X)
+    q.solve_DinvX_(X, q.DdagD(D), eta)
+    H1 = q.kinetic_energy(ctx) + q.gauge_action(ctx, BETA) + q.dot(eta, X).real
+    assert abs((H1 - H0) - (_H(Ur, Pr, (op, orc.WILSON, eta_h)) - _H(Uw, P0, (op, orc.WILSON, eta_h)))) < 1e-6
+    assert abs(H1 - H0) < 1.0
+
+
+
+@pytest.mark.gpu
+@staged
+def test_hmc_update_accepts_and_moves_links(Uw):
+    """update!(StandardHMC, U) with the MD on the device (standardHMC.jl:41-91): a short trajectory is accepted with
+    |Delta H| << 1, the links change, stay in SU(3), and the plaquette stays in the reference's 10 % window around the
+    value the reference's own test expects after its trajectories (test/runtests.jl:89-99, debugplaqdata.txt:7)"""
+    import lqcd_b200 as q
+    U = q.gaugefields_from_array(Uw.copy())
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": KAPPA, "eps_CG": 1e-19, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    fa = q.FermiAction(D, {})
+    rng = np.random.default_rng(5)
+    acc, dH, info = q.hmc_update_(U, BETA, 0.05, 4, fa=fa, SextonWeingargten=True, Nsw=10, rng=rng)
+    assert abs(dH) < 0.5 and info["cg_iters"] > 0
+    if acc:
+        assert np.abs(U.data - Uw).max() > 1e-3
+        assert np.abs(np.einsum("...ij,...kj->...ik", U.data, U.data.conj()) - np.eye(3)).max() < 1e-9
+    plaq = orc.plaquette(DIMS, U.data)
+    assert abs(plaq - 0.5784043949012552) / 0.5784043949012552 < 0.1
+
