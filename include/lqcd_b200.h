@@ -175,9 +175,9 @@ int lqcd_fermion_force_download(lqcd_ctx *ctx, double *const out_mu[4], int ndw)
  *      lqcd_md_momenta_gaussian   gauss_distribution!(p)   (standardMD.jl:86): a_a ~ N(0,1), counter-based generator
  *      lqcd_md_kinetic            md.p * md.p / 2          (standardHMC.jl:47)
  *      lqcd_md_gauge_action       -evaluate_GaugeAction(gauge_action, U)/NC = -(beta/NC) sum_plaq Re tr U_p (standardHMC.jl:49-50)
- *      lqcd_md_update_U           U_update!:  U_mu <- exp(eps p_mu) U_mu                      (eps = the reference's eps*dtau)
- *      lqcd_md_update_P           P_update!:  p_mu -= eps beta/(2 NC) TA(U_mu * staples)
- *      lqcd_md_update_P_fermion   P_update_fermion!: p_mu -= eps TA(UdSfdU_mu), the CG + force run inside (zero initial guess)
+ *      lqcd_md_update_u           U_update!:  U_mu <- exp(eps p_mu) U_mu                      (eps = the reference's eps*dtau)
+ *      lqcd_md_update_p           P_update!:  p_mu -= eps beta/(2 NC) TA(U_mu * staples)
+ *      lqcd_md_update_p_fermion   P_update_fermion!: p_mu -= eps TA(UdSfdU_mu), the CG + force run inside (zero initial guess)
  *      lqcd_md_trajectory         runMD!: mdsteps leapfrog steps of size dtau; nsw = 0 runMD_QPQ!, nsw > 0 (even) runMD_QPQ_sw!
  *                                 (Sexton-Weingarten: nsw gauge sub-steps around one fermion force); op = NULL: quenched. */
 int lqcd_md_momenta_gaussian(lqcd_ctx *ctx, uint64_t seed);
@@ -185,9 +185,9 @@ int lqcd_md_momenta_upload(lqcd_ctx *ctx, const double *const P_mu[4], int ndw);
 int lqcd_md_momenta_download(lqcd_ctx *ctx, double *const P_mu[4], int ndw);
 int lqcd_md_kinetic(lqcd_ctx *ctx, double *out);
 int lqcd_md_gauge_action(lqcd_ctx *ctx, double beta, double *out);
-int lqcd_md_update_U(lqcd_ctx *ctx, double eps);
-int lqcd_md_update_P(lqcd_ctx *ctx, double eps, double beta);
-int lqcd_md_update_P_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters);
+int lqcd_md_update_u(lqcd_ctx *ctx, double eps);
+int lqcd_md_update_p(lqcd_ctx *ctx, double eps, double beta);
+int lqcd_md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters);
 int lqcd_md_trajectory(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double beta, double dtau, int mdsteps, int nsw,
                        double cg_eps, int cg_maxsteps, long long *cg_iters_total);
 

@@ -305,19 +305,19 @@ extern "C" int lqcd_md_gauge_action(lqcd_ctx *ctx, double beta, double *out) {
     *out = -(beta / 3.0) * plaq * 18.0 * (double)ctx->g.V;            // -(beta/NC) sum_plaq Re tr U_p
     return LQCD_OK;
 }
-extern "C" int lqcd_md_update_U(lqcd_ctx *ctx, double eps) {
+extern "C" int lqcd_md_update_u(lqcd_ctx *ctx, double eps) {
     LQCD_TRY(md_ready(ctx, true));
     LQCD_TRY(md_update_u(ctx, eps));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LQCD_OK;
 }
-extern "C" int lqcd_md_update_P(lqcd_ctx *ctx, double eps, double beta) {
+extern "C" int lqcd_md_update_p(lqcd_ctx *ctx, double eps, double beta) {
     LQCD_TRY(md_ready(ctx, true));
     LQCD_TRY(md_update_p_gauge(ctx, eps, beta));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LQCD_OK;
 }
-extern "C" int lqcd_md_update_P_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters) {
+extern "C" int lqcd_md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters) {
     if (!op || !eta) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
     LQCD_TRY(md_ready(ctx, true));
     LQCD_TRY(md_update_p_fermion(ctx, op, eta, eps, cg_eps, cg_maxsteps, iters));

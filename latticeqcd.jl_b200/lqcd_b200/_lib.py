@@ -83,9 +83,9 @@ SIGNATURES = {
     "lqcd_md_momenta_download": (i32, [vp, pvp, i32]),
     "lqcd_md_kinetic": (i32, [vp, pdbl]),
     "lqcd_md_gauge_action": (i32, [vp, dbl, pdbl]),
-    "lqcd_md_update_U": (i32, [vp, dbl]),
-    "lqcd_md_update_P": (i32, [vp, dbl, dbl]),
-    "lqcd_md_update_P_fermion": (i32, [vp, pop, vp, dbl, dbl, i32, pi32]),
+    "lqcd_md_update_u": (i32, [vp, dbl]),
+    "lqcd_md_update_p": (i32, [vp, dbl, dbl]),
+    "lqcd_md_update_p_fermion": (i32, [vp, pop, vp, dbl, dbl, i32, pi32]),
     "lqcd_md_trajectory": (i32, [vp, pop, vp, dbl, dbl, i32, i32, dbl, i32, C.POINTER(C.c_longlong)]),
     "lqcd_comm_export": (i32, [vp, vp]),
     "lqcd_comm_connect": (i32, [vp, vp]),

@@ -533,16 +533,16 @@ def gauge_action(ctx: Context, beta: float) -> float:                 # -evaluat
 
 
 def U_update_(ctx: Context, eps_dtau: float):                         # U_update!(U, p, eps, md) with eps*md.dtau folded in
-    ctx.call("lqcd_md_update_U", float(eps_dtau))
+    ctx.call("lqcd_md_update_u", float(eps_dtau))
 
 
 def P_update_(ctx: Context, eps_dtau: float, beta: float):            # P_update!
-    ctx.call("lqcd_md_update_P", float(eps_dtau), float(beta))
+    ctx.call("lqcd_md_update_p", float(eps_dtau), float(beta))
 
 
 def P_update_fermion_(D: DiracOperator, eta: FermionField, eps_dtau: float) -> int:      # P_update_fermion!
     it = C.c_int(0)
-    D.ctx.call("lqcd_md_update_P_fermion", C.byref(D.op), eta.h, float(eps_dtau), D.eps, D.maxsteps, C.byref(it))
+    D.ctx.call("lqcd_md_update_p_fermion", C.byref(D.op), eta.h, float(eps_dtau), D.eps, D.maxsteps, C.byref(it))
     return it.value
 
 
