@@ -16,10 +16,16 @@
 // restated identically in oracle/lqcd_oracle.c (orc_md_*), whose known-answer tests are energy conservation at O(dtau^2)
 // and reversibility.  One thread per (site, mu); these kernels are link-bandwidth bound and run a few times per MD step
 // next to hundreds of Dslash applications, so they are written for clarity (local 3x3 arrays), not tuned.
-// Single rank (the staples reach one site across the faces; the multi-rank version would read peer links like clover.cu).
+// Several ranks: the staples and plaquettes reach one site across the faces (and one corner site, n+mu-nu); those links
+// are loaded from the neighbour ranks' peer-mapped link arrays (link_view.cuh, as the clover build does).  Writers and readers
+// of the links are ordered across ranks by the in-kernel all-reduce used as a barrier: every rank passes md_barrier after its
+// U_update! before anybody evaluates staples, and again after the staples before the next U_update! may overwrite links a
+// neighbour is still reading.  The fermion force, CG and momentum updates only touch local data (plus the halo protocols
+// of comm.cu / force.cu).
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "rng.cuh"
+#include "link_view.cuh"
 #include <cstring>
 
 struct MdArgs {
@@ -30,6 +36,7 @@ struct MdArgs {
     double eps, coef;
     uint64_t seed;
     Reduce red;
+    LinkView L;
 };
 
 __device__ __forceinline__ const cplx *link_ptr(const cplx *f, int s, int mu) { return f + ((size_t)(s >> 5) * 4 + mu) * (9 * 32) + (s & 31); }
@@ -106,18 +113,8 @@ __device__ __forceinline__ void expm3(cplx (&e)[3][3], const cplx (&x0)[3][3]) {
 __device__ __forceinline__ void coords4(const Geom &g, int s, int (&c)[4]) {
     c[0] = s % g.X; s /= g.X; c[1] = s % g.Y; s /= g.Y; c[2] = s % g.Z; c[3] = s / g.Z;
 }
-// periodic neighbour of site s (coordinates c) one step in direction mu (sign +-1); updates c
-__device__ __forceinline__ int step(const Geom &g, int s, int (&c)[4], int mu, int sign) {
-    const int d[4] = {g.X, g.Y, g.Z, g.T}, st[4] = {1, g.X, g.X * g.Y, g.X * g.Y * g.Z};
-    if (sign > 0) {
-        if (c[mu] == d[mu] - 1) { c[mu] = 0; return s - (d[mu] - 1) * st[mu]; }
-        c[mu]++; return s + st[mu];
-    }
-    if (c[mu] == 0) { c[mu] = d[mu] - 1; return s + (d[mu] - 1) * st[mu]; }
-    c[mu]--; return s - st[mu];
-}
-
-// P_update!: p_mu(n) -= eps * beta/(2 NC) * TA( U_mu(n) * sum of the six staples )
+// P_update!: p_mu(n) -= eps * beta/(2 NC) * TA( U_mu(n) * sum of the six staples ).  Coordinates may leave the local lattice
+// by one step (two directions at once for the corner n+mu-nu): fetch_link maps them to the owning rank.
 __global__ void __launch_bounds__(128) md_update_p_gauge_kernel(const MdArgs A) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= A.g.V * 4) return;
@@ -126,21 +123,19 @@ __global__ void __launch_bounds__(128) md_update_p_gauge_kernel(const MdArgs A) 
     coords4(A.g, s, c);
     cplx V[3][3];
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = cmake(0.0, 0.0);
-    int cm[4] = {c[0], c[1], c[2], c[3]};
-    const int smu = step(A.g, s, cm, mu, +1);
     for (int nu = 0; nu < 4; nu++) {
         if (nu == mu) continue;
-        int cu[4] = {c[0], c[1], c[2], c[3]}, cd[4] = {c[0], c[1], c[2], c[3]}, cmd[4] = {cm[0], cm[1], cm[2], cm[3]};
-        const int snu = step(A.g, s, cu, nu, +1), sdn = step(A.g, s, cd, nu, -1), smudn = step(A.g, smu, cmd, nu, -1);
+        int cmu[4] = {c[0], c[1], c[2], c[3]}, cnu[4] = {c[0], c[1], c[2], c[3]}, cdn[4] = {c[0], c[1], c[2], c[3]}, cmd[4] = {c[0], c[1], c[2], c[3]};
+        cmu[mu] += 1; cnu[nu] += 1; cdn[nu] -= 1; cmd[mu] += 1; cmd[nu] -= 1;
         cplx a[3][3], b[3][3], t[3][3], r[3][3];
-        ld3(a, link_ptr(A.gauge, smu, nu)); ld3(b, link_ptr(A.gauge, snu, mu));
+        fetch_link(a, A.L, A.g, cmu, nu); fetch_link(b, A.L, A.g, cnu, mu);
         mul3<0, 1>(t, a, b);                                          // U_nu(n+mu) U_mu(n+nu)^dag
         ld3(a, link_ptr(A.gauge, s, nu));
         mul3<0, 1>(r, t, a);                                          // ... U_nu(n)^dag
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = cadd(V[i][j], r[i][j]);
-        ld3(a, link_ptr(A.gauge, smudn, nu)); ld3(b, link_ptr(A.gauge, sdn, mu));
+        fetch_link(a, A.L, A.g, cmd, nu); fetch_link(b, A.L, A.g, cdn, mu);
         mul3<1, 1>(t, a, b);                                          // U_nu(n+mu-nu)^dag U_mu(n-nu)^dag
-        ld3(a, link_ptr(A.gauge, sdn, nu));
+        fetch_link(a, A.L, A.g, cdn, nu);
         mul3<0, 0>(r, t, a);                                          // ... U_nu(n-nu)
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = cadd(V[i][j], r[i][j]);
     }
@@ -152,6 +147,35 @@ __global__ void __launch_bounds__(128) md_update_p_gauge_kernel(const MdArgs A) 
     ld3(P, pp);
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) P[i][j] = cmake(fma(-A.coef, T[i][j].x, P[i][j].x), fma(-A.coef, T[i][j].y, P[i][j].y));
     st3(pp, P);
+}
+
+// sum over the local sites of the six plaquettes Re tr U_mu(n) U_nu(n+mu) U_mu(n+nu)^dag U_nu(n)^dag (all-reduced across ranks)
+__global__ void __launch_bounds__(128) md_plaquette_kernel(const MdArgs A) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[1] = {0.0};
+    if (s < A.g.V) {
+        int c[4];
+        coords4(A.g, s, c);
+        for (int mu = 0; mu < 4; mu++)
+            for (int nu = mu + 1; nu < 4; nu++) {
+                int cmu[4] = {c[0], c[1], c[2], c[3]}, cnu[4] = {c[0], c[1], c[2], c[3]};
+                cmu[mu] += 1; cnu[nu] += 1;
+                cplx a[3][3], b[3][3], t[3][3], r[3][3];
+                ld3(a, link_ptr(A.gauge, s, mu)); fetch_link(b, A.L, A.g, cmu, nu);
+                mul3<0, 0>(t, a, b);
+                fetch_link(a, A.L, A.g, cnu, mu);
+                mul3<0, 1>(r, t, a);
+                ld3(b, link_ptr(A.gauge, s, nu));
+                for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) red[0] += r[i][k].x * b[i][k].x + r[i][k].y * b[i][k].y;   // Re tr(r b^dag)
+            }
+    }
+    grid_reduce_finish<1>(red, A.red, FIN_STORE);
+}
+
+// cross-rank barrier: the in-kernel all-reduce of reduce.cuh completes only when every rank has arrived
+__global__ void md_barrier_kernel(const MdArgs A) {
+    double red[1] = {0.0};
+    grid_reduce_finish<1>(red, A.red, FIN_STORE);
 }
 
 // P_update_fermion!: p_mu(n) -= eps * TA( UdSfdU_mu(n) ), the force field left on the device by force.cu
@@ -215,11 +239,11 @@ __global__ void __launch_bounds__(128) md_momenta_kernel(const MdArgs A) {
 // ---- host side -------------------------------------------------------------------------------------------------------------
 int upload_links_to(lqcd_ctx *ctx, cplx *dev_links, const double *const U_mu[4], int ndw);          // context.cu
 int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);      // context.cu
+int comm_check_error(lqcd_ctx *ctx);                                                                // comm.cu
 int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, int maxsteps, int *iters);   // force.cu
 
 static int md_ready(lqcd_ctx *ctx, bool need_mom) {
     if (!ctx) return lqcd_fail(nullptr, LQCD_ERR_ARG, "null ctx");
-    if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "the gauge-sector MD kernels are single-rank in this round");
     if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "no gauge field on the device");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (!ctx->mom) {
@@ -234,6 +258,14 @@ static MdArgs md_args(lqcd_ctx *ctx) {
     memset(&A, 0, sizeof A);
     A.gauge = ctx->gauge; A.mom = ctx->mom; A.force = ctx->force_buf; A.g = ctx->g; A.red = ctx->red;
     return A;
+}
+static int md_barrier(lqcd_ctx *ctx) {
+    if (ctx->nranks == 1) return LQCD_OK;
+    MdArgs A = md_args(ctx);
+    md_barrier_kernel<<<1, 32, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return LQCD_OK;
 }
 #define MD_LAUNCH(kernel, A)                                                                  \
     do {                                                                                      \
@@ -252,8 +284,11 @@ static int md_update_u(lqcd_ctx *ctx, double eps) {
 }
 static int md_update_p_gauge(lqcd_ctx *ctx, double eps, double beta) {
     MdArgs A = md_args(ctx);
+    LQCD_TRY(make_link_view(ctx, A.L));
     A.coef = eps * beta / 6.0;                 // beta / (2 NC)
+    LQCD_TRY(md_barrier(ctx));                 // every rank has finished writing its links ...
     MD_LAUNCH(md_update_p_gauge_kernel, A);
+    LQCD_TRY(md_barrier(ctx));                 // ... and nobody overwrites them while a neighbour still reads
     return LQCD_OK;
 }
 static int md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters) {
@@ -300,9 +335,19 @@ extern "C" int lqcd_md_kinetic(lqcd_ctx *ctx, double *out) {
 }
 extern "C" int lqcd_md_gauge_action(lqcd_ctx *ctx, double beta, double *out) {
     if (!out) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
-    double plaq = 0.0;
-    LQCD_TRY(lqcd_gauge_plaquette(ctx, &plaq));
-    *out = -(beta / 3.0) * plaq * 18.0 * (double)ctx->g.V;            // -(beta/NC) sum_plaq Re tr U_p
+    LQCD_TRY(md_ready(ctx, false));
+    MdArgs A = md_args(ctx);
+    LQCD_TRY(make_link_view(ctx, A.L));
+    LQCD_TRY(md_barrier(ctx));
+    const int bs = 128;
+    md_plaquette_kernel<<<(ctx->g.V + bs - 1) / bs, bs, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->st_host, ctx->red.st, sizeof(SolverState), cudaMemcpyDeviceToHost, ctx->stream));
+    LQCD_TRY(md_barrier(ctx));                 // (after the copy: the barrier's own reduction overwrites st->red)
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    LQCD_TRY(comm_check_error(ctx));
+    *out = -(beta / 3.0) * ctx->st_host->red[0];                      // -(beta/NC) sum_plaq Re tr U_p (global)
     return LQCD_OK;
 }
 extern "C" int lqcd_md_update_u(lqcd_ctx *ctx, double eps) {

@@ -95,3 +95,12 @@ def test_persistent_queue_variant_under_emulation(emu_lib):
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120", LQCD_PERSIST="1"),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_multirank_md_trajectory_under_emulation(emu_lib):
+    """device-resident HMC trajectory on 4 ranks (2 partitioned directions: face and corner links from peer-mapped arrays,
+    device-side barriers between the MD sub-steps)"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", str(35500 + (os.getpid() % 2000)), "tests/mp_md_worker.py", "4x4x4x4", "1x1x2x2"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
