@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--lattice", default="32x32x32x32")
     ap.add_argument("--cg-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--probe-pipe", action="store_true", help=argparse.SUPPRESS)   # child process of probe_pipe_isolated()
     return ap.parse_args()
 
 
@@ -187,6 +188,53 @@ class ClockSampler:
         mx = [int(r[2]) for r in rows if len(r) >= 9 and r[2].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def probe_pipe_child(dims):
+    """Child process: lqcd_dslash_host against the three-call sequence on a fresh context.  Prints PIPE_OK on bit-for-bit
+    agreement.  Runs isolated so that a device fault in the pipelined path (not yet run on hardware when it was written)
+    cannot leave a sticky CUDA error in the measuring process."""
+    import numpy as np
+    import lqcd_b200 as q
+    from lqcd_b200 import _lib as L
+    ctx = q.get_context(dims, procgrid=(1, 1, 1, 1), rank=0, device=int(os.environ.get("LOCAL_RANK", "0")))
+    ctx.call("lqcd_gauge_random", 111, -1.0)
+    op = L.LqcdOp()
+    op.kind, op.kappa, op.r = L.WILSON, KAPPA, 1.0
+    for i, b in enumerate(BC):
+        op.bc[i] = b
+    x, y = q.FermionField(ctx, L.WILSON), q.FermionField(ctx, L.WILSON)
+    q.gauss_distribution_fermion_(x, 112)
+    hx = np.ascontiguousarray(x.to_host())
+    hy = np.zeros_like(hx)
+    for rep in range(2):                      # second pass reuses the staging buffers / events
+        ctx.call("lqcd_fermion_upload", x.h, hx.ctypes.data, 0)
+        ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
+        ctx.call("lqcd_fermion_download", y.h, hy.ctypes.data, 0)
+        ref = hy.copy()
+        hy[...] = 0
+        ctx.call("lqcd_dslash_host", C.byref(op), y.h, x.h, hy.ctypes.data, hx.ctypes.data, L.OP_D, 0)
+        ctx.synchronize()
+        if not np.array_equal(ref, hy):
+            print("PIPE_MISMATCH", flush=True)
+            return
+    print("PIPE_OK", flush=True)
+
+
+def probe_pipe_isolated(lattice, local_rank):
+    """(ok, note): run probe_pipe_child in a subprocess with a timeout"""
+    env = dict(os.environ, LOCAL_RANK=str(local_rank))
+    for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--probe-pipe", "--lattice", lattice], env=env,
+                           capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        return False, "pipelined call timed out in the isolated probe: not used"
+    if r.returncode == 0 and "PIPE_OK" in r.stdout:
+        return True, None
+    tail = (r.stdout + r.stderr).strip().splitlines()[-1:] or [""]
+    return False, f"pipelined call failed the isolated probe (exit {r.returncode}: {tail[0][:160]}): not used"
 
 
 def choose_procgrid(n):
@@ -325,7 +373,10 @@ def run_b200(args, dims):
         # the pipelined call must reproduce the three-call sequence bit for bit on this box, else it is not used
         e2e_step, e2e_call = e2e_step_3call, "x.from_host(h); mul_(y, D, x); y.to_host()  [lqcd_fermion_upload + lqcd_dslash + lqcd_fermion_download]"
         pipe_note, ref_y = None, None
-        if os.environ.get("LQCD_E2E_PIPE", "1") != "0":
+        pipe_ok = os.environ.get("LQCD_E2E_PIPE", "1") != "0"
+        if pipe_ok and world == 1:             # N > 1 takes the three-call sequence inside lqcd_dslash_host anyway
+            pipe_ok, pipe_note = probe_pipe_isolated(args.lattice, local_rank)
+        if pipe_ok:
             try:
                 e2e_step_3call()
                 ref_y = hyn.copy()
@@ -411,7 +462,9 @@ def run_b200(args, dims):
 def main():
     args = parse_args()
     dims = tuple(int(v) for v in args.lattice.split("x"))
-    if args.impl == "reference":
+    if args.probe_pipe:
+        probe_pipe_child(dims)
+    elif args.impl == "reference":
         run_reference(args, dims)
     else:
         run_b200(args, dims)

@@ -16,3 +16,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+def pytest_collection_modifyitems(config, items):
+    """Hardware-unverified GPU tests (gpu + non-strict xfail) run AFTER every verified test: a device fault in one of them
+    leaves a sticky CUDA error in the process and must not be able to take verified tests down with it."""
+    def staged(item):
+        return item.get_closest_marker("gpu") is not None and item.get_closest_marker("xfail") is not None
+    items[:] = [i for i in items if not staged(i)] + [i for i in items if staged(i)]
