@@ -166,6 +166,15 @@ int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta
  * lqcd_fermion_force_download copies it to the four host arrays (link layout, wing ndw).  Collective across ranks. */
 int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate);
 int lqcd_fermion_force_download(lqcd_ctx *ctx, double *const out_mu[4], int ndw);
+/* calc_UdSfdU! for the RHMC action in one call: multi-shift CG, Y_j = D X_j, sum_j alpha[j] force(X_j, Y_j) on the device, then the
+ * copy to out_mu as in lqcd_fermion_force. */
+int lqcd_fermion_force_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                int nshift, double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters);
+/* y = alpha0 x + sum_j alpha[j] (DdagD + shifts[j])^-1 x with ONE multi-shift CG (shifts[0] the smallest): the RHMC heat bath
+ * eta = (DdagD)^{Nf/16} xi of sample_pseudofermions! (standardMD.jl:96) and, through dot_out = Re<x, y> (nullable), the action
+ * eta^dag (DdagD)^{-Nf/8} eta of evaluate_FermiAction (standardHMC.jl:69-71), as single calls.  Collective across ranks. */
+int lqcd_rational_apply(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, double alpha0, const double *alpha,
+                        const double *shifts, int nshift, double eps, int maxsteps, int *iters, double *dot_out);
 
 /* ---- gauge-sector molecular dynamics on the device: the steps of src/md/AbstractMD.jl:78-135 and the
  *      leapfrog integrators of src/md/standardMD.jl:125-165 for NC = 3 and the plaquette action beta/2*(P + P^dag)
@@ -190,6 +199,14 @@ int lqcd_md_update_p(lqcd_ctx *ctx, double eps, double beta);
 int lqcd_md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters);
 int lqcd_md_trajectory(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double beta, double dtau, int mdsteps, int nsw,
                        double cg_eps, int cg_maxsteps, long long *cg_iters_total);
+/* The same two with the RHMC pseudofermion action eta^dag [alpha0 + sum_j alpha[j] / (DdagD + shifts[j])] eta (staggered Nf not in
+ * {4, 8}: README.md:132, test/test_Nf2.toml, test_Nf3.toml): every fermion force is one multi-shift CG and nshift accumulated outer
+ * products, nothing leaves the device during the trajectory. */
+int lqcd_md_update_p_fermion_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                      int nshift, double eps, double cg_eps, int cg_maxsteps, int *iters);
+int lqcd_md_trajectory_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                int nshift, double beta, double dtau, int mdsteps, int nsw, double cg_eps, int cg_maxsteps,
+                                long long *cg_iters_total);
 
 /* ---- multi-GPU plumbing (one process per GPU; handles are exchanged by the host: MPI.jl Allgather in
  *      Julia, torch.distributed.all_gather in the Python mirror) ---------------------------------- */

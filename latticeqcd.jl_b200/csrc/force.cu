@@ -316,6 +316,69 @@ int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, doub
     return force_outer(ctx, op, X, Y, 1.0, 0, nullptr, nullptr);
 }
 
+// RHMC (staggered Nf not in {4, 8}; README.md:132, test/test_Nf2.toml): S_f = eta^dag r(DdagD) eta with the partial fractions
+// r(x) = alpha0 + sum_j alpha[j] / (x + shifts[j]).  X_j = (DdagD + shifts[j])^-1 eta by ONE multi-shift CG, Y_j = D X_j,
+// UdSfdU = sum_j alpha[j] force(X_j, Y_j) accumulated in ctx->force_buf.  Scratch: the solver owns slots 0 .. 2 + LQCD_MAX_SHIFTS,
+// the force keeps 8 / 9 for the plain action, so the shifted solutions live above both.
+#define RATIONAL_SLOT0 (3 + LQCD_MAX_SHIFTS)
+static int rational_solutions(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *shifts, int nshift,
+                              double eps, int maxsteps, lqcd_fermion **xs, int *iters) {
+    if (!shifts || nshift < 1 || nshift > LQCD_MAX_SHIFTS) return lqcd_fail(ctx, LQCD_ERR_ARG, "rational action: nshift must be in [1, %d]", LQCD_MAX_SHIFTS);
+    for (int j = 0; j < nshift; j++) LQCD_TRY(get_scratch(ctx, op->kind, RATIONAL_SLOT0 + j, &xs[j]));
+    int it = 0;
+    double rs = 0.0;
+    LQCD_TRY(lqcd_multishift_cg(ctx, op, xs, eta, shifts, nshift, eps, maxsteps, &it, &rs));
+    if (iters) *iters = it;
+    return LQCD_OK;
+}
+
+int force_for_md_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts, int nshift,
+                          double eps, int maxsteps, int *iters) {
+    LQCD_TRY(check_force_args(ctx, op, eta, eta));
+    if (!alpha) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    lqcd_fermion *xs[LQCD_MAX_SHIFTS], *Y = nullptr;
+    LQCD_TRY(rational_solutions(ctx, op, eta, shifts, nshift, eps, maxsteps, xs, iters));
+    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    for (int j = 0; j < nshift; j++) {
+        LQCD_TRY(lqcd_dslash(ctx, op, Y, xs[j], LQCD_OP_D));
+        LQCD_TRY(force_outer(ctx, op, xs[j], Y, alpha[j], j > 0, nullptr, nullptr));
+    }
+    return LQCD_OK;
+}
+
+// calc_UdSfdU! for the RHMC action: the accumulated force copied to the host arrays (link layout, wing ndw)
+extern "C" int lqcd_fermion_force_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                           int nshift, double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters) {
+    if (!out_mu) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (ndw < 0 || ndw > 4) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad wing width %d", ndw);
+    LQCD_TRY(check_force_args(ctx, op, eta, eta));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    LQCD_TRY(force_for_md_rational(ctx, op, eta, alpha, shifts, nshift, eps, maxsteps, iters));
+    return download_links_from(ctx, ctx->force_buf, out_mu, ndw);
+}
+
+// y = alpha0 x + sum_j alpha[j] (DdagD + shifts[j])^-1 x: the rational heat bath eta = r_hb(DdagD) xi and, with `dot_out`,
+// the action <x, r(DdagD) x> of evaluate_FermiAction, each as one call without host round trips per pole
+extern "C" int lqcd_rational_apply(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *x, double alpha0,
+                                   const double *alpha, const double *shifts, int nshift, double eps, int maxsteps, int *iters, double *dot_out) {
+    if (!ctx || !op || !y || !x || !alpha) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
+    if (y == x) return lqcd_fail(ctx, LQCD_ERR_ARG, "rational apply: output aliases input");
+    if (x->owner != ctx || y->owner != ctx || x->kind != op->kind || y->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad fields");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    lqcd_fermion *xs[LQCD_MAX_SHIFTS];
+    LQCD_TRY(rational_solutions(ctx, op, x, shifts, nshift, eps, maxsteps, xs, iters));
+    LQCD_TRY(blas_copy(ctx, y->d, x->d, x->bytes / sizeof(cplx)));
+    LQCD_TRY(lqcd_blas_scale(ctx, alpha0, 0.0, y));
+    for (int j = 0; j < nshift; j++) LQCD_TRY(lqcd_blas_axpy(ctx, alpha[j], 0.0, xs[j], y));
+    if (dot_out) {
+        double d[2];
+        LQCD_TRY(lqcd_blas_dot(ctx, x, y, d));
+        *dot_out = d[0];
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return comm_check_error(ctx);
+}
+
 extern "C" int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, const lqcd_fermion *Y, double coef, int accumulate) {
     LQCD_TRY(check_force_args(ctx, op, X, Y));
     if (X == Y) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: X aliases Y");

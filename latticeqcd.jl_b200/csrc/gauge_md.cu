@@ -241,6 +241,15 @@ int upload_links_to(lqcd_ctx *ctx, cplx *dev_links, const double *const U_mu[4],
 int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);      // context.cu
 int comm_check_error(lqcd_ctx *ctx);                                                                // comm.cu
 int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, int maxsteps, int *iters);   // force.cu
+int force_for_md_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts, int nshift,
+                          double eps, int maxsteps, int *iters);                                                       // force.cu
+
+// pseudofermion action inside a trajectory: plain eta^dag (DdagD)^-1 eta (nshift = 0) or the RHMC partial fractions
+struct MdFermion {
+    const lqcd_op *op; const lqcd_fermion *eta;
+    const double *alpha, *shifts; int nshift;
+    double cg_eps; int cg_maxsteps;
+};
 
 static int md_ready(lqcd_ctx *ctx, bool need_mom) {
     if (!ctx) return lqcd_fail(nullptr, LQCD_ERR_ARG, "null ctx");
@@ -291,11 +300,41 @@ static int md_update_p_gauge(lqcd_ctx *ctx, double eps, double beta) {
     LQCD_TRY(md_barrier(ctx));                 // ... and nobody overwrites them while a neighbour still reads
     return LQCD_OK;
 }
-static int md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters) {
-    LQCD_TRY(force_for_md(ctx, op, eta, cg_eps, cg_maxsteps, iters));      // leaves UdSfdU in ctx->force_buf
+static int md_update_p_fermion(lqcd_ctx *ctx, const MdFermion &f, double eps, int *iters) {
+    // leaves UdSfdU in ctx->force_buf
+    if (f.nshift > 0) LQCD_TRY(force_for_md_rational(ctx, f.op, f.eta, f.alpha, f.shifts, f.nshift, f.cg_eps, f.cg_maxsteps, iters));
+    else              LQCD_TRY(force_for_md(ctx, f.op, f.eta, f.cg_eps, f.cg_maxsteps, iters));
     MdArgs A = md_args(ctx);
     A.coef = eps;
     MD_LAUNCH(md_update_p_force_kernel, A);
+    return LQCD_OK;
+}
+// runMD_QPQ! (nsw = 0) / runMD_QPQ_sw! (standardMD.jl:125-165); f = nullptr: quenched
+static int md_trajectory(lqcd_ctx *ctx, const MdFermion *f, double beta, double dtau, int mdsteps, int nsw, long long *cg_iters_total) {
+    if (mdsteps < 1 || nsw < 0 || (nsw & 1) || !(dtau > 0.0)) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad MD parameters (mdsteps >= 1, nsw even >= 0, dtau > 0)");
+    if (f && !f->eta) return lqcd_fail(ctx, LQCD_ERR_ARG, "dynamical run needs the pseudofermion field eta");
+    LQCD_TRY(md_ready(ctx, true));
+    long long its = 0;
+    for (int step_i = 0; step_i < mdsteps; step_i++) {
+        int it = 0;
+        if (nsw == 0) {
+            LQCD_TRY(md_update_u(ctx, 0.5 * dtau));
+            LQCD_TRY(md_update_p_gauge(ctx, dtau, beta));
+            if (f) { LQCD_TRY(md_update_p_fermion(ctx, *f, dtau, &it)); its += it; }
+            LQCD_TRY(md_update_u(ctx, 0.5 * dtau));
+        } else {
+            for (int half = 0; half < 2; half++) {
+                for (int isw = 0; isw < nsw / 2; isw++) {
+                    LQCD_TRY(md_update_u(ctx, 0.5 * dtau / nsw));
+                    LQCD_TRY(md_update_p_gauge(ctx, dtau / nsw, beta));
+                    LQCD_TRY(md_update_u(ctx, 0.5 * dtau / nsw));
+                }
+                if (half == 0 && f) { LQCD_TRY(md_update_p_fermion(ctx, *f, dtau, &it)); its += it; }
+            }
+        }
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cg_iters_total) *cg_iters_total = its;
     return LQCD_OK;
 }
 
@@ -365,7 +404,18 @@ extern "C" int lqcd_md_update_p(lqcd_ctx *ctx, double eps, double beta) {
 extern "C" int lqcd_md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, double cg_eps, int cg_maxsteps, int *iters) {
     if (!op || !eta) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
     LQCD_TRY(md_ready(ctx, true));
-    LQCD_TRY(md_update_p_fermion(ctx, op, eta, eps, cg_eps, cg_maxsteps, iters));
+    const MdFermion f = {op, eta, nullptr, nullptr, 0, cg_eps, cg_maxsteps};
+    LQCD_TRY(md_update_p_fermion(ctx, f, eps, iters));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LQCD_OK;
+}
+// the same for the RHMC action eta^dag [alpha0 + sum_j alpha[j] / (DdagD + shifts[j])] eta (alpha0 does not move the links)
+extern "C" int lqcd_md_update_p_fermion_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                                 int nshift, double eps, double cg_eps, int cg_maxsteps, int *iters) {
+    if (!op || !eta || !alpha || !shifts || nshift < 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument / nshift < 1");
+    LQCD_TRY(md_ready(ctx, true));
+    const MdFermion f = {op, eta, alpha, shifts, nshift, cg_eps, cg_maxsteps};
+    LQCD_TRY(md_update_p_fermion(ctx, f, eps, iters));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LQCD_OK;
 }
@@ -375,29 +425,15 @@ extern "C" int lqcd_md_update_p_fermion(lqcd_ctx *ctx, const lqcd_op *op, const 
 // op == NULL: quenched.  cg_iters_total (nullable) accumulates the CG iterations of all fermion-force solves.
 extern "C" int lqcd_md_trajectory(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double beta, double dtau, int mdsteps, int nsw,
                                   double cg_eps, int cg_maxsteps, long long *cg_iters_total) {
-    if (mdsteps < 1 || nsw < 0 || (nsw & 1) || !(dtau > 0.0)) return lqcd_fail(ctx, LQCD_ERR_ARG, "bad MD parameters (mdsteps >= 1, nsw even >= 0, dtau > 0)");
     if (op && !eta) return lqcd_fail(ctx, LQCD_ERR_ARG, "dynamical run needs the pseudofermion field eta");
-    LQCD_TRY(md_ready(ctx, true));
-    long long its = 0;
-    for (int step_i = 0; step_i < mdsteps; step_i++) {
-        int it = 0;
-        if (nsw == 0) {
-            LQCD_TRY(md_update_u(ctx, 0.5 * dtau));
-            LQCD_TRY(md_update_p_gauge(ctx, dtau, beta));
-            if (op) { LQCD_TRY(md_update_p_fermion(ctx, op, eta, dtau, cg_eps, cg_maxsteps, &it)); its += it; }
-            LQCD_TRY(md_update_u(ctx, 0.5 * dtau));
-        } else {
-            for (int half = 0; half < 2; half++) {
-                for (int isw = 0; isw < nsw / 2; isw++) {
-                    LQCD_TRY(md_update_u(ctx, 0.5 * dtau / nsw));
-                    LQCD_TRY(md_update_p_gauge(ctx, dtau / nsw, beta));
-                    LQCD_TRY(md_update_u(ctx, 0.5 * dtau / nsw));
-                }
-                if (half == 0 && op) { LQCD_TRY(md_update_p_fermion(ctx, op, eta, dtau, cg_eps, cg_maxsteps, &it)); its += it; }
-            }
-        }
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (cg_iters_total) *cg_iters_total = its;
-    return LQCD_OK;
+    const MdFermion f = {op, eta, nullptr, nullptr, 0, cg_eps, cg_maxsteps};
+    return md_trajectory(ctx, op ? &f : nullptr, beta, dtau, mdsteps, nsw, cg_iters_total);
+}
+// RHMC trajectory (test/test_Nf2.toml, BASELINE config 5): the fermion force of every step is ONE multi-shift CG + nshift outer products
+extern "C" int lqcd_md_trajectory_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *alpha, const double *shifts,
+                                           int nshift, double beta, double dtau, int mdsteps, int nsw, double cg_eps, int cg_maxsteps,
+                                           long long *cg_iters_total) {
+    if (!op || !eta || !alpha || !shifts || nshift < 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument / nshift < 1");
+    const MdFermion f = {op, eta, alpha, shifts, nshift, cg_eps, cg_maxsteps};
+    return md_trajectory(ctx, &f, beta, dtau, mdsteps, nsw, cg_iters_total);
 }

@@ -219,29 +219,31 @@ end
 
 function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200RHMCAction, U, η)
     D = fa.D(U)
-    n = length(fa.b)
     dη = D.scratch[1]; upload!(dη, η)
-    X = [B200Field(D.ctx, D.op.kind) for _ = 1:n]; Y = B200Field(D.ctx, D.op.kind)
-    iters = Ref{Cint}(0); rs = Ref{Cdouble}(0.0)
-    check(D.ctx.h, ccall((:lqcd_multishift_cg, LIB), Cint,
-        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
-        D.ctx.h, D.op, [x.h for x in X], dη.h, fa.b, n, D.eps, D.maxsteps, iters, rs))
-    for j = 1:n
-        check(D.ctx.h, ccall((:lqcd_dslash, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), D.ctx.h, D.op, Y.h, X[j].h, OP_D))
-        check(D.ctx.h, ccall((:lqcd_fermion_force_xy, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
-                             D.ctx.h, D.op, X[j].h, Y.h, fa.a[j], j > 1 ? 1 : 0))
-    end
     outs = [pointer(UdSfdU[mu].U) for mu = 1:4]
     w = hasproperty(UdSfdU[1], :NDW) ? Int(UdSfdU[1].NDW) : 0
-    GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{ComplexF64}}, Cint), D.ctx.h, outs, w))
+    iters = Ref{Cint}(0)
+    GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force_rational, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ptr{Ptr{ComplexF64}}, Cint, Ref{Cint}),
+        D.ctx.h, D.op, dη.h, fa.a, fa.b, length(fa.b), D.eps, D.maxsteps, outs, w, iters))
     return nothing
+end
+"evaluate_FermiAction(fa, U, eta) = eta^dag r(D^dag D) eta, r ~ x^(-Nf/8): one multi-shift CG on the device"
+function evaluate_FermiAction(fa::B200RHMCAction, U, η)
+    D = fa.D(U)
+    dη = D.scratch[1]; upload!(dη, η)
+    iters = Ref{Cint}(0); S = Ref{Cdouble}(0.0)
+    check(D.ctx.h, ccall((:lqcd_rational_apply, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
+        D.ctx.h, D.op, D.scratch[2].h, dη.h, fa.a0, fa.a, fa.b, length(fa.b), D.eps, D.maxsteps, iters, S))
+    return S[]
 end
 
 # ---- device-resident molecular dynamics (src/md/standardMD.jl:103-165, src/md/AbstractMD.jl:78-135) -------------------------
 # runMD!(U, md) for a StandardMD whose fermi_action is a B200FermiAction (or quenched): the links are uploaded once, momenta
 # are sampled on the device, U_update! / P_update! / P_update_fermion! run as kernels (lqcd_md_trajectory), and U is
 # downloaded at the end.  md.p (host momenta) is bypassed: Sp_old / Sp_new come from lqcd_md_kinetic.
-function runMD_b200!(U::Vector{<:AbstractGaugefields{3,4}}, ctx::B200Context, β, Δτ, MDsteps; fa::Union{Nothing,B200FermiAction}=nothing,
+function runMD_b200!(U::Vector{<:AbstractGaugefields{3,4}}, ctx::B200Context, β, Δτ, MDsteps; fa::Union{Nothing,B200FermiAction,B200RHMCAction}=nothing,
                      η=nothing, SextonWeingargten=false, Nsw=2, seed=rand(UInt64))
     upload_links!(ctx, U)
     check(ctx.h, ccall((:lqcd_md_momenta_gaussian, LIB), Cint, (Ptr{Cvoid}, UInt64), ctx.h, seed))
@@ -251,6 +253,11 @@ function runMD_b200!(U::Vector{<:AbstractGaugefields{3,4}}, ctx::B200Context, β
         check(ctx.h, ccall((:lqcd_md_trajectory, LIB), Cint,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Ref{Clonglong}),
             ctx.h, C_NULL, C_NULL, β, Δτ, MDsteps, SextonWeingargten ? Nsw : 0, 0.0, 1, its))
+    elseif fa isa B200RHMCAction                      # every fermion force = one multi-shift CG + accumulated outer products
+        dη = fa.D.scratch[1]; upload!(dη, η)
+        check(ctx.h, ccall((:lqcd_md_trajectory_rational, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Ref{Clonglong}),
+            ctx.h, fa.D.op, dη.h, fa.a, fa.b, length(fa.b), β, Δτ, MDsteps, SextonWeingargten ? Nsw : 0, fa.D.eps, fa.D.maxsteps, its))
     else
         dη = fa.D.scratch[1]; upload!(dη, η)
         check(ctx.h, ccall((:lqcd_md_trajectory, LIB), Cint,

@@ -78,6 +78,8 @@ SIGNATURES = {
     "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, i32, pi32, pdbl]),
     "lqcd_fermion_force_xy": (i32, [vp, pop, vp, vp, dbl, i32]),
     "lqcd_fermion_force_download": (i32, [vp, pvp, i32]),
+    "lqcd_fermion_force_rational": (i32, [vp, pop, vp, pdbl, pdbl, i32, dbl, i32, pvp, i32, pi32]),
+    "lqcd_rational_apply": (i32, [vp, pop, vp, vp, dbl, pdbl, pdbl, i32, dbl, i32, pi32, pdbl]),
     "lqcd_md_momenta_gaussian": (i32, [vp, u64]),
     "lqcd_md_momenta_upload": (i32, [vp, pvp, i32]),
     "lqcd_md_momenta_download": (i32, [vp, pvp, i32]),
@@ -87,6 +89,8 @@ SIGNATURES = {
     "lqcd_md_update_p": (i32, [vp, dbl, dbl]),
     "lqcd_md_update_p_fermion": (i32, [vp, pop, vp, dbl, dbl, i32, pi32]),
     "lqcd_md_trajectory": (i32, [vp, pop, vp, dbl, dbl, i32, i32, dbl, i32, C.POINTER(C.c_longlong)]),
+    "lqcd_md_update_p_fermion_rational": (i32, [vp, pop, vp, pdbl, pdbl, i32, dbl, dbl, i32, pi32]),
+    "lqcd_md_trajectory_rational": (i32, [vp, pop, vp, pdbl, pdbl, i32, dbl, dbl, i32, i32, dbl, i32, C.POINTER(C.c_longlong)]),
     "lqcd_comm_export": (i32, [vp, vp]),
     "lqcd_comm_connect": (i32, [vp, vp]),
     "lqcd_decompose": (i32, [pi32, pi32, i32, pi32, pi32, pi32, pi32]),

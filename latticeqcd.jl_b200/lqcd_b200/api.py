@@ -429,6 +429,23 @@ class RHMCFermiAction:
         self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]
         self.last = {}
 
+    # single-call device paths (lqcd_rational_apply / lqcd_fermion_force_rational / lqcd_md_trajectory_rational): the poles
+    # never come back to the host; fa.rhmc (backend-generic, shared with the CPU oracle in tests) stays as the cross-check
+    @staticmethod
+    def _coeffs(ra):
+        a = np.ascontiguousarray(ra.alpha, dtype=np.float64)
+        b = np.ascontiguousarray(ra.beta, dtype=np.float64)
+        return float(ra.alpha0), a, b
+
+    def rational_apply_(self, y: FermionField, ra, x: FermionField, want_dot=False):
+        """y = ra(D^dag D) x; returns (CG iterations, Re<x, y> or None)"""
+        D = self.D
+        a0, a, b = self._coeffs(ra)
+        it, d = C.c_int(0), C.c_double(0.0)
+        D.ctx.call("lqcd_rational_apply", C.byref(D.op), y.h, x.h, a0, a.ctypes.data_as(L.pdbl), b.ctypes.data_as(L.pdbl), len(a),
+                   D.eps, D.maxsteps, C.byref(it), C.byref(d) if want_dot else None)
+        return it.value, (d.value if want_dot else None)
+
 
 def FermiAction(D, parameters_action):
     Nf = parameters_action.get("Nf", None)
@@ -448,7 +465,8 @@ def sample_pseudofermions_(eta: FermionField, U, fa, xi: FermionField):   # stan
     (App. C.7); RHMC: eta = (D^dag D)^{Nf/16} xi by the rational approximation."""
     fa.D(U)
     if isinstance(fa, RHMCFermiAction):
-        substitute_fermion_(eta, fa.rhmc.sample_pseudofermions(xi))
+        it, _ = fa.rational_apply_(eta, fa.rhmc.r_heatbath, xi)
+        fa.last = {"iters": it}
         return
     mul_(eta, adjoint(fa.D), xi)
     if fa.even_only:
@@ -459,8 +477,8 @@ def evaluate_FermiAction(fa, U, eta: FermionField) -> float:           # standar
     """S_f = eta^dag (D^dag D)^-1 eta: one CG solve (RHMC: eta^dag (D^dag D)^{-Nf/8} eta, one multi-shift solve)."""
     D = fa.D(U)
     if isinstance(fa, RHMCFermiAction):
-        S = fa.rhmc.evaluate(eta)
-        fa.last = {"iters": fa.rhmc.be.last_iters, "action": S}
+        it, S = fa.rational_apply_(fa._temporary_fermionfields[0], fa.rhmc.r_action, eta, want_dot=True)
+        fa.last = {"iters": it, "action": S}
         return S
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
@@ -475,10 +493,11 @@ def calc_UdSfdU_(UdSfdU: np.ndarray, fa, U, eta: FermionField):         # Abstra
     D = fa.D(U)
     out = (C.c_void_p * 4)(*[UdSfdU[mu].ctypes.data for mu in range(4)])
     if isinstance(fa, RHMCFermiAction):
-        for j, (a, X, Y) in enumerate(fa.rhmc.force_terms(eta)):
-            D.ctx.call("lqcd_fermion_force_xy", C.byref(D.op), X.h, Y.h, float(a), 1 if j else 0)
-        D.ctx.call("lqcd_fermion_force_download", out, 0)
-        fa.last = {"iters": fa.rhmc.be.last_iters}
+        _, a, b = fa._coeffs(fa.rhmc.r_action)
+        it = C.c_int(0)
+        D.ctx.call("lqcd_fermion_force_rational", C.byref(D.op), eta.h, a.ctypes.data_as(L.pdbl), b.ctypes.data_as(L.pdbl), len(a),
+                   D.eps, D.maxsteps, out, 0, C.byref(it))
+        fa.last = {"iters": it.value}
         return fa.last
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
@@ -540,16 +559,29 @@ def P_update_(ctx: Context, eps_dtau: float, beta: float):            # P_update
     ctx.call("lqcd_md_update_p", float(eps_dtau), float(beta))
 
 
-def P_update_fermion_(D: DiracOperator, eta: FermionField, eps_dtau: float) -> int:      # P_update_fermion!
+def P_update_fermion_(D: DiracOperator, eta: FermionField, eps_dtau: float, rational=None) -> int:      # P_update_fermion!
+    """rational: RationalApprox of the RHMC action (fa.rhmc.r_action) -> force of eta^dag r(D^dag D) eta"""
     it = C.c_int(0)
+    if rational is not None:
+        _, a, b = RHMCFermiAction._coeffs(rational)
+        D.ctx.call("lqcd_md_update_p_fermion_rational", C.byref(D.op), eta.h, a.ctypes.data_as(L.pdbl), b.ctypes.data_as(L.pdbl), len(a),
+                   float(eps_dtau), D.eps, D.maxsteps, C.byref(it))
+        return it.value
     D.ctx.call("lqcd_md_update_p_fermion", C.byref(D.op), eta.h, float(eps_dtau), D.eps, D.maxsteps, C.byref(it))
     return it.value
 
 
-def runMD_(ctx: Context, beta, dtau, MDsteps, D: DiracOperator = None, eta: FermionField = None, SextonWeingargten=False, Nsw=2) -> int:
-    """runMD!(U, md) on the device-resident links (standardMD.jl:103-165); returns the CG iterations spent in fermion forces"""
+def runMD_(ctx: Context, beta, dtau, MDsteps, D: DiracOperator = None, eta: FermionField = None, SextonWeingargten=False, Nsw=2,
+           rational=None) -> int:
+    """runMD!(U, md) on the device-resident links (standardMD.jl:103-165); returns the CG iterations spent in fermion forces.
+    rational: RationalApprox of the RHMC action -> every fermion force is one multi-shift CG (lqcd_md_trajectory_rational)"""
     its = C.c_longlong(0)
     nsw = int(Nsw) if SextonWeingargten else 0
+    if rational is not None:
+        _, a, b = RHMCFermiAction._coeffs(rational)
+        ctx.call("lqcd_md_trajectory_rational", C.byref(D.op), eta.h, a.ctypes.data_as(L.pdbl), b.ctypes.data_as(L.pdbl), len(a),
+                 float(beta), float(dtau), int(MDsteps), nsw, D.eps, D.maxsteps, C.byref(its))
+        return its.value
     ctx.call("lqcd_md_trajectory", C.byref(D.op) if D is not None else None, eta.h if eta is not None else None,
              float(beta), float(dtau), int(MDsteps), nsw, D.eps if D is not None else 0.0, D.maxsteps if D is not None else 1, C.byref(its))
     return its.value
@@ -558,10 +590,10 @@ def runMD_(ctx: Context, beta, dtau, MDsteps, D: DiracOperator = None, eta: Ferm
 def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=False, Nsw=2, rng=None, seed=1):
     """update!(updatemethod::StandardHMC, U) (standardHMC.jl:41-91) with the molecular dynamics on the device: upload U once,
     sample p / xi / eta, S_old, runMD!, S_new, Metropolis test on the host, and U is overwritten only when accepted.
-    Plain-HMC fermion actions (Wilson, staggered Nf = 4, 8); returns (accepted, S_new - S_old, info)."""
+    Fermion actions: plain HMC (Wilson, staggered Nf = 4, 8) and RHMC (staggered, other Nf: heat bath, force and action through
+    the rational approximations, one multi-shift CG each); returns (accepted, S_new - S_old, info)."""
     ctx = U.context()
-    if fa is not None and isinstance(fa, RHMCFermiAction):
-        raise NotImplementedError("device-resident trajectories are wired for the plain HMC actions")
+    is_rhmc = fa is not None and isinstance(fa, RHMCFermiAction)
     rng = rng or np.random.default_rng(seed)
     if fa is not None:
         D = fa.D(U)                                                   # uploads the links
@@ -574,13 +606,18 @@ def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=
     if fa is not None:
         xi, eta = fa._temporary_fermionfields[1], fa._temporary_fermionfields[2]
         gauss_sampling_in_action_(xi, U, fa, seed=int(rng.integers(1 << 62)))
-        mul_(eta, adjoint(D), xi)                                     # sample_pseudofermions! without re-uploading U
+        if is_rhmc:
+            fa.rational_apply_(eta, fa.rhmc.r_heatbath, xi)           # eta = (D^dag D)^{Nf/16} xi
+        else:
+            mul_(eta, adjoint(D), xi)                                 # sample_pseudofermions! without re-uploading U
         if fa.even_only:
             mask_parity_(eta, 0)
         S_old += dot(xi, xi).real                                     # standardHMC.jl:54
-    its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw)
+    its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw, rational=fa.rhmc.r_action if is_rhmc else None)
     S_new = kinetic_energy(ctx) + gauge_action(ctx, beta)
-    if fa is not None:
+    if is_rhmc:
+        S_new += fa.rational_apply_(fa._temporary_fermionfields[0], fa.rhmc.r_action, eta, want_dot=True)[1]
+    elif fa is not None:
         X = fa._temporary_fermionfields[0]
         clear_fermion_(X)
         solve_DinvX_(X, DdagD(D), eta)

@@ -21,19 +21,22 @@ BETA, KAPPA = 5.7, 0.12
 def main():
     dims = tuple(int(v) for v in sys.argv[1].split("x"))
     pg = tuple(int(v) for v in sys.argv[2].split("x"))
+    rhmc_mode = len(sys.argv) > 3 and sys.argv[3] == "rhmc"      # staggered Nf = 2 rational action instead of Wilson pseudofermions
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = int(os.environ.get("LOCAL_RANK", rank)) % max(torch.cuda.device_count(), 1)
     Ug = orc.random_su3(dims, seed=51, eps=0.4)
     Pg = orc.md_momenta(dims, seed=52)
-    op = orc.make_op(dims, kappa=KAPPA)
-    xi = orc.gaussian_field(dims, orc.WILSON, seed=53)
-    eta_g = orc.apply(op, orc.WILSON, orc.DDAG, Ug, xi)
+    kind = orc.STAGGERED if rhmc_mode else orc.WILSON
+    op = orc.make_op(dims, kappa=KAPPA, mass=0.5)
+    xi = orc.gaussian_field(dims, kind, seed=53)
+    eta_g = orc.apply(op, kind, orc.DDAG, Ug, xi)
+    import test_md
+    ra = test_md._rational_nf2() if rhmc_mode else None
     ref = {}
     if rank == 0:
-        import test_md
         test_md.DIMS = dims
-        f = (op, orc.WILSON, eta_g)
+        f = (op, kind, eta_g, ra) if rhmc_mode else (op, kind, eta_g)
         ref["K0"], ref["Sg0"] = orc.md_kinetic(dims, Pg), orc.md_gauge_action(dims, Ug, BETA)
         ref["U"], ref["P"] = test_md._traj(Ug, Pg, 0.05, 2, nsw=4, fermion=f)
         ref["H0"], ref["H1"] = test_md._H(Ug, Pg, f), test_md._H(ref["U"], ref["P"], f)
@@ -43,17 +46,23 @@ def main():
     (lx, ly, lz, lt), (ox, oy, oz, ot) = ctx.local_dims, ctx.origin
     sl = (slice(None), slice(ot, ot + lt), slice(oz, oz + lz), slice(oy, oy + ly), slice(ox, ox + lx))
     U = q.gaugefields_from_array(np.ascontiguousarray(Ug[sl]), global_dims=dims, procgrid=pg, rank=rank, device=dev)
-    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
-    D = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": KAPPA, "eps_CG": 1e-22, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    x = q.Initialize_pseudofermion_fields(U[0], "staggered" if rhmc_mode else "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "staggered" if rhmc_mode else "Wilson", "κ": KAPPA, "mass": 0.5, "eps_CG": 1e-22,
+                                "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
     ctx.barrier()                                      # every rank has uploaded its links before anybody reads a neighbour's
     q.set_momenta_(ctx, np.ascontiguousarray(Pg[sl]))
-    eta = q.similar(x).from_host(np.ascontiguousarray(eta_g[sl]))
+    eta = q.similar(x).from_host(np.ascontiguousarray(eta_g[sl[1:] if rhmc_mode else sl]))    # staggered fields have no spin axis
     K0, Sg0 = q.kinetic_energy(ctx), q.gauge_action(ctx, BETA)
-    its = q.runMD_(ctx, BETA, 0.05, 2, D, eta, SextonWeingargten=True, Nsw=4)
+    its = q.runMD_(ctx, BETA, 0.05, 2, D, eta, SextonWeingargten=True, Nsw=4, rational=ra)
     X = q.similar(x)
-    q.clear_fermion_(X)
-    q.solve_DinvX_(X, q.DdagD(D), eta)
-    H1 = q.kinetic_energy(ctx) + q.gauge_action(ctx, BETA) + q.dot(eta, X).real
+    if rhmc_mode:
+        fa = q.FermiAction(D, {"Nf": 2, "rational_lambda_min": 0.22, "rational_lambda_max": 17.0})
+        Sf = fa.rational_apply_(X, ra, eta, want_dot=True)[1]
+    else:
+        q.clear_fermion_(X)
+        q.solve_DinvX_(X, q.DdagD(D), eta)
+        Sf = q.dot(eta, X).real
+    H1 = q.kinetic_energy(ctx) + q.gauge_action(ctx, BETA) + Sf
 
     def gather(a):
         h = torch.from_numpy(np.ascontiguousarray(a).view(np.float64))

@@ -55,7 +55,7 @@ def test_gpu_suite_under_emulation(emu_lib):
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 77, tail
+    assert m and int(m.group(1)) >= 78, tail
 
 
 @pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),
@@ -97,10 +97,11 @@ def test_persistent_queue_variant_under_emulation(emu_lib):
     assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_multirank_md_trajectory_under_emulation(emu_lib):
+@pytest.mark.parametrize("action", ["wilson", "rhmc"])
+def test_multirank_md_trajectory_under_emulation(emu_lib, action):
     """device-resident HMC trajectory on 4 ranks (2 partitioned directions: face and corner links from peer-mapped arrays,
-    device-side barriers between the MD sub-steps)"""
+    device-side barriers between the MD sub-steps); rhmc = staggered Nf = 2 rational action (lqcd_md_trajectory_rational)"""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
-           "--master-port", str(35500 + (os.getpid() % 2000)), "tests/mp_md_worker.py", "4x4x4x4", "1x1x2x2"]
+           "--master-port", str(35500 + (os.getpid() % 2000)), "tests/mp_md_worker.py", "4x4x4x4", "1x1x2x2", action]
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -23,7 +23,13 @@ def _traj(U, P, dtau, n, nsw=0, fermion=None):
     U, P = U.copy(), P.copy()
 
     def pf(eps):
-        op, kind, eta = fermion
+        op, kind, eta = fermion[:3]
+        if len(fermion) == 4:              # RHMC: fermion[3] = rational approximation of the action (alpha_j, beta_j)
+            ra = fermion[3]
+            xs = orc.mscg(op, kind, U, eta, list(ra.beta), eps=1e-22, maxsteps=5000)["xs"]
+            F = sum(a * orc.force(op, kind, U, X, orc.apply(op, kind, orc.D, U, X)) for a, X in zip(ra.alpha, xs))
+            orc.md_update_p_force(DIMS, P, F, eps)
+            return
         X = orc.cg(op, kind, U, eta, eps=1e-22)["x"]
         orc.md_update_p_force(DIMS, P, orc.force(op, kind, U, X, orc.apply(op, kind, orc.D, U, X)), eps)
 
@@ -47,10 +53,39 @@ def _traj(U, P, dtau, n, nsw=0, fermion=None):
 
 def _H(U, P, fermion=None):
     H = orc.md_kinetic(DIMS, P) + orc.md_gauge_action(DIMS, U, BETA)
-    if fermion:
+    if fermion and len(fermion) == 4:
+        op, kind, eta, ra = fermion
+        xs = orc.mscg(op, kind, U, eta, list(ra.beta), eps=1e-22, maxsteps=5000)["xs"]
+        H += np.vdot(eta, ra.alpha0 * eta + sum(a * X for a, X in zip(ra.alpha, xs))).real
+    elif fermion:
         op, kind, eta = fermion
         H += np.vdot(eta, orc.cg(op, kind, U, eta, eps=1e-22)["x"]).real
     return H
+
+
+def _rational_nf2():
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "latticeqcd.jl_b200"))
+    from lqcd_b200 import rhmc
+    return rhmc.rational_approx(-2 / 8.0, 12, 0.22, 17.0)
+
+
+def test_rhmc_leapfrog_energy_scaling(golden_dir):
+    """RHMC trajectory (test/test_Nf2.toml physics on its fixture): with the force sum_j alpha_j F(X_j, Y_j) the leapfrog conserves
+    H = K + S_g + eta^dag r(D^dag D) eta at O(dtau^2) -- the relative weight of the rational force against the gauge force"""
+    U0 = np.load(golden_dir / "staggered_nf2_4444.npy")
+    op = orc.make_op(DIMS, mass=0.5)
+    eta = orc.gaussian_field(DIMS, orc.STAGGERED, seed=19)
+    f = (op, orc.STAGGERED, eta, _rational_nf2())
+    P0 = orc.md_momenta(DIMS, seed=6)
+    H0 = _H(U0, P0, f)
+    dH = []
+    for dtau, n in ((0.1, 4), (0.05, 8), (0.025, 16)):
+        U1, P1 = _traj(U0, P0, dtau, n, nsw=0, fermion=f)
+        dH.append(_H(U1, P1, f) - H0)
+    print("dH", dH)
+    assert abs(dH[0]) < 1.0 and 2.5 < dH[0] / dH[1] < 6.0 and 3.0 < dH[1] / dH[2] < 5.0
 
 
 def test_momenta_and_kinetic_term():
@@ -188,3 +223,46 @@ def test_hmc_update_accepts_and_moves_links(Uw):
     plaq = orc.plaquette(DIMS, U.data)
     assert abs(plaq - 0.5784043949012552) / 0.5784043949012552 < 0.1
 
+
+
+@pytest.mark.gpu
+@staged
+def test_rhmc_trajectory_matches_oracle(golden_dir):
+    """runMD! with the RHMC pseudofermion action on the device (lqcd_md_trajectory_rational: one multi-shift CG + accumulated outer
+    products per fermion force) == the oracle's steps composed in the same order; then hmc_update_ with FermiAction(D, Nf = 2)"""
+    import lqcd_b200 as q
+    U0 = np.load(golden_dir / "staggered_nf2_4444.npy")
+    U = q.gaugefields_from_array(U0.copy())
+    x = q.Initialize_pseudofermion_fields(U[0], "staggered")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "staggered", "mass": 0.5, "eps_CG": 1e-22, "MaxCGstep": 5000, "boundarycondition": [1, 1, 1, -1]})
+    ctx = D.ctx
+    op = orc.make_op(DIMS, mass=0.5)
+    ra = _rational_nf2()
+    eta_h = orc.gaussian_field(DIMS, orc.STAGGERED, seed=19)
+    eta = q.similar(x).from_host(eta_h)
+    P0 = orc.md_momenta(DIMS, seed=6)
+    f = (op, orc.STAGGERED, eta_h, ra)
+    # one fermion momentum update
+    q.set_momenta_(ctx, P0)
+    its = q.P_update_fermion_(D, eta, 0.05, rational=ra)
+    Ur, Pr = U0.copy(), P0.copy()
+    xs = orc.mscg(op, orc.STAGGERED, Ur, eta_h, list(ra.beta), eps=1e-22, maxsteps=5000)
+    F = sum(a * orc.force(op, orc.STAGGERED, Ur, X, orc.apply(op, orc.STAGGERED, orc.D, Ur, X)) for a, X in zip(ra.alpha, xs["xs"]))
+    orc.md_update_p_force(DIMS, Pr, F, 0.05)
+    assert its == xs["iters"]
+    assert np.abs(q.get_momenta(ctx) - Pr).max() < 1e-10
+    # a Sexton-Weingarten trajectory
+    q.set_momenta_(ctx, P0)
+    its = q.runMD_(ctx, BETA, 0.05, 3, D, eta, SextonWeingargten=True, Nsw=4, rational=ra)
+    assert its > 0
+    Ur, Pr = _traj(U0, P0, 0.05, 3, nsw=4, fermion=f)
+    assert np.abs(q.get_links(ctx) - Ur).max() < 1e-9 and np.abs(q.get_momenta(ctx) - Pr).max() < 1e-9
+    # update!(StandardHMC, U) with the RHMC action built the way the wrapper does (universe.jl:106-110,138)
+    U = q.gaugefields_from_array(U0.copy())
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "staggered", "mass": 0.5, "eps_CG": 1e-20, "MaxCGstep": 5000, "boundarycondition": [1, 1, 1, -1]})
+    fa = q.FermiAction(D, {"Nf": 2, "rational_lambda_min": 0.22, "rational_lambda_max": 17.0})
+    acc, dH, info = q.hmc_update_(U, BETA, 0.05, 4, fa=fa, rng=np.random.default_rng(3))
+    assert abs(dH) < 0.5 and info["cg_iters"] > 0
+    if acc:
+        assert np.abs(U.data - U0).max() > 1e-3
+        assert np.abs(np.einsum("...ij,...kj->...ik", U.data, U.data.conj()) - np.eye(3)).max() < 1e-9

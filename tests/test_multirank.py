@@ -101,10 +101,11 @@ def test_multirank_clover_parity(dims, pg):
 
 @pytest.mark.gpu
 @pytest.mark.xfail(reason="multi-rank device-resident MD trajectory: verified under tests/emu only, not yet run on hardware", strict=False)
-@pytest.mark.parametrize("dims,pg", [("8x8x8x16", "1x1x1x2"), ("8x8x8x8", "1x1x2x2")])
-def test_multirank_md_trajectory(dims, pg):
-    """Sexton-Weingarten trajectory with Wilson pseudofermions across ranks (tests/mp_md_worker.py)"""
+@pytest.mark.parametrize("dims,pg,action", [("8x8x8x16", "1x1x1x2", "wilson"), ("8x8x8x8", "1x1x2x2", "wilson"), ("8x8x8x8", "1x1x1x2", "rhmc")])
+def test_multirank_md_trajectory(dims, pg, action):
+    """Sexton-Weingarten trajectory across ranks (tests/mp_md_worker.py): Wilson pseudofermions, and the staggered Nf = 2 RHMC
+    action (multi-shift CG + accumulated rational force per step; BASELINE config 5 in miniature)"""
     n = int(np.prod([int(v) for v in pg.split("x")]))
-    res = run_ranks(n, ROOT / "tests" / "mp_md_worker.py", dims, pg, timeout=900)
+    res = run_ranks(n, ROOT / "tests" / "mp_md_worker.py", dims, pg, action, timeout=900)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
