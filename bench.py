@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--cg-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--probe-pipe", action="store_true", help=argparse.SUPPRESS)   # child process of probe_pipe_isolated()
+    ap.add_argument("--experiment", default=None, help=argparse.SUPPRESS)          # child process of run_experiments()
     return ap.parse_args()
 
 
@@ -235,6 +236,189 @@ def probe_pipe_isolated(lattice, local_rank):
         return True, None
     tail = (r.stdout + r.stderr).strip().splitlines()[-1:] or [""]
     return False, f"pipelined call failed the isolated probe (exit {r.returncode}: {tail[0][:160]}): not used"
+
+
+# ---------------------------------------------------------------------------------------------------
+# "experiments": first hardware timings of code paths that were written while no B200 was reachable (pre-flighted under
+# tests/emu only).  NOT part of value / roofline / e2e: each runs in its own child process after the headline measurement is
+# complete (a device fault or hang there cannot touch the measuring process), is checked for correctness against the verified
+# default path, and its numbers are reported under the "experiments" key for the next round's tuning.
+# ---------------------------------------------------------------------------------------------------
+EXPERIMENTS = {
+    # name: (environment of the child, what it measures)
+    "default": ({}, "verified default Wilson kernel (reference for the rows below; writes the 16^4 comparison vector)"),
+    "wilson_kernel3": ({"LQCD_WILSON_KERNEL": "3"}, "t-marching Wilson kernel with the cp.async.bulk spinor window"),
+    "persist": ({"LQCD_PERSIST": "1"}, "persistent-CTA tile-queue Wilson kernel"),
+    "mrhs_r2": ({"LQCD_MRHS_R": "2"}, "12 right-hand sides, 2 per thread (lqcd_dslash_multi)"),
+    "mrhs_r3": ({"LQCD_MRHS_R": "3"}, "12 right-hand sides, 3 per thread"),
+    "mrhs_r4": ({"LQCD_MRHS_R": "4"}, "12 right-hand sides, 4 per thread"),
+    "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides per pass"),
+    "clover": ({}, "Wilson-clover Dslash (csw = 1.5612)"),
+    "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
+    "md": ({}, "device-resident Sexton-Weingarten trajectory with Wilson pseudofermions, 16^4"),
+}
+
+
+def _timed(fn, reps):
+    """wall clock around calls that return with the library stream drained (every exported call is blocking-on-return)"""
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) * 1e3 / reps
+
+
+def experiment_child(name, dims):
+    """child process: prints ONE JSON dict on stdout"""
+    import numpy as np
+    import lqcd_b200 as q
+    from lqcd_b200 import _lib as L
+    out = {"name": name, "ok": False}
+    ref_file = Path(tempfile.gettempdir()) / f"lqcd_b200_exp_ref_{os.environ.get('LQCD_EXP_TAG', '0')}.npy"
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    small = tuple(int(v) for v in os.environ.get("LQCD_EXP_SMALL", "16x16x16x16").split("x"))     # (tests shrink it under emulation)
+    V = int(np.prod(dims))
+
+    def setup(d, kind=L.WILSON, csw=0.0, eps=-1.0):
+        ctx = q.get_context(d, procgrid=(1, 1, 1, 1), rank=0, device=dev)
+        ctx.call("lqcd_gauge_random", 111, eps)
+        op = L.LqcdOp()
+        op.kind, op.kappa, op.r, op.mass, op.csw = kind, KAPPA, 1.0, 0.5, csw
+        for i, b in enumerate(BC):
+            op.bc[i] = b
+        x, y = q.FermionField(ctx, kind), q.FermionField(ctx, kind)
+        q.gauss_distribution_fermion_(x, 112)
+        return ctx, op, x, y
+
+    def dslash_ms(ctx, op, y, x, reps=20):
+        mean, mn = C.c_double(), C.c_double()
+        ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, 3, 0, C.byref(mean), C.byref(mn))
+        ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
+        return mean.value
+
+    if name in ("default", "wilson_kernel3", "persist"):
+        ctx, op, x, y = setup(small)
+        ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
+        got = y.to_host()
+        if name == "default":
+            np.save(ref_file, got)
+            out["max_rel_dev_vs_default"] = 0.0
+        else:
+            ref = np.load(ref_file)
+            out["max_rel_dev_vs_default"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+        out["ok"] = out["max_rel_dev_vs_default"] < 1e-13
+        out["ms_16^4"] = dslash_ms(ctx, op, y, x, 50)
+        ctx2, op2, x2, y2 = setup(dims)
+        ms = dslash_ms(ctx2, op2, y2, x2)
+        out.update({"ms_per_apply": ms, "GB/s": BYTES_PER_SITE * V / ms / 1e6, "frac_of_peak": BYTES_PER_SITE * V / ms / 1e6 / peaks()[0]})
+    elif name.startswith("mrhs_r") or name == "staggered_mrhs":
+        kind = L.STAGGERED if name == "staggered_mrhs" else L.WILSON
+        nrhs = 12
+        ctx, op, x, y = setup(dims, kind)
+        xs = [x] + [q.FermionField(ctx, kind) for _ in range(nrhs - 1)]
+        for j, f in enumerate(xs[1:]):
+            q.gauss_distribution_fermion_(f, 200 + j)
+        ys = [q.FermionField(ctx, kind) for _ in range(nrhs)]
+        hx = (C.c_void_p * nrhs)(*[f.h.value for f in xs])
+        hy = (C.c_void_p * nrhs)(*[f.h.value for f in ys])
+        ctx.call("lqcd_dslash_multi", C.byref(op), hy, hx, nrhs, L.OP_D)
+        same = True
+        for j in (0, 5, 11):                       # bit-for-bit against the verified single-RHS kernel
+            ctx.call("lqcd_dslash", C.byref(op), y.h, xs[j].h, L.OP_D)
+            same = same and bool(np.array_equal(y.to_host(), ys[j].to_host()))
+        out["ok"] = out["bit_identical_to_single_rhs"] = same
+        ms = _timed(lambda: ctx.call("lqcd_dslash_multi", C.byref(op), hy, hx, nrhs, L.OP_D), 10)
+        single = dslash_ms(ctx, op, y, x)
+        per_site = 672 if kind == L.STAGGERED else BYTES_PER_SITE
+        out.update({"nrhs": nrhs, "ms_per_pass": ms, "ms_per_rhs": ms / nrhs, "ms_single_rhs_kernel": single, "speedup_per_rhs": single * nrhs / ms,
+                    "equivalent_single_rhs_GB/s": per_site * V * nrhs / ms / 1e6})
+    elif name == "clover":
+        ctx, op, x, y = setup(dims, csw=1.5612)
+        ms = dslash_ms(ctx, op, y, x)
+        # gamma5-hermiticity <a, D b> = <D^dag a, b> as the size-independent check (the clover term is Hermitian)
+        a = q.FermionField(ctx, L.WILSON)
+        q.gauss_distribution_fermion_(a, 113)
+        z = q.FermionField(ctx, L.WILSON)
+        ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
+        ctx.call("lqcd_dslash", C.byref(op), z.h, a.h, L.OP_DDAG)
+        l, r = q.dot(a, y), q.dot(z, x)
+        out["adjoint_identity_rel_dev"] = abs(l - r) / abs(l)
+        out["ok"] = out["adjoint_identity_rel_dev"] < 1e-12
+        out.update({"ms_per_apply": ms, "GB/s": (BYTES_PER_SITE + 576) * V / ms / 1e6})
+    elif name == "evenodd":
+        ctx, op, x, y = setup(small, eps=0.3)
+        it, rs = C.c_int(0), C.c_double(0.0)
+        res = {}
+        for fn in ("lqcd_solve", "lqcd_solve_eo"):
+            q.clear_fermion_(y)
+            t0 = time.perf_counter()
+            ctx.call(fn, C.byref(op), y.h, x.h, L.SOLVER_CGNR, L.OP_D, 1e-16, 3000, C.byref(it), C.byref(rs), None)
+            res[fn] = {"iters": it.value, "resid_sq": rs.value, "wall_ms": (time.perf_counter() - t0) * 1e3, "sol": y.to_host()}
+        dev_rel = float(np.abs(res["lqcd_solve"]["sol"] - res["lqcd_solve_eo"]["sol"]).max() / np.abs(res["lqcd_solve"]["sol"]).max())
+        out["ok"] = dev_rel < 1e-6
+        out.update({"solution_rel_dev": dev_rel, "full": {k: v for k, v in res["lqcd_solve"].items() if k != "sol"},
+                    "evenodd": {k: v for k, v in res["lqcd_solve_eo"].items() if k != "sol"}})
+    elif name == "md":
+        ctx, op, x, y = setup(small, eps=0.3)
+        its = C.c_longlong(0)
+
+        def quenched(dtau, steps):          # same start every time: links and momenta come from counter-based generators
+            ctx.call("lqcd_gauge_random", 111, 0.3)
+            ctx.call("lqcd_md_momenta_gaussian", 7)
+            K0, S0, K1, S1 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+            ctx.call("lqcd_md_kinetic", C.byref(K0)); ctx.call("lqcd_md_gauge_action", 5.7, C.byref(S0))
+            t0 = time.perf_counter()
+            ctx.call("lqcd_md_trajectory", None, None, 5.7, dtau, steps, 0, 0.0, 1, C.byref(its))
+            wall = time.perf_counter() - t0
+            ctx.call("lqcd_md_kinetic", C.byref(K1)); ctx.call("lqcd_md_gauge_action", 5.7, C.byref(S1))
+            return (K1.value + S1.value) - (K0.value + S0.value), wall
+
+        dH1, wall = quenched(0.02, 10)
+        dH2, _ = quenched(0.01, 20)
+        out["ok"] = bool(2.5 < dH1 / dH2 < 6.0)                  # leapfrog: Delta H = O(dtau^2)
+        out.update({"quenched_dH_dtau0.02": dH1, "quenched_dH_dtau0.01": dH2, "wall_ms_10_steps": wall * 1e3})
+        ctx.call("lqcd_gauge_random", 111, 0.3)
+        ctx.call("lqcd_md_momenta_gaussian", 7)
+        t0 = time.perf_counter()
+        ctx.call("lqcd_md_trajectory", C.byref(op), x.h, 5.7, 0.02, 2, 4, 1e-16, 3000, C.byref(its))
+        out.update({"dynamical_wall_ms_2_steps_nsw4": (time.perf_counter() - t0) * 1e3, "cg_iters": its.value})
+    else:
+        out["error"] = "unknown experiment"
+    print("EXPERIMENT " + json.dumps(out), flush=True)
+
+
+def run_experiments(lattice, local_rank, budget_s):
+    """parent side: every experiment in its own child process, bounded in time; returns {name: result}"""
+    results = {}
+    t_start = time.perf_counter()
+    tag = str(os.getpid())
+    for name, (env_extra, what) in EXPERIMENTS.items():
+        left = budget_s - (time.perf_counter() - t_start)
+        if left < 20:
+            results[name] = {"skipped": "time budget of the experiments leg used up"}
+            continue
+        env = dict(os.environ, LOCAL_RANK=str(local_rank), LQCD_EXP_TAG=tag, **env_extra)
+        for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--experiment", name, "--lattice", lattice], env=env,
+                               capture_output=True, text=True, timeout=min(left, 120))
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("EXPERIMENT ")]
+            if line:
+                results[name] = json.loads(line[-1][len("EXPERIMENT "):])
+            else:
+                tail = (r.stdout + r.stderr).strip().splitlines()[-1:] or [""]
+                results[name] = {"ok": False, "error": f"exit {r.returncode}: {tail[0][:200]}"}
+        except subprocess.TimeoutExpired:
+            results[name] = {"ok": False, "error": "timed out"}
+        except Exception as exc:
+            results[name] = {"ok": False, "error": repr(exc)}
+        results[name]["what"] = what
+    try:
+        (Path(tempfile.gettempdir()) / f"lqcd_b200_exp_ref_{tag}.npy").unlink()
+    except OSError:
+        pass
+    return results
 
 
 def choose_procgrid(n):
@@ -434,6 +618,13 @@ def run_b200(args, dims):
         cpu = {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["threads"], "kind": "port",
                "sample": f"3 full-lattice Wilson applications at {args.lattice} ({r['ms']:.0f} ms each), oracle/lqcd_oracle.c with OpenMP"}
 
+    experiments = None
+    if rank == 0 and world == 1 and os.environ.get("LQCD_BENCH_EXPERIMENTS", "1") != "0":
+        try:
+            experiments = run_experiments(args.lattice, local_rank, float(os.environ.get("LQCD_BENCH_EXPERIMENTS_S", "240")))
+        except Exception as exc:
+            experiments = {"error": repr(exc)}
+
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -454,6 +645,7 @@ def run_b200(args, dims):
         "cg": {"iters_per_s": cg_ips, "iters": n_it, "ms": cg_ms, "roofline_frac_unfused": CG_BYTES_PER_SITE * V * cg_ips / 1e9 / peak,
                "converged_iters_eps1e-10": it_conv, "resid_sq": rs_conv, "field": "warm eps=0.3"},
         "e2e": e2e, "e2e_cg": e2e_cg, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks,
+        "experiments": experiments,
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -462,7 +654,9 @@ def run_b200(args, dims):
 def main():
     args = parse_args()
     dims = tuple(int(v) for v in args.lattice.split("x"))
-    if args.probe_pipe:
+    if args.experiment:
+        experiment_child(args.experiment, dims)
+    elif args.probe_pipe:
         probe_pipe_child(dims)
     elif args.impl == "reference":
         run_reference(args, dims)

@@ -96,7 +96,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false; ctx->mom = nullptr; ctx->mom_valid = false;
-    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr; ctx->queue = nullptr;
+    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr; ctx->queue = nullptr; ctx->mrhs = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
@@ -139,6 +139,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
 int comm_destroy(lqcd_ctx *ctx);
 void eo_destroy(lqcd_ctx *ctx);       // wilson_eo.cu
 void pipe_destroy(lqcd_ctx *ctx);     // host_pipeline.cu
+void mrhs_destroy(lqcd_ctx *ctx);     // mrhs.cu
 
 extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     if (!ctx) return LQCD_OK;
@@ -147,8 +148,9 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     comm_destroy(ctx);
     eo_destroy(ctx);
     pipe_destroy(ctx);
+    mrhs_destroy(ctx);
     for (int k = 0; k < 2; k++)
-        for (auto *f : ctx->scratch[k]) { cudaFree(f->d); delete f; }
+        for (auto *f : ctx->scratch[k]) if (f) { cudaFree(f->d); delete f; }
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover);
     cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
@@ -373,11 +375,8 @@ extern "C" int lqcd_fermion_free(lqcd_ctx *ctx, lqcd_fermion *f) {
 
 int get_scratch(lqcd_ctx *ctx, int kind, int idx, lqcd_fermion **out) {
     auto &v = ctx->scratch[kind];
-    while ((int)v.size() <= idx) {
-        lqcd_fermion *f = nullptr;
-        LQCD_TRY(alloc_fermion(ctx, kind, &f));
-        v.push_back(f);
-    }
+    if ((int)v.size() <= idx) v.resize(idx + 1, nullptr);      // slots are allocated one by one on first use (callers use sparse ranges)
+    if (!v[idx]) LQCD_TRY(alloc_fermion(ctx, kind, &v[idx]));
     *out = v[idx];
     return LQCD_OK;
 }

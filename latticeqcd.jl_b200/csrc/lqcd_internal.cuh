@@ -172,6 +172,7 @@ struct lqcd_ctx {
     // even-odd preconditioned solve -- see wilson_eo.cu
     struct EoState *eo;
     unsigned int *queue;       // tile queue of the persistent-CTA Dslash variants (zero between launches)
+    struct MrhsWork *mrhs;     // per-right-hand-side solver states / reduction workspaces of the batched solves -- see mrhs.cu
     struct HostPipe *pipe;     // host-field pipeline (streams, events, two staging buffers) -- see host_pipeline.cu
     int eo_active;             // 1 while lqcd_solve_eo runs the Krylov loop: the solver's operator is Mhat on even half fields
 };

@@ -164,6 +164,37 @@ function solve_DinvX!(y::AbstractFermionfields, A::B200Dirac, x::AbstractFermion
     return y
 end
 
+"""
+    solve_DinvX!(ys::Vector, A, xs::Vector)
+
+All right-hand sides in lock step, every link fetched from HBM serving a group of them (lqcd_solve_multi, csrc/mrhs.cu): the loop
+`map(i -> calc_quark_propagators_point_source_each(m, U, D, i, stvec), 1:NC*m.Nspinor)` of measure_Pion_correlator.jl:333-349 and
+the `for ir = 1:Nr` loop of measure_chiral_condensate.jl:176-182 become ONE call.  Per right-hand side the result (and for the
+default "bicg" method the iteration count) is that of its own `solve_DinvX!(y, A, x)`.
+"""
+function solve_DinvX!(ys::Vector{<:AbstractFermionfields}, A::B200Dirac, xs::Vector{<:AbstractFermionfields})
+    n = length(ys); @assert n == length(xs) && n <= 16
+    dx = [B200Field(A.ctx, A.op.kind) for _ = 1:n]; dy = [B200Field(A.ctx, A.op.kind) for _ = 1:n]
+    for j = 1:n; upload!(dx[j], xs[j]); upload!(dy[j], ys[j]); end
+    method = mode(A) == OP_DDAGD ? SOLVER_CG : A.method
+    iters = zeros(Cint, n); rs = zeros(Cdouble, n)
+    check(A.ctx.h, ccall((:lqcd_solve_multi, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cint}, Ptr{Cdouble}),
+        A.ctx.h, A.op, [f.h for f in dy], [f.h for f in dx], n, method, mode(A), A.eps, A.maxsteps, iters, rs))
+    for j = 1:n; download!(ys[j], dy[j]); end
+    return ys
+end
+"mul!(ys, D, xs) for several fields in one pass over the links (lqcd_dslash_multi)"
+function mul!(ys::Vector{<:AbstractFermionfields}, D::B200Dirac, xs::Vector{<:AbstractFermionfields})
+    n = length(ys); @assert n == length(xs) && n <= 16
+    dx = [B200Field(D.ctx, D.op.kind) for _ = 1:n]; dy = [B200Field(D.ctx, D.op.kind) for _ = 1:n]
+    for j = 1:n; upload!(dx[j], xs[j]); end
+    check(D.ctx.h, ccall((:lqcd_dslash_multi, LIB), Cint, (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Cint),
+                         D.ctx.h, D.op, [f.h for f in dy], [f.h for f in dx], n, mode(D)))
+    for j = 1:n; download!(ys[j], dy[j]); end
+    return ys
+end
+
 # ---- fermion action (Wilson two-flavour / staggered Nf=8 form; RHMC fractions go through lqcd_multishift_cg) ----
 struct B200FermiAction
     D::B200Dirac{:D}

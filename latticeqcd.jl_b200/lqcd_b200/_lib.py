@@ -75,6 +75,8 @@ SIGNATURES = {
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_solve_eo": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_multishift_cg": (i32, [vp, pop, pvp, vp, pdbl, i32, dbl, i32, pi32, pdbl]),
+    "lqcd_dslash_multi": (i32, [vp, pop, pvp, pvp, i32, i32]),
+    "lqcd_solve_multi": (i32, [vp, pop, pvp, pvp, i32, i32, i32, dbl, i32, pi32, pdbl]),
     "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, i32, pi32, pdbl]),
     "lqcd_fermion_force_xy": (i32, [vp, pop, vp, vp, dbl, i32]),
     "lqcd_fermion_force_download": (i32, [vp, pvp, i32]),

@@ -380,6 +380,57 @@ def solve_DinvX_(y: FermionField, A, x: FermionField, history=False):
     return D.last
 
 
+def _handles(fields):
+    return (C.c_void_p * len(fields))(*[f.h.value for f in fields])
+
+
+def mul_multi_(ys, A, xs):
+    """mul!(ys[j], A, xs[j]) for all j in ONE pass over the links (lqcd_dslash_multi); bit-identical to the loop of mul_"""
+    D, mode = _base(A)
+    assert len(ys) == len(xs)
+    D.ctx.call("lqcd_dslash_multi", C.byref(D.op), _handles(ys), _handles(xs), len(ys), mode)
+    return ys
+
+
+def solve_DinvX_multi_(ys, A, xs):
+    """solve_DinvX!(ys[j], A, xs[j]) for all j in lock step (lqcd_solve_multi): the loops over sources of
+    calc_quark_propagators_point_source (measure_Pion_correlator.jl:333-349) and of the chiral condensate's noise vectors
+    (measure_chiral_condensate.jl:176-182) as one batched solve.  ys[j] is the initial guess.  Returns a list of per-source infos;
+    raises NotConverged like solve_DinvX_ if any source did not converge."""
+    D, mode = _base(A)
+    assert len(ys) == len(xs)
+    method = L.SOLVER_CG if mode == L.OP_DDAGD else _METHODS[D.method]
+    n = len(ys)
+    its, rs = (C.c_int * n)(), (C.c_double * n)()
+    try:
+        D.ctx.call("lqcd_solve_multi", C.byref(D.op), _handles(ys), _handles(xs), n, method, mode, D.eps, D.maxsteps, its, rs)
+    finally:
+        D.last = {"iters": list(its), "resid_sq": list(rs)}
+    return [{"iters": its[j], "resid_sq": rs[j]} for j in range(n)]
+
+
+def calc_quark_propagators_point_source(D: DiracOperator, origin=(0, 0, 0, 0)):
+    """D^-1 on the NC*Nspinor point sources at `origin` (measure_Pion_correlator.jl:333-409: source i has spin is = (i-1) % Nspinor,
+    colour ic = (i-is) / Nspinor, value 1 at the origin; clear_fermion!(p); solve_DinvX!(p, D, b)), all sources in one batched
+    solve.  Returns (propagators, infos), propagators[i] a device field like the reference's deepcopy(p).  origin = (x, y, z, t)."""
+    nspin = 4 if D.kind == L.WILSON else 1
+    n = 3 * nspin
+    bs = [FermionField(D.ctx, D.kind) for _ in range(n)]
+    ps = [FermionField(D.ctx, D.kind) for _ in range(n)]
+    x0, y0, z0, t0 = origin
+    for i in range(n):
+        is_, ic = i % nspin, i // nspin
+        h = np.zeros(bs[i].host_shape, dtype=np.complex128)
+        if D.kind == L.WILSON:
+            h[is_, t0, z0, y0, x0, ic] = 1.0
+        else:
+            h[t0, z0, y0, x0, ic] = 1.0
+        bs[i].from_host(h)
+        clear_fermion_(ps[i])
+    infos = solve_DinvX_multi_(ps, D, bs)
+    return ps, infos
+
+
 def shiftedcg_(ys, D: DiracOperator, x: FermionField, shifts, eps=None, maxsteps=None):
     """upstream shiftedcg: (DdagD + shifts[j]) ys[j] = x."""
     sh = np.ascontiguousarray(shifts, dtype=np.float64)

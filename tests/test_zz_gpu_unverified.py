@@ -152,3 +152,138 @@ def test_pipelined_host_mul_matches_three_call_sequence(dims, kind):
         want = orc.apply(op, k, mode, Uh, src)
         assert np.abs(out - want).max() / np.abs(want).max() < 1e-13
         assert np.array_equal(x.to_host(), src) and np.array_equal(y.to_host(), out)      # device fields hold source and result
+
+
+# ---- several right-hand sides in lock step (csrc/mrhs.cu) --------------------------------------------------
+def _mrhs_setup(kind, dims, seed=3):
+    import lqcd_b200 as q
+    Uh = orc.random_su3(dims, seed=seed, eps=0.35)
+    U = q.gaugefields_from_array(Uh)
+    name = "Wilson" if kind == orc.WILSON else "staggered"
+    x = q.Initialize_pseudofermion_fields(U[0], name)
+    D = q.Dirac_operator(U, x, {"Dirac_operator": name, "κ": 0.12, "mass": 0.5, "r": 1.0, "boundarycondition": [1, 1, 1, -1],
+                                "eps_CG": 1e-20, "MaxCGstep": 3000})
+    return q, Uh, U, x, D, orc.make_op(dims, kappa=0.12, mass=0.5)
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (6, 8, 4, 4), (32, 4, 4, 4)])
+@pytest.mark.parametrize("kind,nrhs", [(orc.WILSON, 2), (orc.WILSON, 5), (orc.WILSON, 12), (orc.WILSON, 16),
+                                       (orc.STAGGERED, 3), (orc.STAGGERED, 7), (orc.STAGGERED, 16)])
+def test_multi_rhs_dslash_is_bit_identical_to_single(dims, kind, nrhs):
+    """mul_multi_ == the loop of mul_ bit for bit (D, D^dag, D^dag D), and equals the oracle"""
+    q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
+    srcs = [orc.gaussian_field(dims, kind, seed=100 + j) for j in range(nrhs)]
+    xs = [q.similar(x).from_host(s) for s in srcs]
+    ys = [q.similar(x) for _ in range(nrhs)]
+    y1 = q.similar(x)
+    for A, mode in ((D, orc.D), (q.adjoint(D), orc.DDAG), (q.DdagD(D), orc.DDAGD)):
+        q.mul_multi_(ys, A, xs)
+        for j in range(nrhs):
+            q.mul_(y1, A, xs[j])
+            got = ys[j].to_host()
+            assert np.array_equal(got, y1.to_host()), (mode, j)
+            if j in (0, nrhs - 1):
+                want = orc.apply(op, kind, mode, Uh, srcs[j])
+                assert np.abs(got - want).max() / np.abs(want).max() < 1e-13
+            assert np.array_equal(xs[j].to_host(), srcs[j])             # inputs untouched
+
+
+@pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
+@pytest.mark.parametrize("dagger", [False, True])
+def test_multi_rhs_cgnr_matches_single_solves(kind, dagger):
+    """solve_DinvX_multi_ (CGNR = upstream "bicg"): right-hand sides of very different difficulty (point sources, Gaussian noise, a
+    source that is already solved by its initial guess) advance in lock step; each one's iteration count, residual and solution
+    are those of its own single solve, bit for bit; iteration counts equal the oracle's"""
+    dims = (8, 4, 4, 8)
+    q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
+    A = q.adjoint(D) if dagger else D
+    srcs = []
+    for j in range(3):
+        h = np.zeros(x.host_shape, dtype=complex)
+        h[(j, 0, 0, 0, 0, j) if kind == orc.WILSON else (0, 0, j, 0, j)] = 1.0
+        srcs.append(h)
+    srcs += [orc.gaussian_field(dims, kind, seed=40 + j) for j in range(3)]
+    srcs.append(np.zeros(x.host_shape, dtype=complex))                  # b = 0 with x0 = 0: converged at step 0
+    bs = [q.similar(x).from_host(s) for s in srcs]
+    ys = [q.similar(x) for _ in srcs]
+    for y in ys:
+        q.clear_fermion_(y)
+    infos = q.solve_DinvX_multi_(ys, A, bs)
+    y1 = q.similar(x)
+    for j, s in enumerate(srcs):
+        q.clear_fermion_(y1)
+        one = q.solve_DinvX_(y1, A, bs[j])
+        assert infos[j]["iters"] == one["iters"] and infos[j]["resid_sq"] == one["resid_sq"], (j, infos[j], one)
+        assert np.array_equal(ys[j].to_host(), y1.to_host()), j
+        if dagger:                       # the oracle's CGNR solves D x = b only: check the true residual of D^dag x = b
+            tr = s - orc.apply(op, kind, orc.DDAG, Uh, ys[j].to_host())
+            assert np.vdot(tr, tr).real < 1e-18
+            continue
+        ref = orc.cgnr(op, kind, Uh, s, eps=1e-20)
+        assert ref["converged"] and infos[j]["iters"] == ref["iters"], (j, infos[j]["iters"], ref["iters"])
+        if np.abs(ref["x"]).max() > 0:
+            assert np.abs(ys[j].to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+    assert infos[-1]["iters"] == 0
+
+
+@pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
+def test_multi_rhs_cg_on_DdagD(kind):
+    dims = (8, 4, 4, 8)
+    q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
+    srcs = [orc.gaussian_field(dims, kind, seed=60 + j) for j in range(5)]
+    bs = [q.similar(x).from_host(s) for s in srcs]
+    ys = [q.similar(x) for _ in srcs]
+    guess = orc.gaussian_field(dims, kind, seed=70)
+    for j, y in enumerate(ys):
+        if j == 1:
+            y.from_host(guess)                                          # ys[j] doubles as the initial guess
+        else:
+            q.clear_fermion_(y)
+    infos = q.solve_DinvX_multi_(ys, q.DdagD(D), bs)
+    for j, s in enumerate(srcs):
+        ref = orc.cg(op, kind, Uh, s, eps=1e-20, x0=guess if j == 1 else None)
+        assert ref["converged"] and abs(infos[j]["iters"] - ref["iters"]) <= 1, (j, infos[j]["iters"], ref["iters"])
+        assert np.abs(ys[j].to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-9
+
+
+def test_multi_rhs_nonconvergence_names_the_source():
+    import lqcd_b200 as q
+    dims = (4, 4, 4, 4)
+    _, Uh, U, x, D, op = _mrhs_setup(orc.WILSON, dims)
+    D.maxsteps = 3
+    bs = [q.similar(x).from_host(orc.gaussian_field(dims, orc.WILSON, seed=80 + j)) for j in range(4)]
+    bs[2].from_host(np.zeros(x.host_shape, dtype=complex))
+    ys = [q.similar(x) for _ in bs]
+    for y in ys:
+        q.clear_fermion_(y)
+    with pytest.raises(q.NotConverged, match="right-hand side 0"):
+        q.solve_DinvX_multi_(ys, D, bs)
+    assert D.last["iters"] == [3, 3, 0, 3]
+
+
+@pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
+def test_point_source_propagators(golden_dir, kind):
+    """calc_quark_propagators_point_source (measure_Pion_correlator.jl:333-409) on the reference's own 4^4 fixtures: the NC*Nspinor
+    columns of D^-1 from ONE batched solve against the oracle's CGNR per source, and D * column = source"""
+    import lqcd_b200 as q
+    dims = (4, 4, 4, 4)
+    Uh = np.load(golden_dir / ("wilson_4444.npy" if kind == orc.WILSON else "staggered_4444.npy"))
+    U = q.gaugefields_from_array(Uh)
+    name = "Wilson" if kind == orc.WILSON else "staggered"
+    x = q.Initialize_pseudofermion_fields(U[0], name)
+    D = q.Dirac_operator(U, x, {"Dirac_operator": name, "κ": 0.141139, "mass": 0.5, "boundarycondition": [1, 1, 1, -1],
+                                "eps_CG": 1e-19, "MaxCGstep": 3000})
+    op = orc.make_op(dims, kappa=0.141139, mass=0.5)
+    props, infos = q.calc_quark_propagators_point_source(D)
+    nspin = 4 if kind == orc.WILSON else 1
+    assert len(props) == 3 * nspin
+    y = q.similar(x)
+    for i in (0, len(props) // 2, len(props) - 1):
+        is_, ic = i % nspin, i // nspin
+        b = np.zeros(x.host_shape, dtype=complex)
+        b[(is_, 0, 0, 0, 0, ic) if kind == orc.WILSON else (0, 0, 0, 0, ic)] = 1.0
+        ref = orc.cgnr(op, kind, Uh, b, eps=1e-19)
+        assert infos[i]["iters"] == ref["iters"]
+        assert np.abs(props[i].to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+        q.mul_(y, D, props[i])
+        assert np.abs(y.to_host() - b).max() < 1e-8
