@@ -154,6 +154,25 @@ int lqcd_solve_eo(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_
 int lqcd_dslash_host(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, lqcd_fermion *x, double *y_host, const double *x_host,
                      int mode, int ndw);
 
+/* ---- gauge configurations in the reference's file formats (csrc/gauge_io.cu) ------------------------------
+ *      `initial = "<file>"` + loadU_format (src/system/universe.jl:58-77: ILDG :62-65, load_BridgeText! :66-68) and saveU_format
+ *      (src/system/lqcd.jl:226-247: save_binarydata "ILDG", save_textdata "BridgeText").  format: LQCD_IO_ILDG = one LIME record
+ *      "ildg-binary-data" of big-endian float64, LQCD_IO_BRIDGETEXT = one float64 per line as Julia prints it; both site-major
+ *      (x fastest), per site mu, row, column, (re, im).  Files written here are byte-identical to the reference's own fixtures
+ *      (test/confs_HMC_L04040404_beta5.7_Wilson_kappa0.141139/conf_00000100.ildg and .ildg.txt) when given the same links.
+ *      lqcd_io_read_gauge / _write_gauge   HOST only (no GPU, no context; errors through lqcd_last_error(NULL)): file <-> the four
+ *                                          Julia-layout arrays of lqcd_gauge_upload, wing ndw, any NC
+ *      lqcd_gauge_load / lqcd_gauge_save   file <-> device links (NC = 3): every rank moves only the rows of its own block; byte
+ *                                          swap and the site-major <-> AoSoA-32 transposition run in one kernel.  ILDG save across
+ *                                          ranks: the rank owning the lattice origin creates the file -- call it there first,
+ *                                          then (host barrier) on the others.  BridgeText save: single rank. */
+#define LQCD_IO_ILDG 0
+#define LQCD_IO_BRIDGETEXT 1
+int lqcd_io_read_gauge(const char *path, int format, const int dims[4], int nc, double *const U_mu[4], int ndw);
+int lqcd_io_write_gauge(const char *path, int format, const int dims[4], int nc, const double *const U_mu[4], int ndw);
+int lqcd_gauge_load(lqcd_ctx *ctx, const char *path, int format);
+int lqcd_gauge_save(lqcd_ctx *ctx, const char *path, int format);
+
 /* ---- several right-hand sides in lock step ----------------------------------------------------------
  *      The reference's measurement solves are loops of independent solves against the same links: the NC*Nspinor point sources
  *      of calc_quark_propagators_point_source (src/measurements/unusedfiles/measure_Pion_correlator.jl:333-349, solve_DinvX! at

@@ -596,8 +596,13 @@ __global__ void plaquette_kernel(const cplx *gauge, Geom g, Reduce R) {
 extern "C" int lqcd_gauge_plaquette(lqcd_ctx *ctx, double *plaq) {
     if (!ctx || !plaq) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
     if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "no gauge field on the device");
-    if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "plaquette is implemented for a single rank");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nranks > 1) {       // across ranks: the MD plaquette kernel reads the neighbours' peer-mapped links (gauge_md.cu); collective
+        double act = 0.0;
+        LQCD_TRY(lqcd_md_gauge_action(ctx, 1.0, &act));               // = -(1/NC) sum_plaq Re tr U_p over the GLOBAL lattice
+        *plaq = -act / (6.0 * (double)ctx->g.gX * ctx->g.gY * ctx->g.gZ * ctx->g.gT);
+        return LQCD_OK;
+    }
     int bs = 128, grid = (ctx->g.V + bs - 1) / bs;
     plaquette_kernel<<<grid, bs, 0, ctx->stream>>>(ctx->gauge, ctx->g, ctx->red);
     ctx->launches++;

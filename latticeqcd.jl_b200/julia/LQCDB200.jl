@@ -270,6 +270,15 @@ function evaluate_FermiAction(fa::B200RHMCAction, U, η)
     return S[]
 end
 
+# ---- gauge configurations in the reference's file formats straight to / from the device links (csrc/gauge_io.cu) -----------------
+# `initial = "<file>"` + loadU_format (universe.jl:62-68) and saveU_format (lqcd.jl:236-242).  The host-array forms
+# (load_BridgeText!, ILDG + load_gaugefield!, save_binarydata, save_textdata) stay Gaugefields.jl's; these skip the host arrays.
+const IO_FORMATS = Dict("ILDG" => 0, "BridgeText" => 1)
+load_gaugefield_device!(ctx::B200Context, filename::String, loadU_format::String="ILDG") =
+    check(ctx.h, ccall((:lqcd_gauge_load, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint), ctx.h, filename, IO_FORMATS[loadU_format]))
+save_gaugefield_device(ctx::B200Context, filename::String, saveU_format::String="ILDG") =
+    check(ctx.h, ccall((:lqcd_gauge_save, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint), ctx.h, filename, IO_FORMATS[saveU_format]))
+
 # ---- device-resident molecular dynamics (src/md/standardMD.jl:103-165, src/md/AbstractMD.jl:78-135) -------------------------
 # runMD!(U, md) for a StandardMD whose fermi_action is a B200FermiAction (or quenched): the links are uploaded once, momenta
 # are sampled on the device, U_update! / P_update! / P_update_fermion! run as kernels (lqcd_md_trajectory), and U is

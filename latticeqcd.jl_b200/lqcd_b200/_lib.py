@@ -18,6 +18,7 @@ LQCD_OK, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_NOCONV, ERR_NOGPU, ERR_STATE = range(7
 WILSON, STAGGERED = 0, 1
 OP_D, OP_DDAG, OP_DDAGD = 0, 1, 2
 SOLVER_CG, SOLVER_CGNR, SOLVER_BICGSTAB = 0, 1, 2
+IO_ILDG, IO_BRIDGETEXT = 0, 1
 IPC_HANDLE_BYTES = 256
 
 
@@ -75,6 +76,10 @@ SIGNATURES = {
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_solve_eo": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_multishift_cg": (i32, [vp, pop, pvp, vp, pdbl, i32, dbl, i32, pi32, pdbl]),
+    "lqcd_io_read_gauge": (i32, [C.c_char_p, i32, pi32, i32, pvp, i32]),
+    "lqcd_io_write_gauge": (i32, [C.c_char_p, i32, pi32, i32, pvp, i32]),
+    "lqcd_gauge_load": (i32, [vp, C.c_char_p, i32]),
+    "lqcd_gauge_save": (i32, [vp, C.c_char_p, i32]),
     "lqcd_dslash_multi": (i32, [vp, pop, pvp, pvp, i32, i32]),
     "lqcd_solve_multi": (i32, [vp, pop, pvp, pvp, i32, i32, i32, dbl, i32, pi32, pdbl]),
     "lqcd_fermion_force": (i32, [vp, pop, vp, vp, dbl, i32, pvp, i32, pi32, pdbl]),

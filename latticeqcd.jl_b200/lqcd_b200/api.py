@@ -173,6 +173,77 @@ def gaugefields_from_array(arr, global_dims=None, **ctx_args) -> Gaugefields:
 
 
 # ---------------------------------------------------------------------------------------------------
+# gauge configurations in the reference's file formats (universe.jl:58-77, lqcd.jl:226-247; csrc/gauge_io.cu)
+# ---------------------------------------------------------------------------------------------------
+_FORMATS = {"ILDG": L.IO_ILDG, "BridgeText": L.IO_BRIDGETEXT}
+
+
+def _io_call(name, path, fmt, dims, nc, arr):
+    lib = L.load()
+    ptrs = (C.c_void_p * 4)(*[arr[mu].ctypes.data for mu in range(4)])
+    st = getattr(lib, name)(str(path).encode(), _FORMATS[fmt], (C.c_int * 4)(*dims), nc, ptrs, 0)
+    L.check(None, st)
+
+
+def load_gaugefield(path, dims, loadU_format="ILDG", NC=3, **ctx_args) -> Gaugefields:
+    """`initial = path`, loadU_format in {"ILDG", "BridgeText"} (universe.jl:62-68: ILDG(filename) + load_gaugefield!, load_BridgeText!)
+    into host link arrays (no GPU needed).  dims = (NX, NY, NZ, NT)."""
+    NX, NY, NZ, NT = dims
+    data = np.zeros((4, NT, NZ, NY, NX, NC, NC), dtype=np.complex128)
+    _io_call("lqcd_io_read_gauge", path, loadU_format, dims, NC, data)
+    if NC != 3:
+        return data
+    return Gaugefields(data, dims, ctx_args)
+
+
+def load_BridgeText_(path, U: Gaugefields):
+    """load_BridgeText!(filename, U, L, NC) (universe.jl:66-68): overwrite U with the configuration in the file"""
+    _io_call("lqcd_io_read_gauge", path, "BridgeText", U.dims, 3, U.data)
+    return U
+
+
+def save_binarydata(U, path):
+    """save_binarydata(U, filename) (lqcd.jl:239): ILDG.  U: Gaugefields or a raw [4,NT,NZ,NY,NX,NC,NC] array"""
+    data = U.data if isinstance(U, Gaugefields) else np.ascontiguousarray(U, dtype=np.complex128)
+    _, NT, NZ, NY, NX, NC, _ = data.shape
+    _io_call("lqcd_io_write_gauge", path, "ILDG", (NX, NY, NZ, NT), NC, data)
+
+
+def save_textdata(U, path):
+    """save_textdata(U, filename) (lqcd.jl:242): Bridge++ text"""
+    data = U.data if isinstance(U, Gaugefields) else np.ascontiguousarray(U, dtype=np.complex128)
+    _, NT, NZ, NY, NX, NC, _ = data.shape
+    _io_call("lqcd_io_write_gauge", path, "BridgeText", (NX, NY, NZ, NT), NC, data)
+
+
+def plaquette(ctx: Context) -> float:
+    """average plaquette Re tr U_p / NC of the device links (what the reference prints every trajectory, lqcd.jl:186-192)"""
+    out = C.c_double()
+    ctx.call("lqcd_gauge_plaquette", C.byref(out))
+    return out.value
+
+
+def load_gaugefield_device_(ctx: Context, path, loadU_format="ILDG"):
+    """file -> device links of this rank's block (lqcd_gauge_load): nothing passes through host link arrays"""
+    ctx.call("lqcd_gauge_load", str(path).encode(), _FORMATS[loadU_format])
+
+
+def save_gaugefield_device(ctx: Context, path, saveU_format="ILDG"):
+    """device links -> file (lqcd_gauge_save).  Across ranks (ILDG): the rank owning the lattice origin creates the file first"""
+    fmt = _FORMATS[saveU_format]
+    if ctx.dist is None:
+        ctx.call("lqcd_gauge_save", str(path).encode(), fmt)
+        return
+    first = all(o == 0 for o in ctx.origin)
+    if first:
+        ctx.call("lqcd_gauge_save", str(path).encode(), fmt)
+    ctx.barrier()
+    if not first:
+        ctx.call("lqcd_gauge_save", str(path).encode(), fmt)
+    ctx.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------
 # pseudofermion fields (device resident)
 # ---------------------------------------------------------------------------------------------------
 class FermionField:

@@ -48,14 +48,14 @@ def test_translation_rejects_unknown_constructs():
 
 def test_gpu_suite_under_emulation(emu_lib):
     """every single-rank `-m gpu` test, xfail markers ignored (--runxfail): the not-yet-on-hardware kernels must pass here"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
            "--runxfail", "-p", "no:cacheprovider",
            "--deselect", "tests/test_gpu_parity.py::test_16_4_size_independent_properties"]      # 2 min under emulation
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib), capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 108, tail
+    assert m and int(m.group(1)) >= 114, tail
 
 
 @pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),
@@ -105,6 +105,14 @@ def test_multirank_md_trajectory_under_emulation(emu_lib, action):
            "--master-port", str(35500 + (os.getpid() % 2000)), "tests/mp_md_worker.py", "4x4x4x4", "1x1x2x2", action]
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_multirank_gauge_io_under_emulation(emu_lib):
+    """file <-> device links across 4 ranks: block-wise load of ILDG / BridgeText, multi-rank plaquette, collective ILDG save"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", str(37500 + (os.getpid() % 2000)), "tests/mp_io_worker.py", "4x4x8x4", "1x1x2x2"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and "ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_bench_experiments_leg_under_emulation(emu_lib, monkeypatch):

@@ -109,3 +109,12 @@ def test_multirank_md_trajectory(dims, pg, action):
     res = run_ranks(n, ROOT / "tests" / "mp_md_worker.py", dims, pg, action, timeout=900)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="multi-rank gauge file I/O (lqcd_gauge_load / _save): verified under tests/emu only, not yet run on hardware", strict=False)
+def test_multirank_gauge_io():
+    """every rank loads only its block of a global ILDG / BridgeText file; collective ILDG save is byte-identical (tests/mp_io_worker.py)"""
+    res = run_ranks(2, ROOT / "tests" / "mp_io_worker.py", "8x8x8x8", "1x1x1x2", timeout=600)
+    sys.stdout.write(res.stdout[-2000:])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
