@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--probe-pipe", action="store_true", help=argparse.SUPPRESS)   # child process of probe_pipe_isolated()
     ap.add_argument("--experiment", default=None, help=argparse.SUPPRESS)          # child process of run_experiments()
+    ap.add_argument("--experiment-multi", default=None, help=argparse.SUPPRESS)    # child process of run_experiments_multi()
     return ap.parse_args()
 
 
@@ -421,6 +422,111 @@ def run_experiments(lattice, local_rank, budget_s):
     return results
 
 
+# N > 1: the multi-GPU knobs that were prepared for the strong-scaling gap but never timed.  Every rank
+# of the job spawns ONE child with its own RANK / LOCAL_RANK; the children of one experiment form their own process group (gloo,
+# host plumbing only) on a different port, create contexts, connect over CUDA IPC and time the Dslash and a CG with the knob set
+# in their environment.  The parents only wait.  Same isolation argument as above.
+EXPERIMENTS_MULTI = {
+    "default": ({}, "defaults (reference for the rows below)"),
+    "halo_poll_relaxed": ({"LQCD_HALO_POLL": "relaxed"}, "face CTAs poll the halo flags with ld.relaxed.sys instead of ld.acquire.sys"),
+    "pack_fence_gpu": ({"LQCD_PACK_FENCE": "g"}, "gpu-scope fence per pack CTA, one system fence by the last"),
+    "persist": ({"LQCD_PERSIST": "1"}, "persistent CTAs drawing pack / interior / face tiles from one queue"),
+    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream instead of leading CTAs"),
+    "relaxed_and_persist": ({"LQCD_HALO_POLL": "relaxed", "LQCD_PERSIST": "1"}, "both"),
+}
+
+
+def experiment_multi_child(name, dims):
+    import numpy as np
+    import torch.distributed as dist
+    import lqcd_b200 as q
+    from lqcd_b200 import _lib as L
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    pg = choose_procgrid(world)
+    if os.environ.get("LQCD_PROCGRID"):
+        pg = tuple(int(v) for v in os.environ["LQCD_PROCGRID"].split(","))
+    ctx = q.get_context(dims, procgrid=pg, rank=rank, device=dev)
+    q.connect_ranks(ctx, dist)
+    ctx.call("lqcd_gauge_random", 111, 0.3)
+    op = L.LqcdOp()
+    op.kind, op.kappa, op.r = L.WILSON, KAPPA, 1.0
+    for i, b in enumerate(BC):
+        op.bc[i] = b
+    x, y, sol = q.FermionField(ctx, L.WILSON), q.FermionField(ctx, L.WILSON), q.FermionField(ctx, L.WILSON)
+    q.gauss_distribution_fermion_(x, 112)
+    mean, mn = C.c_double(), C.c_double()
+    ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, 5, 0, C.byref(mean), C.byref(mn))
+    dist.barrier()
+    reps, cg_it = int(os.environ.get("LQCD_EXP_REPS", "100")), int(os.environ.get("LQCD_EXP_CG", "200"))      # (tests shrink them)
+    ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
+    ms = mean.value
+    norm_y = q.dot(y, y).real                          # global |D x|^2: must not depend on the knob
+    it, rs = C.c_int(0), C.c_double(0.0)
+
+    def cg(maxit):
+        q.clear_fermion_(sol)
+        st = ctx.lib.lqcd_solve(ctx.h, C.byref(op), sol.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 0.0, maxit, C.byref(it), C.byref(rs), None)
+        assert st in (L.LQCD_OK, L.ERR_NOCONV), ctx.lib.lqcd_last_error(ctx.h)
+    cg(10)
+    dist.barrier()
+    t0 = time.perf_counter()
+    cg(cg_it)
+    ctx.synchronize()
+    cg_s = time.perf_counter() - t0
+    import torch
+    t = torch.tensor([ms, cg_s], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        V = int(np.prod(dims))
+        out = {"name": name, "ok": True, "n_gpus": world, "procgrid": list(pg), "ms_per_apply": float(t[0]), "GFLOP/s": FLOP_PER_SITE * V / float(t[0]) / 1e6,
+               "cg_iters_per_s": it.value / float(t[1]), "norm_Dx_sq": norm_y, "cg_iters": it.value, "resid_sq": rs.value}
+        print("EXPERIMENT " + json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_experiments_multi(lattice, rank, local_rank, world, budget_s, barrier):
+    """called by EVERY rank of the job (collective): returns {name: result} on rank 0, None elsewhere"""
+    results = {}
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    t_start = time.perf_counter()
+    for idx, (name, (env_extra, what)) in enumerate(EXPERIMENTS_MULTI.items()):
+        barrier()                                       # all parents decide together (rank 0's clock is not shared: fixed schedule)
+        if (idx + 1) * 40 > budget_s:
+            results[name] = {"skipped": "time budget of the experiments leg", "what": what}
+            continue
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(base_port + 101 + idx), **env_extra)
+        for k in ("TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE", "ROLE_WORLD_SIZE", "TORCHELASTIC_RESTART_COUNT",
+                  "TORCHELASTIC_MAX_RESTARTS", "TORCHELASTIC_USE_AGENT_STORE", "TORCH_NCCL_ASYNC_ERROR_HANDLING"):
+            env.pop(k, None)
+        res = {"ok": False}
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--experiment-multi", name, "--lattice", lattice], env=env,
+                               capture_output=True, text=True, timeout=75)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("EXPERIMENT ")]
+            if line:
+                res = json.loads(line[-1][len("EXPERIMENT "):])
+            elif rank == 0:
+                tail = (r.stdout + r.stderr).strip().splitlines()[-1:] or [""]
+                res["error"] = f"exit {r.returncode}: {tail[0][:200]}"
+        except subprocess.TimeoutExpired:
+            res["error"] = "timed out"
+        except Exception as exc:
+            res["error"] = repr(exc)
+        res["what"] = what
+        results[name] = res
+    barrier()
+    ref = results.get("default", {}).get("norm_Dx_sq")
+    for v in results.values():
+        if ref and "norm_Dx_sq" in v:
+            v["ok"] = bool(abs(v["norm_Dx_sq"] - ref) <= 1e-12 * abs(ref))
+    results["wall_s"] = time.perf_counter() - t_start
+    return results if rank == 0 else None
+
+
 def choose_procgrid(n):
     # T first, then Z (north_star): keep T_local >= 8 where possible
     return {1: (1, 1, 1, 1), 2: (1, 1, 1, 2), 4: (1, 1, 1, 4), 8: (1, 1, 2, 4)}[n]
@@ -625,6 +731,12 @@ def run_b200(args, dims):
         except Exception as exc:
             experiments = {"error": repr(exc)}
 
+    if world > 1 and os.environ.get("LQCD_BENCH_EXPERIMENTS", "1") != "0":
+        try:
+            experiments = run_experiments_multi(args.lattice, rank, local_rank, world, float(os.environ.get("LQCD_BENCH_EXPERIMENTS_S", "240")), barrier)
+        except Exception as exc:
+            experiments = {"error": repr(exc)}
+
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -654,7 +766,9 @@ def run_b200(args, dims):
 def main():
     args = parse_args()
     dims = tuple(int(v) for v in args.lattice.split("x"))
-    if args.experiment:
+    if args.experiment_multi:
+        experiment_multi_child(args.experiment_multi, dims)
+    elif args.experiment:
         experiment_child(args.experiment, dims)
     elif args.probe_pipe:
         probe_pipe_child(dims)

@@ -128,3 +128,22 @@ def test_bench_experiments_leg_under_emulation(emu_lib, monkeypatch):
     assert not bad, bad
     assert res["mrhs_r3"]["bit_identical_to_single_rhs"] and res["staggered_mrhs"]["bit_identical_to_single_rhs"]
     assert res["wilson_kernel3"]["max_rel_dev_vs_default"] < 1e-13
+
+
+def test_bench_multirank_experiments_leg_under_emulation(emu_lib):
+    """bench.py's N > 1 experiments leg: every rank spawns one child per knob setting, the children form their own process group,
+    connect over (emulated) CUDA IPC and time Dslash / CG; the knob must not change |D x|^2 or the CG residual"""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(38500 + (os.getpid() % 1000)), "tests/mp_bench_exp_worker.py", "4x4x4x8"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120", LQCD_EXP_REPS="3", LQCD_EXP_CG="10"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULTS ")][-1]
+    res = json.loads(line[len("RESULTS "):])
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert set(bench.EXPERIMENTS_MULTI) <= set(res)
+    for name in bench.EXPERIMENTS_MULTI:
+        assert res[name].get("ok"), (name, res[name])
+        assert res[name]["resid_sq"] == res["default"]["resid_sq"] and res[name]["cg_iters"] == 10
