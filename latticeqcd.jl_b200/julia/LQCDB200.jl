@@ -209,7 +209,18 @@ even_only(fa::B200FermiAction) = fa.D.op.kind == STAGGERED && get(fa.parameters_
 "gauss_sampling_in_action!(xi, U, fa) -- src/md/standardMD.jl:95 (host RNG stays the reference's, seeded by Random.seed!, lqcd.jl:61)"
 function gauss_sampling_in_action!(ξ, U, fa::B200FermiAction)
     LatticeDiracOperators.gauss_distribution_fermion!(ξ)                                                        # [UPSTREAM-RECALL]
-    even_only(fa) && LatticeDiracOperators.clear_fermion!(ξ, false)                                             # [UPSTREAM-RECALL] evensite = false
+    if even_only(fa)
+        # eta = P_even D^dag xi0 has the right heat-bath covariance (D^dag D)_ee only for xi0 on ALL sites, but is then a projection:
+        # hand back xi = D (D^dag D)^-1 eta, for which P_even D^dag xi = eta and dot(xi, xi) (Sfold, standardHMC.jl:54) equals
+        # eta^dag (D^dag D)^-1 eta, so the reference's update! stays exact (see lqcd_b200/api.py FermiActionB200)
+        D = fa.D(U)
+        η0, X = fa._temporary_fermionfields[3], fa._temporary_fermionfields[1]
+        mul!(η0, adjoint(D), ξ); LatticeDiracOperators.clear_fermion!(η0, false)                                # [UPSTREAM-RECALL] evensite = false
+        LatticeDiracOperators.clear_fermion!(X)
+        solve_DinvX!(X, DdagD(D), η0)
+        mul!(ξ, D, X)
+    end
+    return ξ
 end
 "sample_pseudofermions!(eta, U, fa, xi): eta = D^dag xi -- src/md/standardMD.jl:96"
 function sample_pseudofermions!(η, U, fa::B200FermiAction, ξ)

@@ -524,9 +524,15 @@ class FermiActionB200:
     def __init__(self, D: DiracOperator, parameters_action: dict):
         self.D = D
         self.Nf = parameters_action.get("Nf", None)
-        # staggered Nf = 4 (UPSTREAM-RECALL, unverified): pseudofermions live on even sites only, odd
-        # sites are zeroed after the Gaussian sampling and after D^dag.  Kept behind this flag so that a different
-        # upstream convention is a one-line change; with it off the action is the 8-taste one.
+        # staggered Nf = 4 (UPSTREAM-RECALL, unverified): the pseudofermion eta lives on even sites only.
+        # D^dag D = m^2 - Dh^2 does not couple the parities, so eta_e^dag (D^dag D)_ee^-1 eta_e describes half the tastes.
+        # Heat bath: xi0 Gaussian on ALL sites, eta = P_even D^dag xi0  =>  <eta eta^dag> = m^2 + D_eo D_eo^dag = (D^dag D)_ee, the
+        # distribution the action needs (zeroing the odd sites of xi0 as well would give <eta eta^dag> = m^2, a wrong heat bath).
+        # But eta <- xi0 is a projection, so xi0^dag xi0 is NOT the initial action that update! takes as Sfold = dot(xi, xi)
+        # (standardHMC.jl:54).  gauss_sampling_in_action_ therefore hands back xi = D X with X = (D^dag D)^-1 eta (one CG): then
+        # P_even D^dag xi = eta and xi^dag xi = eta^dag (D^dag D)^-1 eta exactly, and the reference's update! sequence stays exact
+        # (tests/test_reference_regressions.py: dH = O(dtau^2), not the -O(V) offset of the naive shortcut).
+        # Kept behind this flag; with it off the action is the 8-taste one.
         self.even_only = bool(D.kind == L.STAGGERED and self.Nf == 4 and parameters_action.get("even_site_pseudofermions", True))
         self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]   # standardMD.jl:50
         self.last = {}
@@ -576,10 +582,20 @@ def FermiAction(D, parameters_action):
     return FermiActionB200(D, parameters_action)
 
 
-def gauss_sampling_in_action_(xi: FermionField, U, fa, seed=112):     # standardMD.jl:95
+def _even_site_xi_(fa, D, xi: FermionField):
+    """xi <- D (D^dag D)^-1 P_even D^dag xi (see FermiActionB200): afterwards eta = P_even D^dag xi and xi^dag xi = S_f(eta)"""
+    X, eta = fa._temporary_fermionfields[0], fa._temporary_fermionfields[3]
+    mul_(eta, adjoint(D), xi)
+    mask_parity_(eta, 0)
+    clear_fermion_(X)
+    fa.last = solve_DinvX_(X, DdagD(D), eta)
+    mul_(xi, D, X)
+
+
+def gauss_sampling_in_action_(xi: FermionField, U, fa, seed=112, _bound=False):     # standardMD.jl:95
     gauss_distribution_fermion_(xi, seed)
     if fa.even_only:
-        mask_parity_(xi, 0)
+        _even_site_xi_(fa, fa.D if _bound else fa.D(U), xi)
 
 
 def sample_pseudofermions_(eta: FermionField, U, fa, xi: FermionField):   # standardMD.jl:96
@@ -727,7 +743,7 @@ def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=
     eta = None
     if fa is not None:
         xi, eta = fa._temporary_fermionfields[1], fa._temporary_fermionfields[2]
-        gauss_sampling_in_action_(xi, U, fa, seed=int(rng.integers(1 << 62)))
+        gauss_sampling_in_action_(xi, U, fa, seed=int(rng.integers(1 << 62)), _bound=True)    # D is bound to U already
         if is_rhmc:
             fa.rational_apply_(eta, fa.rhmc.r_heatbath, xi)           # eta = (D^dag D)^{Nf/16} xi
         else:

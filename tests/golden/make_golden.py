@@ -23,6 +23,7 @@ FIX = {
     "wilson_4444": ("confs_HMC_L04040404_beta5.7_Wilson_kappa0.141139", (4, 4, 4, 4), 0.565800226845),
     "staggered_4444": ("confs_HMC_L04040404_beta5.7_Staggered_mass0.5", (4, 4, 4, 4), 0.575584039475),
     "staggered_nf2_4444": ("confs_HMC_L04040404_beta5.7_Staggered_mass0.5_Nf2", (4, 4, 4, 4), 0.566501729368),
+    "staggered_nf3_4444": ("confs_HMC_L04040404_beta5.7_Staggered_mass0.5_Nf3", (4, 4, 4, 4), 0.570837085972),
     "quenched_su3_4444": ("confs_HMC_L04040404_beta5.7_quenched_su3", (4, 4, 4, 4), 0.568215750149),
 }
 out = {}

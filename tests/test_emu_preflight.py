@@ -48,14 +48,14 @@ def test_translation_rejects_unknown_constructs():
 
 def test_gpu_suite_under_emulation(emu_lib):
     """every single-rank `-m gpu` test, xfail markers ignored (--runxfail): the not-yet-on-hardware kernels must pass here"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
-           "--runxfail", "-p", "no:cacheprovider",
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_reference_regressions.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
+           "--runxfail", "-p", "no:cacheprovider", "-n", "4",
            "--deselect", "tests/test_gpu_parity.py::test_16_4_size_independent_properties"]      # 2 min under emulation
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib), capture_output=True, text=True, timeout=1500)
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_TEST_NTRAJ="2", OMP_NUM_THREADS="1"), capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 114, tail
+    assert m and int(m.group(1)) >= 119, tail
 
 
 @pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),
