@@ -2,6 +2,12 @@
 # Round-2 opening experiment battery (run under gpurun; 1 GPU unless noted).  Each block is independent.
 set -x
 mkdir -p gpurun_out
+# 1. every GPU test incl. the staged ones as plain tests (a device fault in one must not hide the rest: one process per file)
+for f in tests/test_gpu_parity.py tests/test_rhmc.py tests/test_md.py tests/test_gauge_io.py tests/test_reference_regressions.py tests/test_zz_gpu_unverified.py tests/test_multirank.py; do
+  timeout 900 python -m pytest $f -m gpu -q -rA --runxfail -p no:cacheprovider 2>&1 | tail -80 > gpurun_out/tests_$(basename $f .py).txt
+done
+# 2. headline bench with the experiments leg (first timings of kernel 3, persistent CTAs, multi-RHS R = 2 / 3 / 4, clover, even-odd, MD)
+LQCD_BENCH_EXPERIMENTS_S=400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_with_experiments.json 2> gpurun_out/bench_with_experiments.err
 python tools/check_kernel3.py 2>&1 | tee gpurun_out/kernel3.txt                       # experimental t-march kernel
 for c in 1 2 4 8; do LQCD_WILSON_KERNEL=3 LQCD_K3_CHUNKS=$c python tools/quick_bench.py 32x32x32x32 2>&1 | grep wilson | sed "s/^/k3 chunks=$c /"; done | tee gpurun_out/kernel3_chunks.txt
 for lat in 32x32x32x32 32x32x16x8; do for cfg in "A=1" "LQCD_PERSIST=1"; do echo -n "$lat $cfg: "; env $cfg python tools/quick_bench.py $lat 2>&1 | grep wilson; done; done | tee gpurun_out/persist_n1.txt
