@@ -98,6 +98,7 @@ int lqcd_fermion_download(lqcd_ctx *ctx, const lqcd_fermion *f, double *host, in
 int lqcd_fermion_zero(lqcd_ctx *ctx, lqcd_fermion *f);                               /* clear_fermion! */
 int lqcd_fermion_copy(lqcd_ctx *ctx, lqcd_fermion *dst, const lqcd_fermion *src);    /* substitute_fermion! */
 int lqcd_fermion_gaussian(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t seed);            /* gauss_distribution_fermion!, sigma^2=1/2 */
+int lqcd_fermion_z4(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t seed);                  /* Z4_distribution_fermi! (measure_chiral_condensate.jl:181) */
 int lqcd_fermion_point_source(lqcd_ctx *ctx, lqcd_fermion *f, const int site[4], int color, int spin);
 /* zero the sites of the other parity: keep (x+y+z+t) % 2 == parity (global coordinates).  Staggered Nf = 4 keeps its
  * pseudofermions on even sites only (D^dag D does not mix parities, so solves stay on that parity). */

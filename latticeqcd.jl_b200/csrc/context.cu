@@ -510,6 +510,28 @@ extern "C" int lqcd_fermion_gaussian(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t se
     return LQCD_OK;
 }
 
+// Z4_distribution_fermi!(x) (measure_chiral_condensate.jl:181): every component one of 1, i, -1, -i with equal probability --
+// the noise sources of the stochastic trace.  Counter-based like the Gaussian field: the same on any process grid.
+__global__ void fermion_z4_kernel(cplx *f, Geom g, int ncomp, uint64_t seed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.V * ncomp) return;
+    const int lane = idx & 31, k = (idx >> 5) % ncomp, blk = (idx >> 5) / ncomp;
+    const uint64_t gs = (uint64_t)global_site(g, blk * 32 + lane);
+    const unsigned q = (unsigned)(splitmix64(seed ^ splitmix64(gs * ncomp + k)) >> 62);      // top two bits
+    f[idx] = make_double2(q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0), q == 1 ? 1.0 : (q == 3 ? -1.0 : 0.0));
+}
+
+extern "C" int lqcd_fermion_z4(lqcd_ctx *ctx, lqcd_fermion *f, uint64_t seed) {
+    LQCD_TRY(check_f(ctx, f));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int n = ctx->g.V * f->ncomp, bs = 256;
+    fermion_z4_kernel<<<(n + bs - 1) / bs, bs, 0, ctx->stream>>>(f->d, ctx->g, f->ncomp, seed);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LQCD_OK;
+}
+
 __global__ void fermion_mask_parity_kernel(cplx *f, Geom g, int ncomp, int parity) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // same indexing as fermion_gaussian_kernel
     if (idx >= g.V * ncomp) return;

@@ -195,6 +195,26 @@ function mul!(ys::Vector{<:AbstractFermionfields}, D::B200Dirac, xs::Vector{<:Ab
     return ys
 end
 
+"""
+    measure_chiral_condensate_b200(D, r_template; Nr=10, factor=1.0)
+
+The Nr noise solves of measure(::Chiral_condensate_measurement) (measure_chiral_condensate.jl:164-204) as one batched solve:
+pbp = real(sum_ir dot(r_ir, D^-1 r_ir) / Nr) / NV * factor with Z4 noise r_ir (the reference's Z4_distribution_fermi!, host RNG).
+"""
+function measure_chiral_condensate_b200(D::B200Dirac, r_template; Nr=10, factor=1.0)
+    rs = [similar(r_template) for _ = 1:Nr]; ps = [similar(r_template) for _ = 1:Nr]
+    for ir = 1:Nr
+        LatticeDiracOperators.clear_fermion!(ps[ir])
+        LatticeDiracOperators.Z4_distribution_fermi!(rs[ir])                                                    # [UPSTREAM-RECALL]
+    end
+    for j = 1:16:Nr
+        k = min(j + 15, Nr)
+        solve_DinvX!(ps[j:k], D, rs[j:k])
+    end
+    NV = prod(D.ctx.dims)
+    return real(sum(dot(rs[ir], ps[ir]) for ir = 1:Nr) / Nr) / NV * factor
+end
+
 # ---- fermion action (Wilson two-flavour / staggered Nf=8 form; RHMC fractions go through lqcd_multishift_cg) ----
 struct B200FermiAction
     D::B200Dirac{:D}

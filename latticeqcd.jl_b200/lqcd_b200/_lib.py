@@ -63,6 +63,7 @@ SIGNATURES = {
     "lqcd_fermion_zero": (i32, [vp, vp]),
     "lqcd_fermion_copy": (i32, [vp, vp, vp]),
     "lqcd_fermion_gaussian": (i32, [vp, vp, u64]),
+    "lqcd_fermion_z4": (i32, [vp, vp, u64]),
     "lqcd_fermion_point_source": (i32, [vp, vp, pi32, i32, i32]),
     "lqcd_fermion_mask_parity": (i32, [vp, vp, i32]),
     "lqcd_blas_axpy": (i32, [vp, dbl, dbl, vp, vp]),

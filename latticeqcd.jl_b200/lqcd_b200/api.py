@@ -313,6 +313,10 @@ def gauss_distribution_fermion_(x: FermionField, seed=112):
     x.ctx.call("lqcd_fermion_gaussian", x.h, int(seed))
 
 
+def Z4_distribution_fermi_(x: FermionField, seed=114):              # measure_chiral_condensate.jl:181
+    x.ctx.call("lqcd_fermion_z4", x.h, int(seed))
+
+
 def dot(a: FermionField, b: FermionField) -> complex:               # standardHMC.jl:54
     out = (C.c_double * 2)()
     a.ctx.call("lqcd_blas_dot", a.h, b.h, out)
@@ -500,6 +504,27 @@ def calc_quark_propagators_point_source(D: DiracOperator, origin=(0, 0, 0, 0)):
         clear_fermion_(ps[i])
     infos = solve_DinvX_multi_(ps, D, bs)
     return ps, infos
+
+
+def measure_chiral_condensate(D: DiracOperator, Nr=10, factor=1.0, seed=114, batched=True):
+    """measure(m::Chiral_condensate_measurement, itrj, U) (measure_chiral_condensate.jl:164-204): for ir = 1:Nr { clear_fermion!(p);
+    Z4_distribution_fermi!(r); solve_DinvX!(p, D, r); pbp += dot(r, p) }, pbp_value = real(pbp / Nr) / NV * factor.  batched: the Nr
+    solves advance in lock step (lqcd_solve_multi); False: one solve_DinvX_ after the other like the reference.  Returns
+    (pbp_value, per-source values, noise fields)."""
+    rs = [FermionField(D.ctx, D.kind) for _ in range(Nr)]
+    ps = [FermionField(D.ctx, D.kind) for _ in range(Nr)]
+    for ir, (r, p) in enumerate(zip(rs, ps)):
+        Z4_distribution_fermi_(r, seed + ir)
+        clear_fermion_(p)
+    if batched:
+        for j in range(0, Nr, 16):
+            solve_DinvX_multi_(ps[j:j + 16], D, rs[j:j + 16])
+    else:
+        for r, p in zip(rs, ps):
+            solve_DinvX_(p, D, r)
+    NV = int(np.prod(D.ctx.dims))                                   # U[1].NV: the global volume
+    vals = [dot(r, p) for r, p in zip(rs, ps)]
+    return float(np.real(sum(vals) / Nr) / NV * factor), vals, rs
 
 
 def shiftedcg_(ys, D: DiracOperator, x: FermionField, shifts, eps=None, maxsteps=None):

@@ -287,3 +287,30 @@ def test_point_source_propagators(golden_dir, kind):
         assert np.abs(props[i].to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
         q.mul_(y, D, props[i])
         assert np.abs(y.to_host() - b).max() < 1e-8
+
+
+@pytest.mark.parametrize("kind", [orc.STAGGERED, orc.WILSON])
+def test_chiral_condensate_batched(golden_dir, kind):
+    """measure(::Chiral_condensate_measurement) (measure_chiral_condensate.jl:164-204) on the reference's fixtures: Z4 noise on the
+    device, the Nr solves in lock step == one after the other (bit for bit, CGNR), and == the oracle's CGNR on the same noise"""
+    import lqcd_b200 as q
+    dims = (4, 4, 4, 4)
+    Uh = np.load(golden_dir / ("wilson_4444.npy" if kind == orc.WILSON else "staggered_4444.npy"))
+    U = q.gaugefields_from_array(Uh)
+    name = "Wilson" if kind == orc.WILSON else "staggered"
+    x = q.Initialize_pseudofermion_fields(U[0], name)
+    D = q.Dirac_operator(U, x, {"Dirac_operator": name, "κ": 0.141139, "mass": 0.5, "boundarycondition": [1, 1, 1, -1],
+                                "eps_CG": 1e-19, "MaxCGstep": 3000})
+    op = orc.make_op(dims, kappa=0.141139, mass=0.5)
+    Nr = 10                                                      # the reference's default number of noise vectors
+    pbp, vals, rs = q.measure_chiral_condensate(D, Nr=Nr, factor=1.0, seed=31)
+    pbp1, vals1, rs1 = q.measure_chiral_condensate(D, Nr=Nr, factor=1.0, seed=31, batched=False)
+    assert pbp == pbp1 and vals == vals1
+    noise = np.stack([r.to_host() for r in rs])
+    assert np.all(np.isin(noise, [1, -1, 1j, -1j]))
+    counts = [np.sum(noise == v) for v in (1, 1j, -1, -1j)]
+    assert min(counts) > 0.2 * noise.size and len({r.to_host().tobytes() for r in rs}) == Nr        # uniform, sources differ
+    ref = [np.vdot(r, orc.cgnr(op, kind, Uh, r, eps=1e-19)["x"]) for r in noise]
+    want = np.real(sum(ref) / Nr) / 256
+    assert abs(pbp - want) < 1e-10 * abs(want)
+    assert want > 0.0                                            # Re tr D^-1 > 0 for these operators
