@@ -147,3 +147,23 @@ def test_bench_multirank_experiments_leg_under_emulation(emu_lib):
     for name in bench.EXPERIMENTS_MULTI:
         assert res[name].get("ok"), (name, res[name])
         assert res[name]["resid_sq"] == res["default"]["resid_sq"] and res[name]["cg_iters"] == 10
+
+
+def test_bench_headline_path_under_emulation(emu_lib):
+    """bench.py's run_b200 end to end (tests/bench_emu_harness.py: torch.cuda / cudart events stubbed, emulated library, tiny
+    lattice): one JSON line with every key of the contract, the pipelined host call selected through its isolated probe, all
+    experiments ok"""
+    import json
+    r = subprocess.run([sys.executable, "tests/bench_emu_harness.py", "--lattice", "8x4x4x4", "--steps", "3", "--warmup", "1", "--cg-iters", "5"],
+                       cwd=ROOT, env=_env(emu_lib, LQCD_EXP_SMALL="4x4x4x4"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines                                    # stdout carries exactly ONE JSON line
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["gpu_launches"] == 3 and d["roofline"]["bound"] == "hbm" and d["cpu_baseline"]["kind"] == "port"
+    assert "lqcd_dslash_host" in d["e2e"]["call"] and "note" not in d["e2e"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * 4 * 4 * 4 * 12 * 16
+    assert all(v.get("ok") for v in d["experiments"].values()), d["experiments"]
