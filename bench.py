@@ -256,6 +256,7 @@ EXPERIMENTS = {
     "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides per pass"),
     "clover": ({}, "Wilson-clover Dslash (csw = 1.5612)"),
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
+    "staggered_even": ({}, "staggered CG on an even-site source: half-field solver vs full-lattice solver"),
     "md": ({}, "device-resident Sexton-Weingarten trajectory with Wilson pseudofermions, 16^4"),
 }
 
@@ -359,6 +360,23 @@ def experiment_child(name, dims):
         out["ok"] = dev_rel < 1e-6
         out.update({"solution_rel_dev": dev_rel, "full": {k: v for k, v in res["lqcd_solve"].items() if k != "sol"},
                     "evenodd": {k: v for k, v in res["lqcd_solve_eo"].items() if k != "sol"}})
+    elif name == "staggered_even":
+        ctx, op, x, y = setup(dims, kind=L.STAGGERED, eps=0.3)
+        ctx.call("lqcd_fermion_mask_parity", x.h, 0)
+        it, rs = C.c_int(0), C.c_double(0.0)
+        res = {}
+        for key in ("full", "half"):
+            q.clear_fermion_(y)
+            t0 = time.perf_counter()
+            if key == "full":
+                ctx.call("lqcd_solve", C.byref(op), y.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 1e-12, 3000, C.byref(it), C.byref(rs), None)
+            else:
+                ctx.call("lqcd_solve_staggered_even", C.byref(op), y.h, x.h, 1e-12, 3000, C.byref(it), C.byref(rs))
+            res[key] = {"iters": it.value, "resid_sq": rs.value, "wall_ms": (time.perf_counter() - t0) * 1e3, "sol": y.to_host()}
+        dev_rel = float(np.abs(res["full"]["sol"] - res["half"]["sol"]).max() / np.abs(res["full"]["sol"]).max())
+        out["ok"] = dev_rel < 1e-8 and abs(res["full"]["iters"] - res["half"]["iters"]) <= 1
+        out.update({"solution_rel_dev": dev_rel, "full": {k: v for k, v in res["full"].items() if k != "sol"},
+                    "half": {k: v for k, v in res["half"].items() if k != "sol"}})
     elif name == "md":
         ctx, op, x, y = setup(small, eps=0.3)
         its = C.c_longlong(0)

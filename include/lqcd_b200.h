@@ -155,6 +155,18 @@ int lqcd_solve_eo(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_
 int lqcd_dslash_host(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, lqcd_fermion *x, double *y_host, const double *x_host,
                      int mode, int ndw);
 
+/* ---- staggered even-site systems on half fields (csrc/staggered_eo.cu) ------------------------------------------------------------
+ *      Staggered Nf = 4 (the reference's default staggered setup, test/test_staggered.toml) keeps its pseudofermion on even sites;
+ *      DdagD = m^2 - Dh^2 does not couple the parities, so its solves are A_ee x_e = b_e with A_ee = m^2 - Dh_eo Dh_oe.
+ *      lqcd_solve_staggered_even      CG on A_ee over checkerboarded half fields: odd sites of b ignored, even part of y = initial
+ *                                     guess, y returns with zero odd sites.  Single rank, even extents.
+ *      lqcd_set_staggered_even_solve  scoped switch (default 0): while on, lqcd_solve(CG, DdagD) on a staggered operator -- also
+ *                                     inside lqcd_fermion_force and lqcd_md_trajectory -- takes that path; the caller guarantees
+ *                                     even-site sources. */
+int lqcd_solve_staggered_even(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const lqcd_fermion *b, double eps, int maxsteps,
+                              int *iters, double *resid_sq);
+int lqcd_set_staggered_even_solve(lqcd_ctx *ctx, int on);
+
 /* ---- gauge configurations in the reference's file formats (csrc/gauge_io.cu) ------------------------------
  *      `initial = "<file>"` + loadU_format (src/system/universe.jl:58-77: ILDG :62-65, load_BridgeText! :66-68) and saveU_format
  *      (src/system/lqcd.jl:226-247: save_binarydata "ILDG", save_textdata "BridgeText").  format: LQCD_IO_ILDG = one LIME record

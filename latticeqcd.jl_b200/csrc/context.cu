@@ -96,7 +96,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     make_tiling(g);
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false; ctx->mom = nullptr; ctx->mom_valid = false;
-    ctx->eo = nullptr; ctx->eo_active = 0; ctx->pipe = nullptr; ctx->queue = nullptr; ctx->mrhs = nullptr;
+    ctx->eo = nullptr; ctx->eo_active = 0; ctx->stag_even_solve = 0; ctx->pipe = nullptr; ctx->queue = nullptr; ctx->mrhs = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)

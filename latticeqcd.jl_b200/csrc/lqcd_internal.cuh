@@ -175,6 +175,7 @@ struct lqcd_ctx {
     struct MrhsWork *mrhs;     // per-right-hand-side solver states / reduction workspaces of the batched solves -- see mrhs.cu
     struct HostPipe *pipe;     // host-field pipeline (streams, events, two staging buffers) -- see host_pipeline.cu
     int eo_active;             // 1 while lqcd_solve_eo runs the Krylov loop: the solver's operator is Mhat on even half fields
+    int stag_even_solve;       // scoped switch (lqcd_set_staggered_even_solve): staggered CG on DdagD runs on even half fields
 };
 
 int lqcd_fail(const lqcd_ctx *ctx, int code, const char *fmt, ...);

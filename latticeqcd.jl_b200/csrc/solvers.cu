@@ -156,6 +156,8 @@ extern "C" int lqcd_solve(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, con
     if (method == LQCD_SOLVER_CG && target != LQCD_OP_DDAGD) return lqcd_fail(ctx, LQCD_ERR_ARG, "CG needs the Hermitian target DdagD");
     if (method != LQCD_SOLVER_CG && target != LQCD_OP_D && target != LQCD_OP_DDAG) return lqcd_fail(ctx, LQCD_ERR_ARG, "CGNR/BiCGStab solve D or D^dag");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->stag_even_solve && op->kind == LQCD_STAGGERED && method == LQCD_SOLVER_CG && !hist && ctx->nranks == 1)
+        return lqcd_solve_staggered_even(ctx, op, y, b, eps, maxsteps, iters, resid_sq);      // staggered_eo.cu (off unless switched on)
     return solve_impl(ctx, op, y->d, b->d, flen(ctx, y), method, target, eps, maxsteps, iters, resid_sq, hist);
 }
 

@@ -19,20 +19,12 @@
 // STATUS: compiled for sm_100a; index logic emulated on the CPU (tests/test_evenodd.py::test_checkerboard_index_emulation);
 // not yet run on hardware (tests/test_zz_gpu_unverified.py).
 #include "wilson_kernel.cuh"
+#include "eo_common.cuh"
 #include <cstring>
 
 void make_tiling(Geom &g);                                     // context.cu
 int solve_impl(lqcd_ctx *ctx, const lqcd_op *op, cplx *x, const cplx *bb, size_t n, int method, int target,
                double eps, int maxsteps, int *iters, double *resid_sq, double *hist);      // solvers.cu
-
-struct EoState {
-    Geom gh;                 // half-lattice geometry (X -> X/2), CTA tiling of its own
-    int fullX;
-    cplx *gauge[2];          // links owned by even / odd sites
-    uint64_t epoch;          // gauge epoch the split links belong to
-    cplx *f[5];              // half fields: 0 b_e, 1 b_o, 2 x_e, 3 t (hop temporary, odd), 4 bhat_e / x_o
-    size_t nhalf;            // complex numbers per Wilson half field
-};
 
 struct EoArgs {
     cplx *out;               // output half field (parity `parity`)
@@ -148,7 +140,7 @@ __global__ void eo_convert_kernel(cplx *full, cplx *he, cplx *ho, Geom g, Geom g
     }
 }
 
-static int eo_state(lqcd_ctx *ctx, EoState **out) {
+int eo_state(lqcd_ctx *ctx, EoState **out) {
     if (ctx->eo) { *out = ctx->eo; return LQCD_OK; }
     const Geom &g = ctx->g;
     if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "the even-odd solve is implemented for a single rank");
@@ -215,6 +207,7 @@ static int eo_hop(lqcd_ctx *ctx, EoState *e, const lqcd_op *op, int dagger, int 
 // y_e = Mhat x_e (dagger: Mhat^dag) with the solver's fused epilogue on the second hop; called by solvers.cu while
 // ctx->eo_active is set.  y, x: even half fields.
 int eo_mhat(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
+    if (op->kind == LQCD_STAGGERED) return stag_even_apply(ctx, op, y, x, dagger, fuse);       // staggered_eo.cu
     EoState *e = ctx->eo;
     DslashFuse plain = DslashFuse();
     plain.use_state = fuse ? fuse->use_state : 0;
@@ -222,7 +215,7 @@ int eo_mhat(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger
     return eo_hop(ctx, e, op, dagger, 0, y, e->f[3], x, -op->kappa * op->kappa, fuse);          // y_e = x_e - kappa^2 H_eo t_o
 }
 
-static int eo_convert(lqcd_ctx *ctx, EoState *e, int to_half, cplx *full, cplx *he, cplx *ho, int ncomp) {
+int eo_convert(lqcd_ctx *ctx, EoState *e, int to_half, cplx *full, cplx *he, cplx *ho, int ncomp) {
     const int bs = 128, grid = (ctx->g.V + bs - 1) / bs;
     if (to_half) eo_convert_kernel<1><<<grid, bs, 0, ctx->stream>>>(full, he, ho, ctx->g, e->gh, ncomp);
     else         eo_convert_kernel<0><<<grid, bs, 0, ctx->stream>>>(full, he, ho, ctx->g, e->gh, ncomp);

@@ -248,11 +248,23 @@ function sample_pseudofermions!(η, U, fa::B200FermiAction, ξ)
     even_only(fa) && LatticeDiracOperators.clear_fermion!(η, false)
     return η
 end
+# even-site action: its (D^dag D) solves run on checkerboarded half fields (lqcd_solve_staggered_even) while this switch is on
+function with_even_site_solves(f, fa::B200FermiAction)
+    on = even_only(fa) && get(fa.parameters_action, "half_field_solver", true)
+    on && check(fa.D.ctx.h, ccall((:lqcd_set_staggered_even_solve, LIB), Cint, (Ptr{Cvoid}, Cint), fa.D.ctx.h, 1))
+    try
+        return f()
+    finally
+        on && check(fa.D.ctx.h, ccall((:lqcd_set_staggered_even_solve, LIB), Cint, (Ptr{Cvoid}, Cint), fa.D.ctx.h, 0))
+    end
+end
 "evaluate_FermiAction(fa, U, eta) = eta^dag (D^dag D)^-1 eta -- src/updates/standardHMC.jl:69-71"
 function evaluate_FermiAction(fa::B200FermiAction, U, η)
     X = fa._temporary_fermionfields[1]
     LatticeDiracOperators.clear_fermion!(X)
-    solve_DinvX!(X, DdagD(fa.D(U)), η)
+    with_even_site_solves(fa) do
+        solve_DinvX!(X, DdagD(fa.D(U)), η)
+    end
     return real(dot(η, X))
 end
 
@@ -264,9 +276,11 @@ function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200FermiA
     outs = [pointer(UdSfdU[mu].U) for mu = 1:4]                 # temporaries from get_temp(temps, Dim), AbstractMD.jl:123
     w = hasproperty(UdSfdU[1], :NDW) ? Int(UdSfdU[1].NDW) : 0
     iters = Ref{Cint}(0); act = Ref{Cdouble}(0.0)
-    GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force, LIB), Cint,
-        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Ptr{ComplexF64}}, Cint, Ref{Cint}, Ref{Cdouble}),
-        D.ctx.h, D.op, dη.h, C_NULL, D.eps, D.maxsteps, outs, w, iters, act))
+    with_even_site_solves(fa) do
+        GC.@preserve UdSfdU check(D.ctx.h, ccall((:lqcd_fermion_force, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Ptr{ComplexF64}}, Cint, Ref{Cint}, Ref{Cdouble}),
+            D.ctx.h, D.op, dη.h, C_NULL, D.eps, D.maxsteps, outs, w, iters, act))
+    end
     return nothing
 end
 

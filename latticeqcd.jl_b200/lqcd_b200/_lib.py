@@ -76,6 +76,8 @@ SIGNATURES = {
     "lqcd_clover_term": (i32, [vp, pop, vp]),
     "lqcd_solve": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
     "lqcd_solve_eo": (i32, [vp, pop, vp, vp, i32, i32, dbl, i32, pi32, pdbl, pdbl]),
+    "lqcd_solve_staggered_even": (i32, [vp, pop, vp, vp, dbl, i32, pi32, pdbl]),
+    "lqcd_set_staggered_even_solve": (i32, [vp, i32]),
     "lqcd_multishift_cg": (i32, [vp, pop, pvp, vp, pdbl, i32, dbl, i32, pi32, pdbl]),
     "lqcd_io_read_gauge": (i32, [C.c_char_p, i32, pi32, i32, pvp, i32]),
     "lqcd_io_write_gauge": (i32, [C.c_char_p, i32, pi32, i32, pvp, i32]),

@@ -20,6 +20,7 @@ re-bound with ``D(U)``.  Pseudofermion fields are device-resident handles with e
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import weakref
 
@@ -560,6 +561,10 @@ class FermiActionB200:
         # Kept behind this flag; with it off the action is the 8-taste one.
         self.even_only = bool(D.kind == L.STAGGERED and self.Nf == 4 and parameters_action.get("even_site_pseudofermions", True))
         self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]   # standardMD.jl:50
+        # even-site action: its CG solves run on half fields unless switched off or the lattice does not qualify
+        ld = D.ctx.local_dims
+        self.half_field_solver = bool(self.even_only and parameters_action.get("half_field_solver", True)
+                                      and all(d % 2 == 0 for d in ld) and (int(np.prod(ld)) // 2) % 32 == 0)
         self.last = {}
 
 
@@ -607,13 +612,29 @@ def FermiAction(D, parameters_action):
     return FermiActionB200(D, parameters_action)
 
 
+@contextlib.contextmanager
+def _even_site_solves(fa):
+    """while an even-site (staggered Nf = 4) action solves (D^dag D) X = eta: route the CG to checkerboarded half fields
+    (lqcd_solve_staggered_even: half the sites, same iterates).  parameters_action["half_field_solver"] = False keeps the
+    full-lattice CG."""
+    on = bool(getattr(fa, "even_only", False) and getattr(fa, "half_field_solver", False) and fa.D.ctx.dist is None)
+    if on:
+        fa.D.ctx.call("lqcd_set_staggered_even_solve", 1)
+    try:
+        yield
+    finally:
+        if on:
+            fa.D.ctx.call("lqcd_set_staggered_even_solve", 0)
+
+
 def _even_site_xi_(fa, D, xi: FermionField):
     """xi <- D (D^dag D)^-1 P_even D^dag xi (see FermiActionB200): afterwards eta = P_even D^dag xi and xi^dag xi = S_f(eta)"""
     X, eta = fa._temporary_fermionfields[0], fa._temporary_fermionfields[3]
     mul_(eta, adjoint(D), xi)
     mask_parity_(eta, 0)
     clear_fermion_(X)
-    fa.last = solve_DinvX_(X, DdagD(D), eta)
+    with _even_site_solves(fa):
+        fa.last = solve_DinvX_(X, DdagD(D), eta)
     mul_(xi, D, X)
 
 
@@ -645,7 +666,8 @@ def evaluate_FermiAction(fa, U, eta: FermionField) -> float:           # standar
         return S
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
-    fa.last = solve_DinvX_(X, DdagD(D), eta)
+    with _even_site_solves(fa):
+        fa.last = solve_DinvX_(X, DdagD(D), eta)
     return dot(eta, X).real
 
 
@@ -665,7 +687,8 @@ def calc_UdSfdU_(UdSfdU: np.ndarray, fa, U, eta: FermionField):         # Abstra
     X = fa._temporary_fermionfields[0]
     clear_fermion_(X)
     it, act = C.c_int(0), C.c_double(0.0)
-    D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, 0, C.byref(it), C.byref(act))
+    with _even_site_solves(fa):
+        D.ctx.call("lqcd_fermion_force", C.byref(D.op), eta.h, X.h, D.eps, D.maxsteps, out, 0, C.byref(it), C.byref(act))
     fa.last = {"iters": it.value, "action": act.value}
     return fa.last
 
@@ -776,14 +799,16 @@ def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=
         if fa.even_only:
             mask_parity_(eta, 0)
         S_old += dot(xi, xi).real                                     # standardHMC.jl:54
-    its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw, rational=fa.rhmc.r_action if is_rhmc else None)
+    with _even_site_solves(fa):
+        its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw, rational=fa.rhmc.r_action if is_rhmc else None)
     S_new = kinetic_energy(ctx) + gauge_action(ctx, beta)
     if is_rhmc:
         S_new += fa.rational_apply_(fa._temporary_fermionfields[0], fa.rhmc.r_action, eta, want_dot=True)[1]
     elif fa is not None:
         X = fa._temporary_fermionfields[0]
         clear_fermion_(X)
-        solve_DinvX_(X, DdagD(D), eta)
+        with _even_site_solves(fa):
+            solve_DinvX_(X, DdagD(D), eta)
         S_new += dot(eta, X).real
     accept = bool(np.exp(min(0.0, S_old - S_new)) >= rng.random())    # exp(Sold - Snew) >= rand(), standardHMC.jl:79
     if accept:

@@ -314,3 +314,74 @@ def test_chiral_condensate_batched(golden_dir, kind):
     want = np.real(sum(ref) / Nr) / 256
     assert abs(pbp - want) < 1e-10 * abs(want)
     assert want > 0.0                                            # Re tr D^-1 > 0 for these operators
+
+
+# ---- staggered even-site systems on half fields (csrc/staggered_eo.cu) -----------------------------------------------------------
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (16, 4, 4, 8), (32, 4, 2, 2)])
+def test_staggered_even_site_solve_matches_full_lattice_solve(dims):
+    """lqcd_solve_staggered_even == the full-lattice CG on an even-site source: same iterates (iteration count within the rounding of
+    the reduction order), same solution, zero odd sites; initial guess honoured; == the oracle"""
+    import ctypes as C
+    import lqcd_b200 as q
+    from lqcd_b200 import _lib as L
+    Uh = orc.random_su3(dims, seed=11, eps=0.4)
+    U = q.gaugefields_from_array(Uh)
+    x = q.Initialize_pseudofermion_fields(U[0], "staggered")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "staggered", "mass": 0.3, "boundarycondition": [1, 1, 1, -1], "eps_CG": 1e-20, "MaxCGstep": 3000})
+    op = orc.make_op(dims, mass=0.3)
+    NX, NY, NZ, NT = dims
+    t, z, y, xx = np.meshgrid(np.arange(NT), np.arange(NZ), np.arange(NY), np.arange(NX), indexing="ij")
+    odd = ((t + z + y + xx) & 1) == 1
+    bh = orc.gaussian_field(dims, orc.STAGGERED, seed=12)
+    bh[odd] = 0.0
+    b = q.similar(x).from_host(bh)
+    for guess in (None, 13):
+        full, half = q.similar(x), q.similar(x)
+        g = np.zeros_like(bh)
+        if guess:
+            g = orc.gaussian_field(dims, orc.STAGGERED, seed=guess)
+            g[odd] = 0.0
+        full.from_host(g); half.from_host(g)
+        info = q.solve_DinvX_(full, q.DdagD(D), b)
+        it, rs = C.c_int(0), C.c_double(0.0)
+        D.ctx.call("lqcd_solve_staggered_even", C.byref(D.op), half.h, b.h, D.eps, D.maxsteps, C.byref(it), C.byref(rs))
+        ref = orc.cg(op, orc.STAGGERED, Uh, bh, eps=1e-20, x0=g if guess else None)
+        assert abs(it.value - info["iters"]) <= 1 and abs(it.value - ref["iters"]) <= 1, (it.value, info["iters"], ref["iters"])
+        hh = half.to_host()
+        assert np.abs(hh[odd]).max() == 0.0
+        assert np.abs(hh - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+        assert np.abs(hh - full.to_host()).max() / np.abs(hh).max() < 1e-10
+    # the scoped switch routes lqcd_solve and is off again afterwards
+    fa = q.FermiAction(D, {"Nf": 4})
+    assert fa.half_field_solver
+    launches0 = D.ctx.launch_count()
+    S_half = q.evaluate_FermiAction(fa, U, b)
+    n_half = D.ctx.launch_count() - launches0
+    fa.half_field_solver = False
+    S_full = q.evaluate_FermiAction(fa, U, b)
+    assert abs(S_half - S_full) < 1e-10 * abs(S_full) and abs(S_half - np.vdot(bh, ref["x"] if guess is None else orc.cg(op, orc.STAGGERED, Uh, bh, eps=1e-20)["x"]).real) < 1e-8 * abs(S_full)
+    assert n_half > 0
+
+
+def test_staggered_nf4_force_and_trajectory_on_half_fields(golden_dir):
+    """FermiAction(D, Nf = 4) with the half-field solver: force and a whole trajectory equal the full-lattice-solver results"""
+    import lqcd_b200 as q
+    dims = (4, 4, 4, 4)
+    Uh = np.load(golden_dir / "staggered_4444.npy")
+    res = {}
+    for half in (True, False):
+        U = q.gaugefields_from_array(Uh.copy())
+        x = q.Initialize_pseudofermion_fields(U[0], "staggered")
+        D = q.Dirac_operator(U, x, {"Dirac_operator": "staggered", "mass": 0.5, "boundarycondition": [1, 1, 1, -1], "eps_CG": 1e-22, "MaxCGstep": 3000})
+        fa = q.FermiAction(D, {"Nf": 4, "half_field_solver": half})
+        assert fa.half_field_solver == half
+        xi, eta = q.similar(x), q.similar(x)
+        q.gauss_sampling_in_action_(xi, U, fa, seed=5)
+        q.sample_pseudofermions_(eta, U, fa, xi)
+        F = np.zeros_like(Uh)
+        q.calc_UdSfdU_(F, fa, U, eta)
+        acc, dH, info = q.hmc_update_(U, 5.7, 0.025, 8, fa=fa, rng=np.random.default_rng(9))
+        res[half] = (xi.to_host(), eta.to_host(), F, U.data.copy(), dH, acc)
+    for a, b in zip(res[True][:4], res[False][:4]):
+        assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+    assert abs(res[True][4] - res[False][4]) < 1e-6 and res[True][5] == res[False][5] and abs(res[True][4]) < 0.5
