@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LQCD_ABI_VERSION 1
+#define LQCD_ABI_VERSION 2        /* 2: + rational-action, multi-RHS, gauge-file, staggered even-site, Z4 entry points (additive) */
 
 enum {
     LQCD_OK = 0,

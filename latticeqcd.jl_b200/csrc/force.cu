@@ -305,8 +305,8 @@ static int check_force_args(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion
 int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, double eps, int maxsteps, int *iters) {
     LQCD_TRY(check_force_args(ctx, op, eta, eta));
     lqcd_fermion *X = nullptr, *Y = nullptr;
-    LQCD_TRY(get_scratch(ctx, op->kind, 8, &X));
-    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    LQCD_TRY(get_scratch(ctx, op->kind, SCR_FORCE_X, &X));
+    LQCD_TRY(get_scratch(ctx, op->kind, SCR_FORCE_Y, &Y));
     CUDA_TRY(ctx, cudaMemsetAsync(X->d, 0, X->bytes, ctx->stream));
     int it = 0;
     double rs = 0.0;
@@ -320,11 +320,10 @@ int force_for_md(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, doub
 // r(x) = alpha0 + sum_j alpha[j] / (x + shifts[j]).  X_j = (DdagD + shifts[j])^-1 eta by ONE multi-shift CG, Y_j = D X_j,
 // UdSfdU = sum_j alpha[j] force(X_j, Y_j) accumulated in ctx->force_buf.  Scratch: the solver owns slots 0 .. 2 + LQCD_MAX_SHIFTS,
 // the force keeps 8 / 9 for the plain action, so the shifted solutions live above both.
-#define RATIONAL_SLOT0 (3 + LQCD_MAX_SHIFTS)
 static int rational_solutions(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, const double *shifts, int nshift,
                               double eps, int maxsteps, lqcd_fermion **xs, int *iters) {
     if (!shifts || nshift < 1 || nshift > LQCD_MAX_SHIFTS) return lqcd_fail(ctx, LQCD_ERR_ARG, "rational action: nshift must be in [1, %d]", LQCD_MAX_SHIFTS);
-    for (int j = 0; j < nshift; j++) LQCD_TRY(get_scratch(ctx, op->kind, RATIONAL_SLOT0 + j, &xs[j]));
+    for (int j = 0; j < nshift; j++) LQCD_TRY(get_scratch(ctx, op->kind, SCR_RATIONAL0 + j, &xs[j]));
     int it = 0;
     double rs = 0.0;
     LQCD_TRY(lqcd_multishift_cg(ctx, op, xs, eta, shifts, nshift, eps, maxsteps, &it, &rs));
@@ -338,7 +337,7 @@ int force_for_md_rational(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *
     if (!alpha) return lqcd_fail(ctx, LQCD_ERR_ARG, "null argument");
     lqcd_fermion *xs[LQCD_MAX_SHIFTS], *Y = nullptr;
     LQCD_TRY(rational_solutions(ctx, op, eta, shifts, nshift, eps, maxsteps, xs, iters));
-    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    LQCD_TRY(get_scratch(ctx, op->kind, SCR_FORCE_Y, &Y));
     for (int j = 0; j < nshift; j++) {
         LQCD_TRY(lqcd_dslash(ctx, op, Y, xs[j], LQCD_OP_D));
         LQCD_TRY(force_outer(ctx, op, xs[j], Y, alpha[j], j > 0, nullptr, nullptr));
@@ -402,10 +401,10 @@ extern "C" int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_f
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     lqcd_fermion *X = x_inout, *Y = nullptr;
     if (!X) {
-        LQCD_TRY(get_scratch(ctx, op->kind, 8, &X));
+        LQCD_TRY(get_scratch(ctx, op->kind, SCR_FORCE_X, &X));
         CUDA_TRY(ctx, cudaMemsetAsync(X->d, 0, X->bytes, ctx->stream));
     }
-    LQCD_TRY(get_scratch(ctx, op->kind, 9, &Y));
+    LQCD_TRY(get_scratch(ctx, op->kind, SCR_FORCE_Y, &Y));
     int it = 0;
     double rs = 0.0;
     LQCD_TRY(lqcd_solve(ctx, op, X, eta, LQCD_SOLVER_CG, LQCD_OP_DDAGD, eps, maxsteps, &it, &rs, nullptr));

@@ -494,7 +494,7 @@ extern "C" int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion 
         cplx *tmp[LQCD_MAX_RHS];
         for (int j = 0; j < nrhs; j++) {
             lqcd_fermion *t = nullptr;
-            LQCD_TRY(get_scratch(ctx, op->kind, 80 + j, &t));
+            LQCD_TRY(get_scratch(ctx, op->kind, SCR_MRHS0 + j, &t));
             tmp[j] = t->d;
         }
         LQCD_TRY(launch_mrhs(ctx, op, tmp, in, nrhs, 0, 0, 0, 0));
@@ -575,7 +575,7 @@ extern "C" int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *
     LQCD_TRY(mrhs_work(ctx, &w));
     const int kind = op->kind;
     const size_t n = (size_t)ctx->g.nblk * ys[0]->ncomp * 32;
-    // per-RHS work vectors: scratch slots 80 + 16 v + j (v = 0 .. 3), allocated on first use
+    // per-RHS work vectors: scratch slots SCR_MRHS0 + 16 v + j (v = 0 .. 3), allocated on first use
     cplx *x[LQCD_MAX_RHS], *v0[LQCD_MAX_RHS], *v1[LQCD_MAX_RHS], *v2[LQCD_MAX_RHS], *v3[LQCD_MAX_RHS];
     const cplx *b[LQCD_MAX_RHS];
     const int nvec = method == LQCD_SOLVER_CG ? 4 : 3;
@@ -584,7 +584,7 @@ extern "C" int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *
         cplx **dst[4] = {&v0[j], &v1[j], &v2[j], &v3[j]};
         for (int v = 0; v < nvec; v++) {
             lqcd_fermion *f = nullptr;
-            LQCD_TRY(get_scratch(ctx, kind, 80 + 16 * v + j, &f));
+            LQCD_TRY(get_scratch(ctx, kind, SCR_MRHS0 + 16 * v + j, &f));
             *dst[v] = f->d;
         }
     }

@@ -21,7 +21,7 @@ def test_library_builds_and_loads():
     import __graft_entry__ as g
     g.build()
     lib = _lib.load()
-    assert lib.lqcd_abi_version() == 1
+    assert lib.lqcd_abi_version() == 2
 
 
 def test_every_header_symbol_is_exported_and_bound():
