@@ -253,6 +253,7 @@ EXPERIMENTS = {
     "mrhs_r2": ({"LQCD_MRHS_R": "2"}, "12 right-hand sides, 2 per thread (lqcd_dslash_multi)"),
     "mrhs_r3": ({"LQCD_MRHS_R": "3"}, "12 right-hand sides, 3 per thread"),
     "mrhs_r4": ({"LQCD_MRHS_R": "4"}, "12 right-hand sides, 4 per thread"),
+    "mrhs_smem": ({"LQCD_MRHS_SMEM": "1"}, "12 right-hand sides, links staged in shared memory by cp.async.bulk (one CTA per SM)"),
     "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides per pass"),
     "clover": ({}, "Wilson-clover Dslash (csw = 1.5612)"),
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
@@ -313,7 +314,7 @@ def experiment_child(name, dims):
         ctx2, op2, x2, y2 = setup(dims)
         ms = dslash_ms(ctx2, op2, y2, x2)
         out.update({"ms_per_apply": ms, "GB/s": BYTES_PER_SITE * V / ms / 1e6, "frac_of_peak": BYTES_PER_SITE * V / ms / 1e6 / peaks()[0]})
-    elif name.startswith("mrhs_r") or name == "staggered_mrhs":
+    elif name.startswith("mrhs_") or name == "staggered_mrhs":
         kind = L.STAGGERED if name == "staggered_mrhs" else L.WILSON
         nrhs = 12
         ctx, op, x, y = setup(dims, kind)

@@ -25,6 +25,7 @@
 #include "reduce.cuh"
 #include "site_map.cuh"
 #include "wilson_spin.cuh"
+#include "bulk_copy.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -160,6 +161,130 @@ __global__ void __launch_bounds__(128, MINB) wilson_mrhs_kernel(const MrhsArgs A
         }
         if (A.want_norm) {
             if (reduced) __syncthreads();          // the shared scratch of the previous right-hand side's reduction is free again
+            grid_reduce_finish<3>(red, reduce_of(A.red[j]), A.finish);
+            reduced = true;
+        }
+    }
+}
+
+
+// ---- Wilson, links staged in shared memory by bulk copies (LQCD_MRHS_SMEM=1, experimental) ------------------------------------
+// The register-resident version above shares a link between R = 3 right-hand sides.  Here a warp stages ALL links its 32-site
+// block needs -- its own 18 KB record (the four forward links of every site) and, per direction, the 4.5 KB mu-slab of the block
+// one step back (the backward links) -- in shared memory with five cp.async.bulk copies that complete on an mbarrier, and then runs
+// over all nrhs right-hand sides reading links from shared memory and spinors from global memory: 36 KB of link traffic per
+// block whatever nrhs is (1152/nrhs B per site and right-hand side, of which only the own record is compulsory HBM traffic:
+// the neighbour slabs are L2 hits), + 384 B of spinors -> 432 B at nrhs = 12.  The per-RHS arithmetic and reductions are those of
+// wilson_mrhs_kernel (bit-identical results).  One CTA of 4 warps holds 4 x 36 KB = 144 KB: one CTA per SM, the loads of a whole
+// right-hand side (96 x 128-bit per thread) are independent and in flight together.  Regular tilings only.
+#define MS_OWN (36 * 32)                    // complex numbers of a block's link record
+#define MS_SLAB (9 * 32)                    // ... of one direction's slab
+#define MS_WARP (MS_OWN + 4 * MS_SLAB)      // per-warp staging area (36 864 B)
+
+template <int MU, int FWD, int DAG>
+__device__ __forceinline__ void hop_sm(cplx (&acc)[12], const cplx *__restrict__ sp, const cplx *lk, bool wrapped, double phase) {
+    constexpr int S = (FWD ^ DAG) ? -1 : +1;      // sp: neighbour spinor (global, lane applied); lk: link element 0 (shared, lane applied)
+    cplx h0[3], h1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        cplx p0 = __ldg(sp + (0 + c) * 32), p1 = __ldg(sp + (3 + c) * 32);
+        cplx p2 = __ldg(sp + (6 + c) * 32), p3 = __ldg(sp + (9 + c) * 32);
+        project<MU, S>(h0[c], h1[c], p0, p1, p2, p3);
+    }
+    if (wrapped) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            if (FWD) { const cplx u = lk[(a * 3 + b) * 32]; cfma(g0, u, h0[b]); cfma(g1, u, h1[b]); }
+            else     { const cplx u = lk[(b * 3 + a) * 32]; cfmac(g0, u, h0[b]); cfmac(g1, u, h1[b]); }
+        }
+        reconstruct<MU, S>(acc, a, g0, g1);
+    }
+}
+
+template <int DAG>
+__global__ void __launch_bounds__(128, 1) wilson_mrhs_smem_kernel(const MrhsArgs A) {
+    extern __shared__ __align__(128) unsigned char ms_smem[];
+    const Geom &g = A.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    cplx *own = reinterpret_cast<cplx *>(ms_smem) + (size_t)warp * MS_WARP;
+    cplx *slab = own + MS_OWN;                                                      // [4][9][32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ms_smem + (size_t)4 * MS_WARP * sizeof(cplx)) + warp;
+    const int blk = block_of_warp(g, blockIdx.x, warp);
+    const bool active = blk < g.nblk;
+    // block-lattice coordinates and the blocks one step back in every direction
+    int bc[4], r = blk;
+    for (int i = 0; i < 3; i++) { bc[i] = r % g.nb[i]; r /= g.nb[i]; }
+    bc[3] = r;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (active) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(MS_WARP * sizeof(cplx)));
+            bulk_g2s(own, A.gauge + (size_t)blk * MS_OWN, (uint32_t)(MS_OWN * sizeof(cplx)), bar);
+            int stride = 1;
+            for (int mu = 0; mu < 4; mu++) {
+                const int nbk = blk + (bc[mu] == 0 ? (g.nb[mu] - 1) : -1) * stride;
+                bulk_g2s(slab + mu * MS_SLAB, A.gauge + ((size_t)nbk * 4 + mu) * MS_SLAB, (uint32_t)(MS_SLAB * sizeof(cplx)), bar);
+                stride *= g.nb[mu];
+            }
+        }
+    }
+    __syncwarp();
+    int x = 0, y = 0, z = 0, t = 0, s = 0;
+    const cplx *lkb[4];                       // backward link of direction mu for this lane (element 0)
+    if (active) {
+        s = blk * 32 + lane;
+        site_coords(g, s, x, y, z, t);
+        // position inside the block: lane = l0 + s0 (l1 + s1 (l2 + s2 l3))
+        int l[4], q = lane, st = 1;
+        for (int i = 0; i < 3; i++) { l[i] = q % g.s[i]; q /= g.s[i]; }
+        l[3] = q;
+        for (int mu = 0; mu < 4; mu++) {
+            lkb[mu] = l[mu] > 0 ? own + mu * MS_SLAB + (lane - st) : slab + mu * MS_SLAB + (lane + (g.s[mu] - 1) * st);
+            st *= g.s[mu];
+        }
+        mbar_wait(bar, 0);
+    }
+    const size_t base = (size_t)blk * (12 * 32) + lane;
+    const double mk = -A.kappa;
+    bool reduced = false;
+    for (int j = 0; j < A.nrhs; j++) {
+        if (A.use_state && A.red[j].st->done) continue;             // CTA-uniform
+        double red[3] = {0.0, 0.0, 0.0};
+        if (active) {
+            const cplx *in = A.in[j];
+            cplx acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
+#define MS_PAIR(MU, coord, dim, strd)                                                                                     \
+            {                                                                                                             \
+                const bool wf = (coord == dim - 1), wb = (coord == 0);                                                    \
+                const int nf = wf ? s - (dim - 1) * (strd) : s + (strd), nb_ = wb ? s + (dim - 1) * (strd) : s - (strd);  \
+                hop_sm<MU, 1, DAG>(acc, in + (size_t)(nf >> 5) * (12 * 32) + (nf & 31), own + MU * MS_SLAB + lane, wf, A.bc[MU]);   \
+                hop_sm<MU, 0, DAG>(acc, in + (size_t)(nb_ >> 5) * (12 * 32) + (nb_ & 31), lkb[MU], wb, A.bc[MU]);         \
+            }
+            MS_PAIR(0, x, g.X, 1)
+            MS_PAIR(1, y, g.Y, g.X)
+            MS_PAIR(2, z, g.Z, g.X * g.Y)
+            MS_PAIR(3, t, g.T, g.X * g.Y * g.Z)
+#undef MS_PAIR
+            cplx *dst = A.out[j];
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const cplx xi = __ldg(in + base + k * 32);
+                const cplx yk = cmake(fma(mk, acc[k].x, xi.x), fma(mk, acc[k].y, xi.y));
+                red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
+                dst[base + k * 32] = yk;
+            }
+        }
+        if (A.want_norm) {
+            if (reduced) __syncthreads();
             grid_reduce_finish<3>(red, reduce_of(A.red[j]), A.finish);
             reduced = true;
         }
@@ -428,6 +553,22 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
     if (op->kind == LQCD_WILSON) {
         if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
         if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "multi-RHS Wilson kernel: LQCD_WPC > 4 is not supported");
+        static int smem_links = -1;
+        if (smem_links < 0) { const char *e = getenv("LQCD_MRHS_SMEM"); smem_links = (e && atoi(e) == 1) ? 1 : 0; }
+        if (smem_links && ctx->g.regular && bs == 128) {       // experimental: links staged in shared memory by bulk copies
+            const size_t smem = (size_t)4 * MS_WARP * sizeof(cplx) + 4 * sizeof(uint64_t) + 32;
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_mrhs_smem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_mrhs_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            if (dagger) wilson_mrhs_smem_kernel<1><<<gx, bs, smem, ctx->stream>>>(A);
+            else        wilson_mrhs_smem_kernel<0><<<gx, bs, smem, ctx->stream>>>(A);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            return LQCD_OK;
+        }
         const int R = wilson_group(nrhs);
         const dim3 grid(gx, (nrhs + R - 1) / R);
 #define WM(R_, MB_) do { if (dagger) wilson_mrhs_kernel<1, R_, MB_><<<grid, bs, 0, ctx->stream>>>(A); else wilson_mrhs_kernel<0, R_, MB_><<<grid, bs, 0, ctx->stream>>>(A); } while (0)

@@ -84,6 +84,18 @@ def test_tmarch_kernel_under_emulation(emu_lib, bulk):
     assert m and int(m.group(1)) > 500 and "launches wilson_dslash_kernel" not in r.stderr, r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("bulk", ["early", "late"])
+def test_mrhs_smem_links_kernel_under_emulation(emu_lib, bulk):
+    """LQCD_MRHS_SMEM=1: multi-RHS Wilson kernel with the links staged in shared memory by cp.async.bulk + mbarrier (both completion
+    schedules of the bulk-copy model): bit-identical to the single-RHS kernel, propagators equal the oracle's"""
+    cmd = [sys.executable, "-m", "pytest", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x", "--runxfail", "-p", "no:cacheprovider",
+           "-k", "multi_rhs_dslash or point_source_propagators"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_MRHS_SMEM="1", LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"launches wilson_mrhs_smem_kernel\s+(\d+)", r.stderr)
+    assert m and int(m.group(1)) > 50, r.stderr[-2000:]
+
+
 def test_persistent_queue_variant_under_emulation(emu_lib):
     """LQCD_PERSIST=1 (persistent CTAs drawing tiles from a self-resetting queue): single-rank solver tests + a 2-rank worker"""
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
