@@ -450,7 +450,8 @@ EXPERIMENTS_MULTI = {
     "halo_poll_relaxed": ({"LQCD_HALO_POLL": "relaxed"}, "face CTAs poll the halo flags with ld.relaxed.sys instead of ld.acquire.sys"),
     "pack_fence_gpu": ({"LQCD_PACK_FENCE": "g"}, "gpu-scope fence per pack CTA, one system fence by the last"),
     "persist": ({"LQCD_PERSIST": "1"}, "persistent CTAs drawing pack / interior / face tiles from one queue"),
-    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream instead of leading CTAs"),
+    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream (default with >= 2 partitioned directions)"),
+    "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel (default with one partitioned direction, small local volume)"),
     "relaxed_and_persist": ({"LQCD_HALO_POLL": "relaxed", "LQCD_PERSIST": "1"}, "both"),
 }
 
@@ -513,7 +514,7 @@ def run_experiments_multi(lattice, rank, local_rank, world, budget_s, barrier):
     t_start = time.perf_counter()
     for idx, (name, (env_extra, what)) in enumerate(EXPERIMENTS_MULTI.items()):
         barrier()                                       # all parents decide together (rank 0's clock is not shared: fixed schedule)
-        if (idx + 1) * 40 > budget_s:
+        if (idx + 1) * 34 > budget_s:
             results[name] = {"skipped": "time budget of the experiments leg", "what": what}
             continue
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
