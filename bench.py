@@ -445,14 +445,14 @@ def run_experiments(lattice, local_rank, budget_s):
 # of the job spawns ONE child with its own RANK / LOCAL_RANK; the children of one experiment form their own process group (gloo,
 # host plumbing only) on a different port, create contexts, connect over CUDA IPC and time the Dslash and a CG with the knob set
 # in their environment.  The parents only wait.  Same isolation argument as above.
-EXPERIMENTS_MULTI = {
+EXPERIMENTS_MULTI = {       # most informative first: the leg stops starting new ones when its time budget is used up
     "default": ({}, "defaults (reference for the rows below)"),
     "halo_poll_relaxed": ({"LQCD_HALO_POLL": "relaxed"}, "face CTAs poll the halo flags with ld.relaxed.sys instead of ld.acquire.sys"),
+    "persist": ({"LQCD_PERSIST": "1", "LQCD_SELF_PACK": "1"}, "persistent CTAs drawing pack / interior / face tiles from one queue"),
+    "relaxed_and_persist": ({"LQCD_HALO_POLL": "relaxed", "LQCD_PERSIST": "1", "LQCD_SELF_PACK": "1"}, "both"),
     "pack_fence_gpu": ({"LQCD_PACK_FENCE": "g"}, "gpu-scope fence per pack CTA, one system fence by the last"),
-    "persist": ({"LQCD_PERSIST": "1"}, "persistent CTAs drawing pack / interior / face tiles from one queue"),
     "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream (default with >= 2 partitioned directions)"),
     "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel (default with one partitioned direction, small local volume)"),
-    "relaxed_and_persist": ({"LQCD_HALO_POLL": "relaxed", "LQCD_PERSIST": "1"}, "both"),
 }
 
 
