@@ -55,7 +55,7 @@ def test_gpu_suite_under_emulation(emu_lib):
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 126, tail
+    assert m and int(m.group(1)) >= 132, tail
 
 
 @pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),

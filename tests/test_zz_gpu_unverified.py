@@ -385,3 +385,21 @@ def test_staggered_nf4_force_and_trajectory_on_half_fields(golden_dir):
     for a, b in zip(res[True][:4], res[False][:4]):
         assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
     assert abs(res[True][4] - res[False][4]) < 1e-6 and res[True][5] == res[False][5] and abs(res[True][4]) < 0.5
+
+
+@pytest.mark.parametrize("dims", [(24, 4, 4, 4), (24, 24, 2, 2), (12, 6, 4, 4)])
+@pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
+def test_extents_of_24(dims, kind):
+    """BASELINE config 3 is a 24^4 lattice: extents that neither divide nor are divided by the 32-site block (irregular tiling)"""
+    q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
+    src = orc.gaussian_field(dims, kind, seed=5)
+    y = q.similar(x)
+    q.mul_(y, D, x.from_host(src))
+    want = orc.apply(op, kind, orc.D, Uh, src)
+    assert np.abs(y.to_host() - want).max() / np.abs(want).max() < 1e-13
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    ref = orc.cg(op, kind, Uh, src, eps=1e-20)
+    assert info["iters"] == ref["iters"]
+    assert np.abs(sol.to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
