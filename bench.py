@@ -259,6 +259,7 @@ EXPERIMENTS = {
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
     "staggered_even": ({}, "staggered CG on an even-site source: half-field solver vs full-lattice solver"),
     "md": ({}, "device-resident Sexton-Weingarten trajectory with Wilson pseudofermions, 16^4"),
+    "rhmc_md": ({}, "device-resident RHMC trajectory (staggered Nf = 2: multi-shift CG + rational force per step), 16^4"),
 }
 
 
@@ -402,6 +403,34 @@ def experiment_child(name, dims):
         t0 = time.perf_counter()
         ctx.call("lqcd_md_trajectory", C.byref(op), x.h, 5.7, 0.02, 2, 4, 1e-16, 3000, C.byref(its))
         out.update({"dynamical_wall_ms_2_steps_nsw4": (time.perf_counter() - t0) * 1e3, "cg_iters": its.value})
+    elif name == "rhmc_md":
+        from lqcd_b200 import rhmc
+        ra = rhmc.rational_approx(-2 / 8.0, 12, 0.22, 17.0)             # x^(-Nf/8), Nf = 2, mass 0.5: spec(DdagD) in [0.25, 16.25]
+        al = np.ascontiguousarray(ra.alpha, dtype=np.float64)
+        sh = np.ascontiguousarray(ra.beta, dtype=np.float64)
+        pa, ps = al.ctypes.data_as(L.pdbl), sh.ctypes.data_as(L.pdbl)
+        ctx, op, x, y = setup(small, kind=L.STAGGERED, eps=0.3)
+        its, it1, S = C.c_longlong(0), C.c_int(0), C.c_double(0.0)
+
+        def run(dtau, steps):
+            ctx.call("lqcd_gauge_random", 111, 0.3)
+            ctx.call("lqcd_md_momenta_gaussian", 7)
+            K, G = C.c_double(), C.c_double()
+            H = []
+            for leg in range(2):
+                ctx.call("lqcd_md_kinetic", C.byref(K)); ctx.call("lqcd_md_gauge_action", 5.7, C.byref(G))
+                ctx.call("lqcd_rational_apply", C.byref(op), y.h, x.h, float(ra.alpha0), pa, ps, len(al), 1e-18, 3000, C.byref(it1), C.byref(S))
+                H.append(K.value + G.value + S.value)
+                if leg == 0:
+                    t0 = time.perf_counter()
+                    ctx.call("lqcd_md_trajectory_rational", C.byref(op), x.h, pa, ps, len(al), 5.7, dtau, steps, 0, 1e-18, 3000, C.byref(its))
+                    wall = time.perf_counter() - t0
+            return H[1] - H[0], wall, its.value
+
+        dH1, wall, nit = run(0.02, 4)
+        dH2, _, _ = run(0.01, 8)
+        out["ok"] = bool(2.5 < dH1 / dH2 < 6.0)
+        out.update({"dH_dtau0.02": dH1, "dH_dtau0.01": dH2, "wall_ms_4_steps": wall * 1e3, "multishift_cg_iters": nit, "poles": len(al)})
     else:
         out["error"] = "unknown experiment"
     print("EXPERIMENT " + json.dumps(out), flush=True)
