@@ -75,7 +75,7 @@ static int julia_float(char *dst, double v) {
     char sci[40];
     auto r = std::to_chars(sci, sci + sizeof sci, v, std::chars_format::scientific);      // d[.ddd]e[+-]XX, shortest digits
     *r.ptr = 0;
-    char digits[24];
+    char digits[24] = {0};
     int nd = 0;
     const char *q = sci;
     for (; *q && *q != 'e'; q++)
@@ -118,7 +118,7 @@ static int read_block(const lqcd_ctx *ctx, const char *path, int format, const B
     if (!f) return lqcd_fail(ctx, LQCD_ERR_ARG, "cannot open %s: %s", path, strerror(errno));
     int rc = LQCD_OK;
     if (format == LQCD_IO_ILDG) {
-        LimeRecord rec;
+        LimeRecord rec = {0, 0};
         rc = lime_find_payload(ctx, f, path, &rec);
         if (rc == LQCD_OK && rec.length != gV * sd * 8)
             rc = lqcd_fail(ctx, LQCD_ERR_ARG, "%s: payload of %llu bytes does not match a %dx%dx%dx%d NC=%d lattice (%zu bytes)", path,
