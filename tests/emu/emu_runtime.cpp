@@ -169,9 +169,14 @@ void run_cta() {
         f.state = RUN; f.gen = 0;
         C->warp_alive[t >> 5]++;
     }
+    // LQCD_EMU_THREAD_ORDER=reverse: the runnable threads of a CTA are resumed from the highest thread index down (a missing
+    // __syncthreads / __syncwarp between a shared-memory write and a read by another thread shows up in one of the two orders)
+    static int trev = -1;
+    if (trev < 0) { const char *e = getenv("LQCD_EMU_THREAD_ORDER"); trev = (e && e[0] == 'r') ? 1 : 0; }
     while (C->alive > 0) {
         bool progress = false;
-        for (int t = 0; t < n; t++) {
+        for (int tt = 0; tt < n; tt++) {
+            const int t = trev ? n - 1 - tt : tt;
             Fiber &f = C->fib[t];
             if (f.state == DONE) continue;
             if (f.state == WAIT_CTA) { if (f.gen == C->cta_gen) continue; f.state = RUN; }
@@ -213,13 +218,18 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, cudaStream_t, const std::fun
     C->nthreads = (int)nthreads;
     C->body = &body;
     blockDim = block; gridDim = grid;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
-                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-                if (dyn_smem) memset(dyn_smem_ptr, 0xFF, dyn_smem);      // shared memory starts uninitialised
-                run_cta();
-            }
+    // LQCD_EMU_CTA_ORDER=reverse: run the CTAs of every launch in DESCENDING blockIdx order.  A kernel whose CTAs exchange data
+    // within one launch (a CTA reading what another one writes: in-place stencils, missing double buffering) gives different
+    // results in the two orders; kernels that rely on dispatch order across ranks (halo flags) are single-rank-only in this mode.
+    static int reverse = -1;
+    if (reverse < 0) { const char *e = getenv("LQCD_EMU_CTA_ORDER"); reverse = (e && e[0] == 'r') ? 1 : 0; }
+    const unsigned long long ncta = (unsigned long long)grid.x * grid.y * grid.z;
+    for (unsigned long long i = 0; i < ncta; i++) {
+        const unsigned long long c = reverse ? ncta - 1 - i : i;
+        blockIdx.x = (unsigned)(c % grid.x); blockIdx.y = (unsigned)((c / grid.x) % grid.y); blockIdx.z = (unsigned)(c / ((unsigned long long)grid.x * grid.y));
+        if (dyn_smem) memset(dyn_smem_ptr, 0xFF, dyn_smem);      // shared memory starts uninitialised
+        run_cta();
+    }
     C->body = nullptr;
 }
 void cta_barrier() {

@@ -58,6 +58,20 @@ def test_gpu_suite_under_emulation(emu_lib):
     assert m and int(m.group(1)) >= 132, tail
 
 
+def test_gpu_suite_is_schedule_independent_under_emulation(emu_lib):
+    """the single-rank `-m gpu` suite again with the CTAs of every launch executed in DESCENDING blockIdx order and the threads of
+    a CTA resumed from the highest index down: a kernel whose CTAs exchange data within one launch (in-place stencil, missing
+    double buffer) or that misses a barrier between a shared-memory write and another thread's read fails in one of the orders"""
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q",
+           "-x", "--runxfail", "-p", "no:cacheprovider", "-n", "4",
+           "-k", "not size_independent and not cgnr_matches_single and not multi_rhs_cg_on and not pipelined_host"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_CTA_ORDER="reverse", LQCD_EMU_THREAD_ORDER="reverse", OMP_NUM_THREADS="1"),
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 90, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("dims,pg,kind", [("4x4x4x8", "1x1x1x2", "Wilson full"), ("4x4x4x4", "1x1x2x2", "staggered full"),
                                           ("4x4x8x4", "1x1x2x2", "Wilson clover")])
 def test_multirank_under_emulation(emu_lib, dims, pg, kind):
