@@ -15,8 +15,9 @@ with x^p ~ alpha_0 + sum_j alpha_j / (x + beta_j).  Upstream obtains the coeffic
 relative-error least-squares fit started from the Stieltjes-integral quadrature of x^p (same functional form,
 same use; the coefficients differ from Remez' by construction, the approximation error is asserted instead).
 
-Everything above the solver is written against a tiny *backend* (vector ops + shifted solve), so the identical
-code runs on the CPU oracle (tests, no GPU) and on the B200 library.
+Everything above the solver is written against a tiny *backend* (vector ops + shifted solve): the product backend is
+B200Backend below; the test-suite plugs in a CPU backend of its own (tests/oracle_backend.py) to check the same composition
+against dense matrix functions without a GPU.
 """
 from __future__ import annotations
 
@@ -105,38 +106,6 @@ def _fit_negative_power(power, order, lo, hi, npts, fix_c0):
 # backend protocol: new_like(v), copy(v), axpy(y, a, x) [y += a x], scale(v, a), dot(a, b) -> complex,
 #                   apply(mode, x) -> y  (mode in {"D", "Ddag"}),  shifted_solve(b, shifts) -> list of x_j
 # ---------------------------------------------------------------------------------------------------
-class OracleBackend:
-    """CPU oracle backend (tests only)."""
-
-    def __init__(self, orc, op, kind, U, eps=1e-24, maxsteps=5000):
-        self.orc, self.op, self.kind, self.U, self.eps, self.maxsteps = orc, op, kind, U, eps, maxsteps
-        self.last_iters = 0
-
-    def new_like(self, v):
-        return np.zeros_like(v)
-
-    def copy(self, v):
-        return v.copy()
-
-    def axpy(self, y, a, x):
-        y += a * x
-
-    def scale(self, v, a):
-        v *= a
-
-    def dot(self, a, b):
-        return complex(np.vdot(a, b))
-
-    def apply(self, mode, x):
-        return self.orc.apply(self.op, self.kind, {"D": self.orc.D, "Ddag": self.orc.DDAG}[mode], self.U, x)
-
-    def shifted_solve(self, b, shifts):
-        r = self.orc.mscg(self.op, self.kind, self.U, b, shifts, eps=self.eps, maxsteps=self.maxsteps)
-        assert r["converged"]
-        self.last_iters = r["iters"]
-        return r["xs"]
-
-
 class B200Backend:
     """liblqcd_b200 backend: device-resident FermionField handles, lqcd_multishift_cg for the shifted systems."""
 

@@ -19,6 +19,7 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 sys.path[:0] = [str(ROOT / "latticeqcd.jl_b200"), str(ROOT / "tests")]
 from lqcd_b200 import rhmc                    # noqa: E402
+from oracle_backend import OracleBackend          # noqa: E402
 from oracle import oracle as orc              # noqa: E402
 import test_md                                # noqa: E402
 
@@ -54,7 +55,7 @@ def oracle_hmc(U0, p, ntraj, seed):
         even = ((t + z + y + x) & 1) == 0
     act = None
     if p["Nf"] in (2, 3):
-        act = rhmc.RHMCAction(rhmc.OracleBackend(orc, op, kind, U0), p["Nf"], 0.22, 17.0, order=12)
+        act = rhmc.RHMCAction(OracleBackend(orc, op, kind, U0), p["Nf"], 0.22, 17.0, order=12)
     U, acc, dHs = U0.copy(), 0, []
     test_md.DIMS, test_md.BETA = DIMS, BETA
     for _ in range(ntraj):

@@ -6,8 +6,9 @@ import pytest
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT / "latticeqcd.jl_b200"))
+sys.path[:0] = [str(ROOT / "latticeqcd.jl_b200"), str(ROOT / "tests")]
 from lqcd_b200 import rhmc
+from oracle_backend import OracleBackend
 from oracle import oracle as orc
 
 DIMS = (4, 4, 4, 4)
@@ -40,7 +41,7 @@ def test_rhmc_against_dense_spectrum(golden_dir, Nf):
     A = _dense_DdagD(op, U)
     w, V = np.linalg.eigh((A + A.conj().T) / 2)
     assert w.min() > 0.25 - 1e-9
-    be = rhmc.OracleBackend(orc, op, orc.STAGGERED, U)
+    be = OracleBackend(orc, op, orc.STAGGERED, U)
     act = rhmc.RHMCAction(be, Nf, 0.9 * w.min(), 1.1 * w.max(), order=12)
     xi = orc.gaussian_field(DIMS, orc.STAGGERED, seed=77)
     phi = act.sample_pseudofermions(xi)
@@ -74,7 +75,7 @@ def test_rhmc_on_b200(golden_dir):
     S = act.evaluate(phi)
     assert abs(S - np.vdot(xi_h, xi_h).real) < 1e-5 * S
     # same numbers as the oracle backend with the same rational functions
-    be = rhmc.OracleBackend(orc, orc.make_op(DIMS, mass=0.5), orc.STAGGERED, Uh)
+    be = OracleBackend(orc, orc.make_op(DIMS, mass=0.5), orc.STAGGERED, Uh)
     act_cpu = rhmc.RHMCAction(be, 2, 0.22, 6.0, order=12)
     phi_cpu = act_cpu.sample_pseudofermions(xi_h)
     assert np.abs(phi.to_host() - phi_cpu).max() < 1e-9 * np.abs(phi_cpu).max()
@@ -94,7 +95,7 @@ def test_rhmc_force_finite_difference(golden_dir):
     phi = orc.gaussian_field(DIMS, orc.STAGGERED, seed=91)
 
     def make(Ux):
-        return rhmc.RHMCAction(rhmc.OracleBackend(orc, op, orc.STAGGERED, Ux), 2, 0.22, 17.0, order=12)
+        return rhmc.RHMCAction(OracleBackend(orc, op, orc.STAGGERED, Ux), 2, 0.22, 17.0, order=12)
 
     act = make(U)
     F = np.zeros_like(U)
@@ -164,7 +165,7 @@ def test_fermi_action_nf_dispatch_on_b200(golden_dir):
     q.sample_pseudofermions_(eta, U, fa2, xi)
     S = q.evaluate_FermiAction(fa2, U, eta)
     assert abs(S - np.vdot(xi_h, xi_h).real) < 1e-5 * S
-    act_cpu = rhmc.RHMCAction(rhmc.OracleBackend(orc, op, orc.STAGGERED, Uh), 2, 0.22, 17.0, order=12)
+    act_cpu = rhmc.RHMCAction(OracleBackend(orc, op, orc.STAGGERED, Uh), 2, 0.22, 17.0, order=12)
     eta_h = eta.to_host()
     Fr = np.zeros_like(Uh)
     for a, X, Y in act_cpu.force_terms(eta_h):
