@@ -1,3 +1,4 @@
+import os
 import sys
 from pathlib import Path
 
@@ -7,6 +8,21 @@ ROOT = Path(__file__).resolve().parents[1]
 for p in (ROOT, ROOT / "latticeqcd.jl_b200"):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """The CPU suite (`-m "not gpu"`) spends most of its time in independent subprocess-based pre-flight tests: run it on 4 xdist
+    workers unless the caller chose a distribution.  GPU runs (`-m gpu`) stay serial and in collection order."""
+    opt = config.option
+    if (getattr(opt, "markexpr", "") == "not gpu" and hasattr(opt, "numprocesses") and not opt.numprocesses
+            and not os.environ.get("PYTEST_XDIST_WORKER") and not getattr(opt, "collectonly", False)
+            and getattr(opt, "dist", "no") == "no" and os.environ.get("LQCD_TEST_SERIAL") != "1"):
+        os.environ.setdefault("OMP_NUM_THREADS", "2")          # the oracle's OpenMP teams would oversubscribe the workers' cores
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+        opt.numprocesses = 4
+        opt.dist = "load"
+        opt.tx = ["popen"] * 4
 
 
 def pytest_configure(config):
