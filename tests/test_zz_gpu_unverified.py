@@ -403,3 +403,55 @@ def test_extents_of_24(dims, kind):
     ref = orc.cg(op, kind, Uh, src, eps=1e-20)
     assert info["iters"] == ref["iters"]
     assert np.abs(sol.to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["Wilson", "staggered"])
+def test_full_size_32_4_properties(kind):
+    """BASELINE headline size (32^4, one GPU): properties that need no oracle run -- linearity, <a, D b> = <D^dag a, b>, CG true
+    residual -- and the newer entry points against the verified single-RHS kernel AT THIS SIZE: multi-RHS Dslash bit-identical,
+    pipelined host mul! equal to upload + mul! + download, staggered half-field solve equal to the full-lattice solve"""
+    import ctypes as C
+    import lqcd_b200 as q
+    import os
+    dims = tuple(int(v) for v in os.environ.get("LQCD_TEST_FULL_DIMS", "32x32x32x32").split("x"))     # (the emulated pre-flight shrinks it)
+    ctx = q.get_context(dims)
+    U = q.Initialize_Gaugefields(3, 0, *dims, condition="cold")
+    a = q.Initialize_pseudofermion_fields(U[0], kind)
+    D = q.Dirac_operator(U, a, {"Dirac_operator": kind, "κ": 0.12, "mass": 0.5, "eps_CG": 1e-16, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    ctx.call("lqcd_gauge_random", 111, 0.3)                 # overwrite the cold links on the device with a warm synthetic field
+    b, Da, Db, Dab, Dda = (q.similar(a) for _ in range(5))
+    q.gauss_distribution_fermion_(a, 1); q.gauss_distribution_fermion_(b, 2)
+    q.mul_(Da, D, a); q.mul_(Db, D, b); q.mul_(Dda, q.adjoint(D), a)
+    l, r = q.dot(a, Db), q.dot(Dda, b)
+    assert abs(l - r) < 1e-9 * abs(l)
+    s = q.similar(a)
+    q.substitute_fermion_(s, a); q.add_(s, 0.5 - 0.25j, b)          # s = a + c b
+    q.mul_(Dab, D, s)
+    q.add_(Dab, -1.0, Da); q.add_(Dab, -(0.5 - 0.25j), Db)
+    assert q.dot(Dab, Dab).real < 1e-20 * q.dot(Da, Da).real
+    # multi-RHS == single-RHS, bit for bit
+    ys = [q.similar(a), q.similar(a), q.similar(a)]
+    q.mul_multi_(ys, D, [a, b, s])
+    assert np.array_equal(ys[0].to_host(), Da.to_host()) and np.array_equal(ys[1].to_host(), Db.to_host())
+    # pipelined host mul! == three-call sequence
+    ah = a.to_host()
+    yh = np.zeros_like(ah)
+    q.mul_host_(yh, D, ah)
+    assert np.array_equal(yh, Da.to_host())
+    # solve and recompute the true residual on the device
+    sol, chk = q.similar(a), q.similar(a)
+    if kind == "staggered":
+        q.mask_parity_(b, 0)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), b)
+    q.mul_(chk, q.DdagD(D), sol)
+    q.add_(chk, -1.0, b)
+    assert q.dot(chk, chk).real < 1e-14 and 5 < info["iters"] < 3000
+    if kind == "staggered":
+        half = q.similar(a)
+        q.clear_fermion_(half)
+        it, rs = C.c_int(0), C.c_double(0.0)
+        ctx.call("lqcd_solve_staggered_even", C.byref(D.op), half.h, b.h, D.eps, D.maxsteps, C.byref(it), C.byref(rs))
+        assert abs(it.value - info["iters"]) <= 1
+        q.add_(half, -1.0, sol)
+        assert q.dot(half, half).real < 1e-18 * q.dot(sol, sol).real
