@@ -83,7 +83,7 @@ def test_multirank_force_parity(dims, pg, kind):
     """same worker as test_multirank_parity; kept as a separate staged test because the worker now also checks the multi-rank
     fermion force and multi-shift CG, which have not run on hardware yet (tests/mp_worker.py "full")"""
     n = int(np.prod([int(v) for v in pg.split("x")]))
-    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, kind, "full", timeout=900)
+    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, kind, "full", timeout=240)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
@@ -94,7 +94,7 @@ def test_multirank_force_parity(dims, pg, kind):
 def test_multirank_clover_parity(dims, pg):
     """Wilson-clover across ranks: the clover leaves read the neighbours' links through peer-mapped link arrays (clover.cu)"""
     n = int(np.prod([int(v) for v in pg.split("x")]))
-    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, "Wilson", "clover", timeout=900)
+    res = run_ranks(n, ROOT / "tests" / "mp_worker.py", dims, pg, "Wilson", "clover", timeout=240)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
@@ -106,7 +106,7 @@ def test_multirank_md_trajectory(dims, pg, action):
     """Sexton-Weingarten trajectory across ranks (tests/mp_md_worker.py): Wilson pseudofermions, and the staggered Nf = 2 RHMC
     action (multi-shift CG + accumulated rational force per step; BASELINE config 5 in miniature)"""
     n = int(np.prod([int(v) for v in pg.split("x")]))
-    res = run_ranks(n, ROOT / "tests" / "mp_md_worker.py", dims, pg, action, timeout=900)
+    res = run_ranks(n, ROOT / "tests" / "mp_md_worker.py", dims, pg, action, timeout=240)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
@@ -115,6 +115,6 @@ def test_multirank_md_trajectory(dims, pg, action):
 @pytest.mark.xfail(reason="multi-rank gauge file I/O (lqcd_gauge_load / _save): verified under tests/emu only, not yet run on hardware", strict=False)
 def test_multirank_gauge_io():
     """every rank loads only its block of a global ILDG / BridgeText file; collective ILDG save is byte-identical (tests/mp_io_worker.py)"""
-    res = run_ranks(2, ROOT / "tests" / "mp_io_worker.py", "8x8x8x8", "1x1x1x2", timeout=600)
+    res = run_ranks(2, ROOT / "tests" / "mp_io_worker.py", "8x8x8x8", "1x1x1x2", timeout=240)
     sys.stdout.write(res.stdout[-2000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
