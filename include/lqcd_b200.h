@@ -59,7 +59,8 @@ typedef struct lqcd_fermion lqcd_fermion;
 typedef struct {
     int kind;          /* LQCD_WILSON | LQCD_STAGGERED                          params["Dirac_operator"] */
     double kappa;      /* Wilson hopping parameter                              params["κ"]  (universe.jl:114) */
-    double r;          /* Wilson parameter; only r == 1 has a kernel            params["r"]  (universe.jl:115) */
+    double r;          /* Wilson parameter (r != 1: slower two-kernel route,    params["r"]  (universe.jl:115)
+                          single rank, no force / multi-shift / even-odd) */
     double mass;       /* staggered mass                                        params["mass"] (universe.jl:109) */
     double csw;        /* clover coefficient (0 = none; Clover is not reachable from run_LQCD) */
     double bc[4];      /* fermion boundary phases, +-1                          params["boundarycondition"] (universe.jl:135) */

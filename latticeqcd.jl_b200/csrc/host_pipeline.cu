@@ -84,7 +84,7 @@ extern "C" int lqcd_dslash_host(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *
     // after the copy-in has finished, so more slabs = shorter tail; 16 keeps every copy piece > 1 MB at 32^4.
     int S = 1;
     if (g.regular) for (int c = 16; c >= 2; c--) if (g.nt[3] % c == 0) { S = c; break; }
-    const bool plain = ctx->nranks > 1 || ndw != 0 || !g.regular || S < 2 ||
+    const bool plain = ctx->nranks > 1 || ndw != 0 || !g.regular || S < 2 || (op->kind == LQCD_WILSON && op->r != 1.0) ||
                        y->kind != op->kind || x->kind != op->kind;
     if (plain) {                      // same result through the three-call sequence (every argument check happens there)
         LQCD_TRY(lqcd_fermion_upload(ctx, x, x_host, ndw));

@@ -315,8 +315,9 @@ int blas_copy(lqcd_ctx *ctx, cplx *dst, const cplx *src, size_t n);
 // while their own slots are live, never the other way round:
 //   SCR_FORCE_X / _Y   plain pseudofermion force (X = (DdagD)^-1 eta, Y = D X); Y also serves the rational force after its solve
 //   SCR_RATIONAL0 + j  shifted solutions of the rational (RHMC) action, j < LQCD_MAX_SHIFTS
+//   SCR_RTERM          spin-diagonal remainder of the Wilson operator with r != 1 (wilson_general_r.cu)
 //   SCR_MRHS0 + 16 v + j   work vector v (< 4) of right-hand side j (< 16) of the batched solvers
 //   0 .. 2 + LQCD_MAX_SHIFTS   the Krylov loops (solve_impl: 0-5, multi-shift: 0-2 and 3 + j)
-enum { SCR_FORCE_X = 8, SCR_FORCE_Y = 9, SCR_RATIONAL0 = 3 + LQCD_MAX_SHIFTS, SCR_MRHS0 = 80 };
+enum { SCR_FORCE_X = 8, SCR_FORCE_Y = 9, SCR_RATIONAL0 = 3 + LQCD_MAX_SHIFTS, SCR_RTERM = 3 + 2 * LQCD_MAX_SHIFTS, SCR_MRHS0 = 80 };
 int get_scratch(lqcd_ctx *ctx, int kind, int idx, lqcd_fermion **out);
 int reduce_grid(const lqcd_ctx *ctx);

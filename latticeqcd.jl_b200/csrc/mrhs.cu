@@ -617,7 +617,7 @@ static int check_fields(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys
 
 // the batched kernels cover: one rank, plain Wilson / staggered, full (not even-odd) fields, regular or irregular tiling
 static bool batched_ok(const lqcd_ctx *ctx, const lqcd_op *op) {
-    return ctx->nranks == 1 && !(op->kind == LQCD_WILSON && op->csw != 0.0) && !ctx->eo_active && 32 * ctx->g.wpc <= (op->kind == LQCD_WILSON ? 128 : 256);
+    return ctx->nranks == 1 && !(op->kind == LQCD_WILSON && (op->csw != 0.0 || op->r != 1.0)) && !ctx->eo_active && 32 * ctx->g.wpc <= (op->kind == LQCD_WILSON ? 128 : 256);
 }
 
 extern "C" int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const xs[], int nrhs, int mode) {

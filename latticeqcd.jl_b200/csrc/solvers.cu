@@ -38,9 +38,11 @@ static int check_op(const lqcd_ctx *ctx, const lqcd_op *op) {
 }
 
 int eo_mhat(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse);   // wilson_eo.cu
+int wilson_dslash_general_r(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse);   // wilson_general_r.cu
 
 static int one_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
     if (ctx->eo_active) return eo_mhat(ctx, op, y, x, dagger, fuse);      // lqcd_solve_eo: the "operator" is Mhat on even half fields
+    if (op->kind == LQCD_WILSON && op->r != 1.0) return wilson_dslash_general_r(ctx, op, y, x, dagger, fuse);      // rare general case
     if (ctx->nranks > 1) return comm_dslash(ctx, op, y, x, dagger, fuse);
     if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream);
     return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream);

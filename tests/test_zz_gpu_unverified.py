@@ -455,3 +455,43 @@ def test_full_size_32_4_properties(kind):
         assert abs(it.value - info["iters"]) <= 1
         q.add_(half, -1.0, sol)
         assert q.dot(half, half).real < 1e-18 * q.dot(sol, sol).real
+
+
+@pytest.mark.parametrize("r", [0.5, 1.3])
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4)])
+def test_wilson_general_r(dims, r):
+    """params["r"] != 1 (universe.jl:115 forwards it; default 1): M = M_{r=1} - kappa (r-1) L through the spin-diagonal remainder
+    kernel + the unchanged r = 1 kernel.  mul! in all three modes, CG / CGNR with identical iteration counts, multi-RHS and host
+    mul! (which take the single-RHS path), multi-shift rejected with a message"""
+    import lqcd_b200 as q
+    Uh = orc.random_su3(dims, seed=17, eps=0.35)
+    U = q.gaugefields_from_array(Uh)
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, {"Dirac_operator": "Wilson", "κ": 0.11, "r": r, "boundarycondition": [1, 1, 1, -1], "eps_CG": 1e-20, "MaxCGstep": 3000})
+    op = orc.make_op(dims, kappa=0.11, r=r)
+    src = orc.gaussian_field(dims, orc.WILSON, seed=18)
+    x.from_host(src)
+    y = q.similar(x)
+    for A, mode in ((D, orc.D), (q.adjoint(D), orc.DDAG), (q.DdagD(D), orc.DDAGD)):
+        q.mul_(y, A, x)
+        want = orc.apply(op, orc.WILSON, mode, Uh, src)
+        assert np.abs(y.to_host() - want).max() / np.abs(want).max() < 1e-13, mode
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    ref = orc.cg(op, orc.WILSON, Uh, src, eps=1e-20)
+    assert ref["converged"] and info["iters"] == ref["iters"]
+    assert np.abs(sol.to_host() - ref["x"]).max() / np.abs(ref["x"]).max() < 1e-10
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, D, x)
+    ref = orc.cgnr(op, orc.WILSON, Uh, src, eps=1e-20)
+    assert ref["converged"] and info["iters"] == ref["iters"]
+    ys = [q.similar(x), q.similar(x)]
+    q.mul_multi_(ys, D, [x, sol])
+    q.mul_(y, D, x)
+    assert np.array_equal(ys[0].to_host(), y.to_host())
+    yh = np.zeros_like(src)
+    q.mul_host_(yh, D, src)
+    assert np.array_equal(yh, y.to_host())
+    with pytest.raises(q.LqcdError, match="r = 1 only"):
+        q.shiftedcg_([q.similar(x)], D, x, [0.1])
