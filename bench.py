@@ -259,6 +259,7 @@ EXPERIMENTS = {
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
     "staggered_even": ({}, "staggered CG on an even-site source: half-field solver vs full-lattice solver"),
     "md": ({}, "device-resident Sexton-Weingarten trajectory with Wilson pseudofermions, 16^4"),
+    "force": ({}, "fermion-force outer-product kernels (Wilson, staggered) alone, 32^4"),
     "rhmc_md": ({}, "device-resident RHMC trajectory (staggered Nf = 2: multi-shift CG + rational force per step), 16^4"),
 }
 
@@ -315,6 +316,25 @@ def experiment_child(name, dims):
         ctx2, op2, x2, y2 = setup(dims)
         ms = dslash_ms(ctx2, op2, y2, x2)
         out.update({"ms_per_apply": ms, "GB/s": BYTES_PER_SITE * V / ms / 1e6, "frac_of_peak": BYTES_PER_SITE * V / ms / 1e6 / peaks()[0]})
+        # CG iterations/s with this kernel variant (warm field, fixed 60 iterations)
+        ctx2.call("lqcd_gauge_random", 111, 0.3)
+        it, rs = C.c_int(0), C.c_double(0.0)
+        for n_it in (10, 60):
+            q.clear_fermion_(y2)
+            t0 = time.perf_counter()
+            st = ctx2.lib.lqcd_solve(ctx2.h, C.byref(op2), y2.h, x2.h, L.SOLVER_CG, L.OP_DDAGD, 0.0, n_it, C.byref(it), C.byref(rs), None)
+            ctx2.synchronize()
+            dt = time.perf_counter() - t0
+        out.update({"cg_iters_per_s": it.value / dt, "cg_resid_sq_after_60": rs.value})
+    elif name == "force":
+        res = {}
+        for kind, key in ((L.WILSON, "wilson"), (L.STAGGERED, "staggered")):
+            ctx, op, x, y = setup(dims, kind=kind, eps=0.3)
+            ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)                    # some (X, Y) pair: the kernel's cost does not depend on it
+            t = _timed(lambda: ctx.call("lqcd_fermion_force_xy", C.byref(op), x.h, y.h, 1.0, 0), 10)
+            res[key] = {"ms_outer_product_kernel": t, "GB/s_nominal (links + force + X, Y at the site and its 4 forward neighbours)": (576 + 576 + 2 * (192 if kind == L.WILSON else 48) * 5) * V / t / 1e6}
+        out["ok"] = True
+        out.update(res)
     elif name.startswith("mrhs_") or name == "staggered_mrhs":
         kind = L.STAGGERED if name == "staggered_mrhs" else L.WILSON
         nrhs = 12
