@@ -274,11 +274,20 @@ def _timed(fn, reps):
 
 
 def experiment_child(name, dims):
-    """child process: prints ONE JSON dict on stdout"""
+    """child process: prints ONE JSON dict on stdout (whatever was measured before an error is kept)"""
+    out = {"name": name, "ok": False}
+    try:
+        _experiment_body(name, dims, out)
+    except BaseException as exc:                     # a failed check / library error: report it, keep the partial numbers
+        out["ok"] = False
+        out["error"] = repr(exc)[:300]
+    print("EXPERIMENT " + json.dumps(out), flush=True)
+
+
+def _experiment_body(name, dims, out):
     import numpy as np
     import lqcd_b200 as q
     from lqcd_b200 import _lib as L
-    out = {"name": name, "ok": False}
     ref_file = Path(tempfile.gettempdir()) / f"lqcd_b200_exp_ref_{os.environ.get('LQCD_EXP_TAG', '0')}.npy"
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     small = tuple(int(v) for v in os.environ.get("LQCD_EXP_SMALL", "16x16x16x16").split("x"))     # (tests shrink it under emulation)
@@ -453,7 +462,6 @@ def experiment_child(name, dims):
         out.update({"dH_dtau0.02": dH1, "dH_dtau0.01": dH2, "wall_ms_4_steps": wall * 1e3, "multishift_cg_iters": nit, "poles": len(al)})
     else:
         out["error"] = "unknown experiment"
-    print("EXPERIMENT " + json.dumps(out), flush=True)
 
 
 def run_experiments(lattice, local_rank, budget_s):
