@@ -28,6 +28,21 @@ def pytest_cmdline_main(config):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # Build the CUDA library (nvcc cross-compiles without a GPU; incremental, a no-op when up to date) and the oracle ONCE, in
+    # the controlling process, before any xdist worker starts: workers must never race on a missing / half-written .so.
+    if not os.environ.get("PYTEST_XDIST_WORKER") and os.environ.get("LQCD_TEST_NO_BUILD") != "1":
+        try:
+            import importlib.util
+            import shutil
+            if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
+                spec = importlib.util.spec_from_file_location("lqcd_b200_build", ROOT / "latticeqcd.jl_b200" / "build.py")
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.build()
+            from oracle import oracle as _orc
+            _orc.build()
+        except Exception as exc:          # the tests that need the libraries will say so themselves
+            sys.stderr.write(f"[conftest] pre-build skipped: {exc!r}\n")
 
 
 @pytest.fixture(scope="session")

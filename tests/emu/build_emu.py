@@ -218,6 +218,19 @@ def sources():
 
 
 def build(asan: bool = False, force: bool = False) -> Path:
+    """(re)builds the emulated library if any input is newer; safe to call from several processes at once (pytest-xdist workers):
+    one builds under an exclusive file lock, the others wait and then find it up to date"""
+    import fcntl
+    BUILD.mkdir(parents=True, exist_ok=True)
+    with open(BUILD / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(asan, force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(asan: bool, force: bool) -> Path:
     tag = "_asan" if asan else ""
     srcdir = BUILD / ("src" + tag)
     srcdir.mkdir(parents=True, exist_ok=True)
@@ -250,12 +263,14 @@ def build(asan: bool = False, force: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(cc, units))
-    link = ["g++", "-shared", "-o", str(out), *map(str, objs), "-lrt", "-lm"]
+    tmp = out.with_suffix(".so.tmp")
+    link = ["g++", "-shared", "-o", str(tmp), *map(str, objs), "-lrt", "-lm"]
     if asan:
         link.append("-fsanitize=address")
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    os.replace(tmp, out)
     return out
 
 
