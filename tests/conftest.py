@@ -30,7 +30,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     # Build the CUDA library (nvcc cross-compiles without a GPU; incremental, a no-op when up to date) and the oracle ONCE, in
     # the controlling process, before any xdist worker starts: workers must never race on a missing / half-written .so.
-    if not os.environ.get("PYTEST_XDIST_WORKER") and os.environ.get("LQCD_TEST_NO_BUILD") != "1":
+    # (`-m gpu` runs on the B200 box use the library that travelled with the snapshot: nothing is rebuilt there.)
+    if (not os.environ.get("PYTEST_XDIST_WORKER") and os.environ.get("LQCD_TEST_NO_BUILD") != "1"
+            and getattr(config.option, "markexpr", "") != "gpu"):
         try:
             import importlib.util
             import shutil
