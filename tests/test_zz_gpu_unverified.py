@@ -317,7 +317,7 @@ def test_chiral_condensate_batched(golden_dir, kind):
 
 
 # ---- staggered even-site systems on half fields (csrc/staggered_eo.cu) -----------------------------------------------------------
-@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (16, 4, 4, 8), (32, 4, 2, 2)])
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (16, 4, 4, 8), (32, 4, 2, 2), (24, 4, 4, 4), (12, 6, 4, 4)])
 def test_staggered_even_site_solve_matches_full_lattice_solve(dims):
     """lqcd_solve_staggered_even == the full-lattice CG on an even-site source: same iterates (iteration count within the rounding of
     the reduction order), same solution, zero odd sites; initial guess honoured; == the oracle"""
