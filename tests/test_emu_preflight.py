@@ -193,3 +193,12 @@ def test_bench_headline_path_under_emulation(emu_lib):
     assert "lqcd_dslash_host" in d["e2e"]["call"] and "note" not in d["e2e"]
     assert d["e2e"]["h2d_bytes_per_step"] == 8 * 4 * 4 * 4 * 12 * 16
     assert all(v.get("ok") for v in d["experiments"].values()), d["experiments"]
+
+
+def test_c_example_under_emulation(emu_lib, tmp_path, golden_dir):
+    """examples/propagator.c (plain C client of the ABI) linked against the emulated build: plaquette of the reference's fixture,
+    per-source CGNR iteration counts and the pion correlator equal the oracle's"""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import test_c_example as t
+    exe = t._compile(tmp_path, emu_lib.parent, emu_lib.name)
+    t.check_against_oracle(exe, golden_dir, tmp_path)
