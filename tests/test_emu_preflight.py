@@ -133,6 +133,16 @@ def test_multirank_md_trajectory_under_emulation(emu_lib, action):
     assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_config5_shape_rhmc_trajectory_on_8_ranks_under_emulation(emu_lib):
+    """BASELINE config 5 in miniature: staggered Nf = 2 RHMC trajectory (multi-shift CG + rational force per step) on 8 ranks in the
+    1.1.2.4 process grid bench.py uses at N = 8"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=8", "--master-addr", "127.0.0.1",
+           "--master-port", str(39500 + (os.getpid() % 1000)), "tests/mp_md_worker.py", "4x4x8x16", "1x1x2x4", "rhmc"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="300", OMP_NUM_THREADS="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_multirank_gauge_io_under_emulation(emu_lib):
     """file <-> device links across 4 ranks: block-wise load of ILDG / BridgeText, multi-rank plaquette, collective ILDG save"""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
