@@ -51,11 +51,11 @@ def test_gpu_suite_under_emulation(emu_lib):
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_reference_regressions.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
            "--runxfail", "-p", "no:cacheprovider", "-n", "4",
            "--deselect", "tests/test_gpu_parity.py::test_16_4_size_independent_properties"]      # 2 min under emulation
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_TEST_NTRAJ="2", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4"), capture_output=True, text=True, timeout=1500)
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_TEST_NTRAJ="2", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4", LQCD_TEST_CONFIG1_DIMS="8x4x4x4", LQCD_TEST_CONFIG2_DIMS="12x6x4x4"), capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 140, tail
+    assert m and int(m.group(1)) >= 143, tail
 
 
 def test_gpu_suite_is_schedule_independent_under_emulation(emu_lib):
@@ -65,7 +65,7 @@ def test_gpu_suite_is_schedule_independent_under_emulation(emu_lib):
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q",
            "-x", "--runxfail", "-p", "no:cacheprovider", "-n", "4",
            "-k", "not size_independent and not cgnr_matches_single and not multi_rhs_cg_on and not pipelined_host"]
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_CTA_ORDER="reverse", LQCD_EMU_THREAD_ORDER="reverse", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4"),
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_CTA_ORDER="reverse", LQCD_EMU_THREAD_ORDER="reverse", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4", LQCD_TEST_CONFIG1_DIMS="8x4x4x4", LQCD_TEST_CONFIG2_DIMS="12x6x4x4"),
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     m = re.search(r"(\d+) passed", r.stdout)

@@ -495,3 +495,60 @@ def test_wilson_general_r(dims, r):
     assert np.array_equal(yh, y.to_host())
     with pytest.raises(q.LqcdError, match="r = 1 only"):
         q.shiftedcg_([q.similar(x)], D, x, [0.1])
+
+
+def _env_dims(name, default):
+    import os
+    return tuple(int(v) for v in os.environ.get(name, default).split("x"))
+
+
+def test_config1_16_4_evenodd_cg():
+    """BASELINE config 1 at full size (16^4 Wilson, even-odd preconditioned CG on one GPU): the Schur-preconditioned solve returns the
+    solution of the full system (true residual recomputed with the verified operator), in fewer iterations than the plain solve"""
+    import lqcd_b200 as q
+    dims = _env_dims("LQCD_TEST_CONFIG1_DIMS", "16x16x16x16")            # (the emulated pre-flight shrinks it)
+    ctx = q.get_context(dims)
+    U = q.Initialize_Gaugefields(3, 0, *dims, condition="cold")
+    b = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    params = {"Dirac_operator": "Wilson", "κ": 0.125, "eps_CG": 1e-16, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]}
+    D = q.Dirac_operator(U, b, params)
+    Deo = q.Dirac_operator(U, b, dict(params, evenodd=True))
+    ctx.call("lqcd_gauge_random", 111, 0.3)
+    q.gauss_distribution_fermion_(b, 5)
+    x_full, x_eo, chk = q.similar(b), q.similar(b), q.similar(b)
+    q.clear_fermion_(x_full); q.clear_fermion_(x_eo)
+    i_full = q.solve_DinvX_(x_full, D, b)
+    i_eo = q.solve_DinvX_(x_eo, Deo, b)
+    q.mul_(chk, D, x_eo)
+    q.add_(chk, -1.0, b)
+    assert q.dot(chk, chk).real < 1e-14
+    q.add_(x_eo, -1.0, x_full)
+    assert q.dot(x_eo, x_eo).real < 1e-12 * q.dot(x_full, x_full).real
+    assert i_eo["iters"] < i_full["iters"]
+
+
+def test_config2_24_4_staggered_nf4_trajectory():
+    """BASELINE config 2 at full size (24^4 staggered Nf = 4 HMC on one GPU, test_staggered.toml integrator): device-resident
+    trajectories with the even-site action on half fields conserve H at O(dtau^2), keep the links in SU(3), and the half-field
+    and full-lattice solvers give the same Delta H"""
+    import lqcd_b200 as q
+    dims = _env_dims("LQCD_TEST_CONFIG2_DIMS", "24x24x24x24")
+    ctx = q.get_context(dims)
+    U0 = q.Initialize_Gaugefields(3, 0, *dims, condition="cold")
+    x = q.Initialize_pseudofermion_fields(U0[0], "staggered")
+    D = q.Dirac_operator(U0, x, {"Dirac_operator": "staggered", "mass": 0.5, "eps_CG": 1e-18, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]})
+    ctx.call("lqcd_gauge_random", 111, 0.2)
+    warm = q.get_links(ctx)                                   # synthetic warm start (there is no thermalised 24^4 fixture)
+    dH = {}
+    for half in (True, False):
+        for dtau, steps in ((0.02, 4), (0.01, 8)):
+            U = q.gaugefields_from_array(warm.copy())
+            fa = q.FermiAction(D, {"Nf": 4, "half_field_solver": half})
+            acc, d, info = q.hmc_update_(U, 5.7, dtau, steps, fa=fa, rng=np.random.default_rng(4))
+            dH[(half, dtau)] = d
+            assert info["cg_iters"] > 0
+            if acc:
+                M = U.data.reshape(-1, 3, 3)[:: max(1, U.data.size // 9 // 4096)]
+                assert np.abs(np.einsum("nij,nkj->nik", M, M.conj()) - np.eye(3)).max() < 1e-9
+    assert 2.5 < dH[(True, 0.02)] / dH[(True, 0.01)] < 6.0, dH
+    assert abs(dH[(True, 0.02)] - dH[(False, 0.02)]) < 1e-6 * max(1.0, abs(dH[(False, 0.02)])), dH
