@@ -55,3 +55,31 @@ def test_bad_arguments_are_reported_not_crashed():
     p = (ctypes.c_int * 4)(1, 1, 1, 3)
     st = lib.lqcd_ctx_create(d, p, 0, 0, ctypes.byref(out))
     assert st != 0 and lib.lqcd_last_error(None)
+
+
+def test_null_handles_are_argument_errors_everywhere():
+    """every entry point that takes a context must answer a NULL context (and NULL operands) with LQCD_ERR_ARG and a message --
+    never a crash -- so a binding mistake on the Julia side surfaces as error(...) (SURVEY.md 8b "Errors")"""
+    lib = _lib.load()
+    skip = {"lqcd_last_error", "lqcd_abi_version", "lqcd_decompose", "lqcd_io_read_gauge", "lqcd_io_write_gauge", "lqcd_ctx_create", "lqcd_ctx_destroy"}
+    for name, (res, args) in sorted(_lib.SIGNATURES.items()):
+        if name in skip:
+            continue
+        vals = []
+        for a in args:
+            if a in (ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t):
+                vals.append(a(1))
+            elif a is ctypes.c_double:
+                vals.append(a(1.0))
+            else:
+                vals.append(None)                      # every pointer NULL, the context included
+        st = getattr(lib, name)(*vals)
+        if name in ("lqcd_fermion_free", "lqcd_host_unregister"):       # releasing nothing is fine (finalizers)
+            assert st in (0, _lib.ERR_ARG), (name, st)
+            continue
+        assert st == _lib.ERR_ARG, (name, st)
+        assert lib.lqcd_last_error(None), name
+    assert lib.lqcd_ctx_destroy(None) == 0              # destroying nothing is fine (finalizers)
+    d = (ctypes.c_int * 4)(4, 4, 4, 4)
+    assert lib.lqcd_io_read_gauge(None, 0, d, 3, None, 0) == _lib.ERR_ARG
+    assert lib.lqcd_io_write_gauge(b"/nonexistent/dir/x.ildg", 0, d, 3, None, 0) == _lib.ERR_ARG
