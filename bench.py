@@ -19,6 +19,11 @@ synthetic hot SU(3) links generated on the device (seed 111) and a Gaussian sour
   cpu_baseline / --impl reference: the CPU oracle (oracle/lqcd_oracle.c, a restatement of the reference's
              Julia CPU path; the reference itself is Julia and cannot run here) on all host threads.
 
+  experiments  NOT part of the headline: after everything above is measured, code paths that were written while no B200 was
+             reachable (t-marching / persistent / multi-RHS / shared-memory-link kernels, clover, even-odd and half-field
+             solves, device-resident MD and RHMC trajectories; at N > 1 the multi-GPU knobs) are timed and self-checked in
+             isolated child processes with a time budget (LQCD_BENCH_EXPERIMENTS=0 switches the leg off).
+
 N > 1 (torchrun): strong scaling -- the 32^4 lattice is split along T (then Z) over the ranks.
 """
 import argparse
