@@ -221,7 +221,19 @@ struct B200FermiAction
     _temporary_fermionfields::Vector{Any}        # src/md/standardMD.jl:50 does similar(fermi_action._temporary_fermionfields[1])
     parameters_action::Dict
 end
-FermiAction(D::B200Dirac{:D}, parameters_action) = B200FermiAction(D, [similar(D.cpu_template) for _ = 1:4], parameters_action)
+"FermiAction(D, parameters_action) -- src/system/universe.jl:138; staggered Nf not in {4, 8} -> rational HMC like upstream (README.md:132)"
+function FermiAction(D::B200Dirac{:D}, parameters_action)
+    temps = [similar(D.cpu_template) for _ = 1:4]
+    Nf = get(parameters_action, "Nf", D.op.kind == STAGGERED ? 8 : 2)
+    (D.op.kind == STAGGERED && !(Nf in (4, 8))) || return B200FermiAction(D, temps, parameters_action)
+    # partial fractions x^p ~ c0 + sum_j c[j] / (x + s[j]) on the spectrum of D^dag D, [m^2, m^2 + 16]: upstream takes them from
+    # AlgRemez_jll; any (c0, c, s) triple of that form works -- passed in as parameters_action["rational_action"] (p = -Nf/8)
+    # and ["rational_heatbath"] (p = +Nf/16), e.g. computed once with lqcd_b200/rhmc.py:rational_approx.
+    haskey(parameters_action, "rational_action") && haskey(parameters_action, "rational_heatbath") ||
+        error("B200 RHMC: parameters_action needs \"rational_action\" and \"rational_heatbath\" = (c0, c::Vector, s::Vector)")
+    a0, a, b = parameters_action["rational_action"]; h0, h, hb = parameters_action["rational_heatbath"]
+    return B200RHMCAction(D, Float64(a0), Float64.(a), Float64.(b), Float64(h0), Float64.(h), Float64.(hb), temps)
+end
 
 # staggered Nf = 4: even-site pseudofermions (odd sites zeroed after the Gaussian sampling and after D^dag) [UPSTREAM-RECALL,
 # SURVEY.md App. C.7]; Nf = 8 and Wilson: all sites.  Other staggered Nf -> B200RHMCAction below.
@@ -289,8 +301,28 @@ end
 # force sum_j a[j] * force(X_j, Y_j) is accumulated on the device, X_j from ONE lqcd_multishift_cg, Y_j = D X_j.
 struct B200RHMCAction
     D::B200Dirac{:D}
-    a0::Float64; a::Vector{Float64}; b::Vector{Float64}          # action approximation, b ascending
+    a0::Float64; a::Vector{Float64}; b::Vector{Float64}          # action approximation x^(-Nf/8), b ascending
+    h0::Float64; h::Vector{Float64}; hb::Vector{Float64}         # heat-bath approximation x^(+Nf/16)
     _temporary_fermionfields::Vector{Any}
+end
+
+"y = c0 x + sum_j c[j] (D^dag D + s[j])^-1 x with ONE multi-shift CG on the device (lqcd_rational_apply); returns Re<x, y>"
+function rational_apply!(y, D::B200Dirac, x, c0, c, s)
+    dx, dy = D.scratch[1], D.scratch[2]
+    upload!(dx, x)
+    iters = Ref{Cint}(0); d = Ref{Cdouble}(0.0)
+    check(D.ctx.h, ccall((:lqcd_rational_apply, LIB), Cint,
+        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
+        D.ctx.h, D.op, dy.h, dx.h, c0, c, s, length(c), D.eps, D.maxsteps, iters, d))
+    download!(y, dy)
+    return d[]
+end
+"gauss_sampling_in_action!(xi, U, fa) -- src/md/standardMD.jl:95"
+gauss_sampling_in_action!(ξ, U, fa::B200RHMCAction) = LatticeDiracOperators.gauss_distribution_fermion!(ξ)     # [UPSTREAM-RECALL]
+"sample_pseudofermions!(eta, U, fa, xi): eta = (D^dag D)^{Nf/16} xi -- src/md/standardMD.jl:96"
+function sample_pseudofermions!(η, U, fa::B200RHMCAction, ξ)
+    rational_apply!(η, fa.D(U), ξ, fa.h0, fa.h, fa.hb)
+    return η
 end
 
 function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200RHMCAction, U, η)
@@ -305,15 +337,7 @@ function calc_UdSfdU!(UdSfdU::Vector{<:AbstractGaugefields{3,4}}, fa::B200RHMCAc
     return nothing
 end
 "evaluate_FermiAction(fa, U, eta) = eta^dag r(D^dag D) eta, r ~ x^(-Nf/8): one multi-shift CG on the device"
-function evaluate_FermiAction(fa::B200RHMCAction, U, η)
-    D = fa.D(U)
-    dη = D.scratch[1]; upload!(dη, η)
-    iters = Ref{Cint}(0); S = Ref{Cdouble}(0.0)
-    check(D.ctx.h, ccall((:lqcd_rational_apply, LIB), Cint,
-        (Ptr{Cvoid}, Ref{LqcdOp}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
-        D.ctx.h, D.op, D.scratch[2].h, dη.h, fa.a0, fa.a, fa.b, length(fa.b), D.eps, D.maxsteps, iters, S))
-    return S[]
-end
+evaluate_FermiAction(fa::B200RHMCAction, U, η) = rational_apply!(fa._temporary_fermionfields[1], fa.D(U), η, fa.a0, fa.a, fa.b)
 
 # ---- gauge configurations in the reference's file formats straight to / from the device links (csrc/gauge_io.cu) -----------------
 # `initial = "<file>"` + loadU_format (universe.jl:62-68) and saveU_format (lqcd.jl:236-242).  The host-array forms
