@@ -212,3 +212,14 @@ def test_c_example_under_emulation(emu_lib, tmp_path, golden_dir):
     import test_c_example as t
     exe = t._compile(tmp_path, emu_lib.parent, emu_lib.name)
     t.check_against_oracle(exe, golden_dir, tmp_path)
+
+
+def test_bench_watchdog_prints_the_headline_if_the_experiments_leg_overruns(emu_lib):
+    import json
+    r = subprocess.run([sys.executable, "tests/bench_emu_harness.py", "--lattice", "8x4x4x4", "--steps", "3", "--warmup", "1", "--cg-iters", "5"],
+                       cwd=ROOT, env=_env(emu_lib, LQCD_EXP_SMALL="4x4x4x4", LQCD_BENCH_WATCHDOG_S="2"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and "watchdog" in d["experiments"]["error"]
