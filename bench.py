@@ -842,7 +842,8 @@ def run_b200(args, dims):
     want = os.environ.get("LQCD_BENCH_EXPERIMENTS", "1") != "0"
     budget = float(os.environ.get("LQCD_BENCH_EXPERIMENTS_S", "240"))
     watchdog = None
-    if want and rank == 0:
+    if want:
+        # (every rank arms it: a rank that is stuck behind a lost peer must not keep the launcher waiting either)
         # if the experiments leg (child processes, at N > 1 also barriers between the parents) overruns badly, the measured line is
         # printed without it and the process ends: the headline can never be lost to the diagnostics
         def overrun():
