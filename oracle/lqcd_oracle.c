@@ -604,6 +604,80 @@ void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4
     }
 }
 
+/* ---- clover-term part of the pseudofermion force (new capability like the clover term itself; groundwork for the device kernel).
+ *      S_f = phi^dag (M^dag M)^-1 phi, M = A - kappa H, X = (M^dag M)^-1 phi, Y = M X:  dS = -2 Re[Y^dag dM X].  The hopping part
+ *      is orc_wilson_force (it never sees A); the clover part is
+ *          -2 Re sum_n Y(n)^dag dA(n) X(n),   dA = kappa csw sum_p sigma_p (x) i dF^_p,   F^_p = (Q_p - Q_p^dag)/8 - trace,
+ *      = -2 Re sum_{n,p} (i c / 8) tr[ dQ_p(n) K_p(n) ],   K = Lambda' + Lambda'^dag,  Lambda'= Lambda - tr(Lambda)/3,
+ *        Lambda_p(n)[b,a] = sum_{al,be} sigma_p[al,be] X(n)[be,b] conj(Y(n)[al,a]).
+ *      Q_p is the sum of the four leaves of orc_clover_build; varying U_rho(m) -> exp(eps A) U_rho(m) inside a leaf
+ *      L1 L2 L3 L4 (closed at n) gives tr[A U S K P] for a forward link (P = links before it, S = links after it) and
+ *      -tr[A S K P U^dag] for a backward one, so with G the sum of those matrices  dS = -2 Re tr[A (i c / 8) G]:
+ *      out_rho(m) += (i c / 8) G_rho(m) in the convention of orc_wilson_force (dS/d eps = -2 Re tr[A out]).  Serial scatter. */
+void orc_clover_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y) {
+    geom g = mkgeom(op->dims);
+    const int64_t V = g.V;
+    const double coef = op->kappa * op->csw;
+    zc gam[4][4][4], sig[6][4][4];
+    for (int mu = 0; mu < 4; mu++) for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++)
+        gam[mu][a][b] = 0.5 * (op->rplusg[mu][a][b] - op->rminusg[mu][a][b]);
+    int pl = 0;
+    for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++, pl++)
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) {
+            zc s = 0;
+            for (int k = 0; k < 4; k++) s += gam[mu][a][k] * gam[nu][k][b] - gam[nu][a][k] * gam[mu][k][b];
+            sig[pl][a][b] = 0.5 * I * s;
+        }
+    for (int64_t n = 0; n < V; n++) {
+        int c0[4]; site_coords(&g, n, c0);
+        int p = 0;
+        for (int mu = 0; mu < 4; mu++) for (int nu = mu + 1; nu < 4; nu++, p++) {
+            zc K[9];
+            {   /* Lambda[b + 3 a] (row b, column a), traceless part, plus its adjoint */
+                zc Lm[9], tr = 0;
+                for (int b = 0; b < 3; b++) for (int a = 0; a < 3; a++) {
+                    zc s = 0;
+                    for (int al = 0; al < 4; al++) for (int be = 0; be < 4; be++)
+                        s += sig[p][al][be] * X[b + 3 * (n + V * be)] * conj(Y[a + 3 * (n + V * al)]);
+                    Lm[b + 3 * a] = s;
+                }
+                for (int a = 0; a < 3; a++) tr += Lm[a + 3 * a];
+                for (int a = 0; a < 3; a++) Lm[a + 3 * a] -= tr / 3.0;
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[i + 3 * j] = Lm[i + 3 * j] + conj(Lm[j + 3 * i]);
+            }
+            const int dirs[4][4] = {{mu, nu, mu, nu}, {nu, mu, nu, mu}, {mu, nu, mu, nu}, {nu, mu, nu, mu}};
+            const int sgns[4][4] = {{+1, +1, -1, -1}, {+1, -1, -1, +1}, {-1, -1, +1, +1}, {-1, +1, +1, -1}};
+            for (int leaf = 0; leaf < 4; leaf++) {
+                zc Lk[4][9], P[5][9], S[5][9];
+                int64_t site[4]; int dg[4];
+                int c[4] = {c0[0], c0[1], c0[2], c0[3]};
+                int64_t s = n;
+                for (int k = 0; k < 4; k++) {
+                    const int d = dirs[leaf][k];
+                    if (sgns[leaf][k] > 0) { site[k] = s; dg[k] = 0; memcpy(Lk[k], u[d] + 9 * s, sizeof Lk[k]); s = hopsite(&g, s, c, d, +1); }
+                    else {
+                        s = hopsite(&g, s, c, d, -1); site[k] = s; dg[k] = 1;
+                        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Lk[k][i + 3 * j] = conj(u[d][9 * s + j + 3 * i]);
+                    }
+                }
+                const zc one[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                memcpy(P[0], one, sizeof one); memcpy(S[4], one, sizeof one);
+                for (int k = 0; k < 4; k++) mulx(P[k + 1], P[k], 0, Lk[k], 0);            /* P[k] = L_1 .. L_k */
+                for (int k = 3; k >= 0; k--) mulx(S[k], Lk[k], 0, S[k + 1], 0);            /* S[k] = L_{k+1} .. L_4 */
+                for (int k = 0; k < 4; k++) {
+                    zc t1[9], R[9], G[9];
+                    mulx(t1, S[k + 1], 0, K, 0);
+                    mulx(R, t1, 0, P[k], 0);                                               /* (links after) K (links before) */
+                    if (!dg[k]) mulx(G, Lk[k], 0, R, 0);                                   /* U R */
+                    else { mulx(G, R, 0, Lk[k], 0); for (int i = 0; i < 9; i++) G[i] = -G[i]; }     /* -R U^dag */
+                    zc *o = out[dirs[leaf][k]] + 9 * site[k];
+                    for (int i = 0; i < 9; i++) o[i] += (I * coef / 8.0) * G[i];
+                }
+            }
+        }
+    }
+}
+
 /* ---- even-odd preconditioned Wilson solve (see lqcd_oracle.h) ---- */
 int orc_eo_solve(const orc_op *op, int method, int dagger, zc *x, const zc *const u[4], const zc *b,
                  double eps, int maxsteps, double *resid_sq, double *hist) {

@@ -104,6 +104,8 @@ void orc_staggered_force(const orc_op *op, zc *const out[4], const zc *const u[4
 /* clover term A(n) (see orc_op.csw): clov[site*72 + blk*36 + i + 6*j].  fmunu (nullable, V*6*9, plane order
  * (0,1),(0,2),(0,3),(1,2),(1,3),(2,3), [a + 3 b]) receives F^_mu_nu for tests. */
 void orc_clover_build(const orc_op *op, zc *clov, zc *fmunu, const zc *const u[4]);
+/* clover-term part of the pseudofermion force, ADDED to out (same convention as orc_wilson_force); see lqcd_oracle.c */
+void orc_clover_force(const orc_op *op, zc *const out[4], const zc *const u[4], const zc *X, const zc *Y);
 
 /* gauge-sector molecular dynamics steps (src/md/AbstractMD.jl:78-135): momenta p[mu][a + 3*(b + 3*site)] are anti-Hermitian
  * traceless matrices; see the block comment in lqcd_oracle.c for the conventions. */

@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L.orc_plaquette.argtypes = [C.POINTER(ci), pp]; L.orc_plaquette.restype = dbl
         L.orc_wilson_force.argtypes = [op, pp, pp, vp, vp]
         L.orc_staggered_force.argtypes = [op, pp, pp, vp, vp]
+        L.orc_clover_force.argtypes = [op, pp, pp, vp, vp]
         L.orc_clover_build.argtypes = [op, vp, vp, pp]
         L.orc_eo_solve.argtypes = [op, ci, ci, vp, pp, vp, dbl, ci, C.POINTER(dbl), vp]
         L.orc_eo_solve.restype = ci
@@ -239,9 +240,12 @@ def md_momenta(dims, seed=1) -> np.ndarray:
 
 
 def force(op, kind, U, X, Y) -> np.ndarray:
+    """UdSfdU for X = (D^dag D)^-1 phi, Y = D X.  Wilson-clover (op.csw != 0): hopping part + clover-term part."""
     out = np.zeros_like(U)
     fn = lib().orc_wilson_force if kind == WILSON else lib().orc_staggered_force
     fn(C.byref(op), _uptrs(out), _uptrs(U), _chk(X), _chk(Y))
+    if kind == WILSON and op.csw != 0.0:
+        lib().orc_clover_force(C.byref(op), _uptrs(out), _uptrs(U), _chk(X), _chk(Y))
     return out
 
 

@@ -152,3 +152,45 @@ def test_device_packing_and_apply_emulation():
             out[2 * b + i // 3, :, i % 3] = yv[i]
     want = psi + np_ref.clover_term(U, psi, KAPPA, CSW)
     assert np.abs(out.reshape(psi.shape) - want).max() < 1e-13
+
+
+def _expm_antiherm(A):
+    w, V = np.linalg.eigh(1j * A)
+    return (V * np.exp(-1j * w)) @ V.conj().T
+
+
+def test_clover_force_finite_difference():
+    """Wilson-clover pseudofermion force (hopping part + clover-term part, oracle): dS_f/d eps = -2 Re tr[A F_mu(n)] for
+    U_mu(n) -> exp(eps A) U_mu(n) with S_f = phi^dag (M^dag M)^-1 phi and the clover term REBUILT on the varied links --
+    pins leaf orientation, sigma_mu_nu convention and the i c / 8 weight of the clover-term derivative (groundwork for the
+    device kernel: the force entry points still reject csw != 0)"""
+    dims = (4, 4, 4, 4)
+    U = orc.random_su3(dims, seed=33, eps=0.35)
+    phi = orc.gaussian_field(dims, orc.WILSON, seed=34)
+
+    def action(Ux):
+        op = orc.make_op(dims, kappa=0.11, csw=CSW)
+        orc.clover_build(op, Ux)
+        r = orc.cg(op, orc.WILSON, Ux, phi, eps=1e-24)
+        assert r["converged"]
+        return np.vdot(phi, r["x"]).real, r["x"], op
+
+    S0, X, op = action(U)
+    Y = orc.apply(op, orc.WILSON, orc.D, U, X)
+    F = orc.force(op, orc.WILSON, U, X, Y)
+    op0 = orc.make_op(dims, kappa=0.11)
+    F_hop = orc.force(op0, orc.WILSON, U, X, Y)
+    assert np.abs(F - F_hop).max() > 1e-3 * np.abs(F_hop).max()         # the clover part is not negligible here
+    rng = np.random.default_rng(7)
+    for (mu, t, z, y, x) in [(0, 0, 0, 0, 0), (3, 3, 1, 2, 0), (1, 2, 3, 3, 3), (2, 1, 1, 1, 1)]:
+        H = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+        A = (H - H.conj().T) / 2
+        A -= np.trace(A) / 3 * np.eye(3)
+        want = -2 * np.real(np.trace(A @ F[mu, t, z, y, x].T))
+        h, vals = 1e-5, []
+        for sgn in (+1, -1):
+            U2 = U.copy()
+            U2[mu, t, z, y, x] = (_expm_antiherm(sgn * h * A) @ U[mu, t, z, y, x].T).T
+            vals.append(action(np.ascontiguousarray(U2))[0])
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - want) < 2e-6 * max(1.0, abs(want)), (fd, want)
