@@ -206,7 +206,8 @@ int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[],
 /* ---- fermion force: calc_UdSfdU!(UdSfdU, fermi_action, U, eta) (AbstractMD.jl:129) ---------------
  * Given eta: X = (DdagD)^-1 eta by CG, Y = D X, then the 4 link-shaped outer-product fields are written
  * to the host arrays out_mu (same layout as the links, wing width ndw; the halo is zero-filled).
- * x_inout (nullable) is X (initial guess / result). */
+ * x_inout (nullable) is X (initial guess / result).  Wilson-clover (op->csw != 0): hopping part + clover-term derivative
+ * (csrc/clover_force.cu; single rank). */
 int lqcd_fermion_force(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *eta, lqcd_fermion *x_inout,
                        double eps, int maxsteps, double *const out_mu[4], int ndw, int *iters, double *action);
 /* The bilinear part alone, for rational actions (RHMC, staggered Nf not in {4, 8}: README.md:132, test/test_Nf2.toml):

@@ -130,6 +130,12 @@ static void make_sigma(CloverSigma &S) {
                     }
 }
 
+void clover_sigma_tables(cplx (*out)[2][2][2]) {            // clover_force.cu
+    CloverSigma S;
+    make_sigma(S);
+    memcpy(out, S.s, sizeof S.s);
+}
+
 int comm_link_view(lqcd_ctx *ctx, const cplx **bases);     // comm.cu: every rank's link array (peer mapped); error if unavailable
 
 int ensure_clover(lqcd_ctx *ctx, const lqcd_op *op) {

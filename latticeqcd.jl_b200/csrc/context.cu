@@ -97,7 +97,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     ctx->gauge = nullptr; ctx->gauge_valid = false; ctx->stage = nullptr; ctx->stage_bytes = 0;
     ctx->flush = nullptr; ctx->flush_bytes = 0; ctx->launches = 0; ctx->comm = nullptr; ctx->force_buf = nullptr; ctx->force_valid = false; ctx->mom = nullptr; ctx->mom_valid = false;
     ctx->eo = nullptr; ctx->eo_active = 0; ctx->stag_even_solve = 0; ctx->pipe = nullptr; ctx->queue = nullptr; ctx->mrhs = nullptr;
-    ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
+    ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_k = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
     CT(cudaSetDevice(device));
@@ -151,7 +151,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     mrhs_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) if (f) { cudaFree(f->d); delete f; }
-    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover);
+    cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover); cudaFree(ctx->clover_k);
     cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);

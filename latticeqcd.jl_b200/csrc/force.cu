@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(128) force_pack_kernel(const ForceArgs A, int 
 
 int download_links_from(lqcd_ctx *ctx, const cplx *dev_links, double *const U_mu[4], int ndw);     // context.cu
 int comm_check_error(lqcd_ctx *ctx);                                                                // comm.cu
+int clover_force_accumulate(lqcd_ctx *ctx, const lqcd_op *op, const cplx *X, const cplx *Y, double weight);   // clover_force.cu
 
 // F <- [F +] coef * force(X, Y) into the device-resident link-shaped buffer (RHMC: sum_j alpha_j force(X_j, Y_j) without
 // leaving the GPU).  Collective across ranks.  `barrier_with`: field whose <.,X> reduction closes the call (see header).
@@ -279,6 +280,7 @@ static int force_outer(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion *X, 
     }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (op->kind == LQCD_WILSON && op->csw != 0.0) LQCD_TRY(clover_force_accumulate(ctx, op, X->d, Y->d, coef));      // clover_force.cu
     ctx->force_valid = true;
     // <dot_with, X> (global).  Across ranks this reduction also ORDERS the force slots: it is enqueued after the force
     // kernel and its all-reduce completes only when every rank has got this far, so it runs on every multi-rank call.
@@ -296,7 +298,7 @@ static int check_force_args(lqcd_ctx *ctx, const lqcd_op *op, const lqcd_fermion
     if (a->owner != ctx || b->owner != ctx) return lqcd_fail(ctx, LQCD_ERR_ARG, "field belongs to another context");
     if (a->kind != op->kind || b->kind != op->kind) return lqcd_fail(ctx, LQCD_ERR_ARG, "fermion kind does not match the operator");
     if (op->kind == LQCD_WILSON && op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force implements r = 1 only");
-    if (op->kind == LQCD_WILSON && op->csw != 0.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: the clover-term derivative is not implemented (csw must be 0)");
+    if (op->kind == LQCD_WILSON && op->csw != 0.0 && ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: the clover-term derivative is implemented for a single rank (csw must be 0 across ranks)");
     if (!ctx->gauge_valid) return lqcd_fail(ctx, LQCD_ERR_STATE, "force requested before lqcd_gauge_upload");
     return LQCD_OK;
 }

@@ -164,6 +164,7 @@ struct lqcd_ctx {
     uint64_t gauge_epoch;      // bumped by every lqcd_gauge_upload / lqcd_gauge_random
     cplx *clover;              // packed clover term (clover.cu), valid for (clover_epoch, clover_coef)
     uint64_t clover_epoch; double clover_coef;
+    cplx *clover_k;            // K_p(n) field of the clover-term force (clover_force.cu), allocated on first use
     uint64_t launches;
     int num_sms;
     mutable std::string err;

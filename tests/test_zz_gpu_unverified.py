@@ -552,3 +552,41 @@ def test_config2_24_4_staggered_nf4_trajectory():
                 assert np.abs(np.einsum("nij,nkj->nik", M, M.conj()) - np.eye(3)).max() < 1e-9
     assert 2.5 < dH[(True, 0.02)] / dH[(True, 0.01)] < 6.0, dH
     assert abs(dH[(True, 0.02)] - dH[(False, 0.02)]) < 1e-6 * max(1.0, abs(dH[(False, 0.02)])), dH
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4)])
+def test_clover_force_matches_oracle(dims):
+    """calc_UdSfdU! for the Wilson-clover action: hopping part + clover-term part (csrc/clover_force.cu, gather form) against the
+    oracle's scatter form, which is pinned by finite differences (tests/test_clover.py)"""
+    q, Uh, U, x, D, op, clov = _clover_setup(dims, 0.11)
+    fa = q.FermiAction(D, {})
+    eta_h = orc.gaussian_field(dims, orc.WILSON, seed=29)
+    eta = q.similar(x).from_host(eta_h)
+    F = np.zeros_like(Uh)
+    info = q.calc_UdSfdU_(F, fa, U, eta)
+    ref = orc.cg(op, orc.WILSON, Uh, eta_h, eps=1e-20)
+    assert info["iters"] == ref["iters"]
+    Fr = orc.force(op, orc.WILSON, Uh, ref["x"], orc.apply(op, orc.WILSON, orc.D, Uh, ref["x"]))
+    op0 = orc.make_op(dims, kappa=0.11)
+    Fhop = orc.force(op0, orc.WILSON, Uh, ref["x"], orc.apply(op, orc.WILSON, orc.D, Uh, ref["x"]))
+    assert np.abs(Fr - Fhop).max() > 1e-3 * np.abs(Fr).max()              # the clover part matters in this check
+    assert np.abs(F - Fr).max() < 1e-9 * np.abs(Fr).max()
+
+
+def test_wilson_clover_hmc_trajectory():
+    """device-resident Sexton-Weingarten trajectories with the Wilson-clover action (the reference's disabled test_wilsonclover.jl
+    setup: kappa = 0.141139, c_SW = 1.5612): Delta H = O(dtau^2) -- the relative weight of the clover-term force is right"""
+    import lqcd_b200 as q
+    dims = (4, 4, 4, 4)
+    Uh = orc.random_su3(dims, seed=37, eps=0.3)
+    dH = {}
+    for dtau, steps in ((0.04, 4), (0.02, 8)):
+        U = q.gaugefields_from_array(Uh.copy())
+        x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+        D = q.Dirac_operator(U, x, {"Dirac_operator": "WilsonClover", "κ": 0.12, "Clover_coefficient": CSW, "eps_CG": 1e-20, "MaxCGstep": 3000,
+                                    "boundarycondition": [1, 1, 1, -1]})
+        fa = q.FermiAction(D, {})
+        acc, d, info = q.hmc_update_(U, 5.7, dtau, steps, fa=fa, SextonWeingargten=True, Nsw=4, rng=np.random.default_rng(8))
+        dH[dtau] = d
+        assert info["cg_iters"] > 0
+    assert abs(dH[0.04]) < 1.0 and 2.5 < dH[0.04] / dH[0.02] < 6.0, dH
