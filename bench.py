@@ -343,8 +343,8 @@ def _experiment_body(name, dims, out):
         out.update({"cg_iters_per_s": it.value / dt, "cg_resid_sq_after_60": rs.value})
     elif name == "force":
         res = {}
-        for kind, key in ((L.WILSON, "wilson"), (L.STAGGERED, "staggered")):
-            ctx, op, x, y = setup(dims, kind=kind, eps=0.3)
+        for kind, key, csw in ((L.WILSON, "wilson", 0.0), (L.STAGGERED, "staggered", 0.0), (L.WILSON, "wilson_clover (hopping + clover-term kernels)", 1.5612)):
+            ctx, op, x, y = setup(dims, kind=kind, eps=0.3, csw=csw)
             ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)                    # some (X, Y) pair: the kernel's cost does not depend on it
             t = _timed(lambda: ctx.call("lqcd_fermion_force_xy", C.byref(op), x.h, y.h, 1.0, 0), 10)
             res[key] = {"ms_outer_product_kernel": t, "GB/s_nominal (links + force + X, Y at the site and its 4 forward neighbours)": (576 + 576 + 2 * (192 if kind == L.WILSON else 48) * 5) * V / t / 1e6}
