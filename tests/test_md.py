@@ -24,6 +24,8 @@ def _traj(U, P, dtau, n, nsw=0, fermion=None):
 
     def pf(eps):
         op, kind, eta = fermion[:3]
+        if kind == orc.WILSON and op.csw != 0.0:
+            orc.clover_build(op, U)                 # the clover term follows the links
         if len(fermion) == 4:              # RHMC: fermion[3] = rational approximation of the action (alpha_j, beta_j)
             ra = fermion[3]
             xs = orc.mscg(op, kind, U, eta, list(ra.beta), eps=1e-22, maxsteps=5000)["xs"]
@@ -59,8 +61,29 @@ def _H(U, P, fermion=None):
         H += np.vdot(eta, ra.alpha0 * eta + sum(a * X for a, X in zip(ra.alpha, xs))).real
     elif fermion:
         op, kind, eta = fermion
+        if kind == orc.WILSON and op.csw != 0.0:
+            orc.clover_build(op, U)
         H += np.vdot(eta, orc.cg(op, kind, U, eta, eps=1e-22)["x"]).real
     return H
+
+
+def test_wilson_clover_leapfrog_energy_scaling(Uw):
+    """Wilson-clover pseudofermions (the reference's disabled test_wilsonclover.jl physics: c_SW = 1.5612): with the hopping AND
+    the clover-term force the leapfrog conserves H at O(dtau^2) on the oracle"""
+    op = orc.make_op(DIMS, kappa=0.12, csw=1.5612)
+    orc.clover_build(op, Uw)
+    xi = orc.gaussian_field(DIMS, orc.WILSON, seed=9)
+    eta = orc.apply(op, orc.WILSON, orc.DDAG, Uw, xi)
+    P0 = orc.md_momenta(DIMS, seed=4)
+    f = (op, orc.WILSON, eta)
+    H0 = _H(Uw, P0, f)
+    assert abs(H0 - (orc.md_kinetic(DIMS, P0) + orc.md_gauge_action(DIMS, Uw, BETA) + np.vdot(xi, xi).real)) < 1e-8 * abs(H0)
+    dH = []
+    for dtau, n in ((0.05, 6), (0.025, 12), (0.0125, 24)):
+        U1, P1 = _traj(Uw, P0, dtau, n, nsw=0, fermion=f)
+        dH.append(_H(U1, P1, f) - H0)
+    print("dH", dH)
+    assert abs(dH[0]) < 1.0 and 2.5 < dH[0] / dH[1] < 6.0 and 3.0 < dH[1] / dH[2] < 5.0
 
 
 def _rational_nf2():
