@@ -4,8 +4,9 @@ set -x
 mkdir -p gpurun_out
 # 1. every GPU test incl. the staged ones as plain tests (a device fault in one must not hide the rest: one process per file)
 for f in tests/test_gpu_parity.py tests/test_rhmc.py tests/test_md.py tests/test_gauge_io.py tests/test_reference_regressions.py tests/test_zz_gpu_unverified.py tests/test_multirank.py; do
-  LQCD_STAGED_BUDGET_S=100000 timeout 900 python -m pytest $f -m gpu -q -rA --runxfail -p no:cacheprovider 2>&1 | tail -80 > gpurun_out/tests_$(basename $f .py).txt
+  LQCD_STAGED_BUDGET_S=100000 timeout 900 python -m pytest $f -m gpu -q -rA --runxfail -p no:cacheprovider 2>&1 | tail -400 > gpurun_out/tests_$(basename $f .py).txt
 done
+python tools/staged_report.py gpurun_out/tests_*.txt > gpurun_out/staged_report.txt 2>&1
 # 2. headline bench with the experiments leg (first timings of kernel 3, persistent CTAs, multi-RHS R = 2 / 3 / 4, clover, even-odd, MD)
 LQCD_BENCH_EXPERIMENTS_S=400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_with_experiments.json 2> gpurun_out/bench_with_experiments.err
 python tools/check_kernel3.py 2>&1 | tee gpurun_out/kernel3.txt                       # experimental t-march kernel
