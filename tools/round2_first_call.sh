@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 # 1. every GPU test incl. the staged ones as plain tests (a device fault in one must not hide the rest: one process per file)
-for f in tests/test_gpu_parity.py tests/test_rhmc.py tests/test_md.py tests/test_gauge_io.py tests/test_reference_regressions.py tests/test_zz_gpu_unverified.py tests/test_multirank.py; do
+for f in tests/test_gpu_parity.py tests/test_rhmc.py tests/test_md.py tests/test_gauge_io.py tests/test_reference_regressions.py tests/test_c_example.py tests/test_zz_gpu_unverified.py tests/test_multirank.py; do
   LQCD_STAGED_BUDGET_S=100000 timeout 900 python -m pytest $f -m gpu -q -rA --runxfail -p no:cacheprovider 2>&1 | tail -400 > gpurun_out/tests_$(basename $f .py).txt
 done
 python tools/staged_report.py gpurun_out/tests_*.txt > gpurun_out/staged_report.txt 2>&1
