@@ -198,7 +198,8 @@ int lqcd_gauge_save(lqcd_ctx *ctx, const char *path, int format);
  *                          per right-hand side bit-identical to lqcd_solve) or CG (target DdagD); BICGSTAB runs the right-hand
  *                          sides one after the other.  iters / resid_sq: arrays of nrhs (nullable).  LQCD_ERR_NOCONV if any
  *                          right-hand side did not converge (the arrays are filled for all of them).
- *      Several ranks, csw != 0: the same entry points take the single-RHS path, one right-hand side after the other. */
+ *      Wilson-clover is covered (clover term in the epilogue).  Several ranks, r != 1: the same entry points take the single-RHS
+ *      path, one right-hand side after the other. */
 int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const xs[], int nrhs, int mode);
 int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const bs[], int nrhs,
                      int method, int target, double eps, int maxsteps, int *iters, double *resid_sq);

@@ -19,12 +19,12 @@
 //
 // Solver: CGNR (upstream "bicg", what solve_DinvX!(p, D, b) runs) and CG on DdagD, all right-hand sides advancing together; each
 // has its OWN SolverState / reduction workspace in device memory, converged systems drop out of the kernels (mask), the host
-// polls all states one batch behind the GPU.  Single rank, csw = 0; anything else takes the single-RHS path inside the same
+// polls all states one batch behind the GPU.  Single rank (Wilson-clover included); anything else takes the single-RHS path inside the same
 // entry points, one right-hand side after the other.
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"
-#include "wilson_spin.cuh"
+#include "wilson_kernel.cuh"      // clover_apply (site-local clover term of the single-RHS kernel)
 #include "bulk_copy.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -39,6 +39,7 @@ struct MrhsArgs {
     cplx *out[LQCD_MAX_RHS];
     MrhsRed red[LQCD_MAX_RHS];
     const cplx *gauge;
+    const cplx *clover;  // Wilson-clover: packed clover blocks (wilson_kernel.cuh), else null
     Geom g;
     double kappa, mass, sign;
     double bc[4];
@@ -118,7 +119,7 @@ __device__ __forceinline__ void hop_pair_m(cplx (&acc)[R][12], const MrhsArgs &A
     }
 }
 
-template <int DAG, int R, int MINB>
+template <int DAG, int R, int MINB, int CLOVER>
 __global__ void __launch_bounds__(128, MINB) wilson_mrhs_kernel(const MrhsArgs A) {
     const int rhs0 = blockIdx.y * R;
     const unsigned mask = live_mask<R>(A, rhs0);
@@ -151,9 +152,12 @@ __global__ void __launch_bounds__(128, MINB) wilson_mrhs_kernel(const MrhsArgs A
         if (active) {
             const cplx *xin = A.in[j];
             cplx *dst = A.out[j];
+            cplx ax[12];                    // CLOVER only (dead otherwise): A(n) x(n), as in the single-RHS kernel
+            if constexpr (CLOVER != 0) clover_apply(ax, A.clover + (size_t)blk * (36 * 32) + lane, xin + base);
 #pragma unroll
             for (int k = 0; k < 12; k++) {
-                const cplx xi = __ldg(xin + base + k * 32);
+                cplx xi;
+                if constexpr (CLOVER != 0) xi = ax[k]; else xi = __ldg(xin + base + k * 32);
                 const cplx yk = cmake(fma(mk, acc[r][k].x, xi.x), fma(mk, acc[r][k].y, xi.y));
                 red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
                 dst[base + k * 32] = yk;
@@ -553,9 +557,10 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
     if (op->kind == LQCD_WILSON) {
         if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
         if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "multi-RHS Wilson kernel: LQCD_WPC > 4 is not supported");
+        if (op->csw != 0.0) { LQCD_TRY(ensure_clover(ctx, op)); A.clover = ctx->clover; }
         static int smem_links = -1;
         if (smem_links < 0) { const char *e = getenv("LQCD_MRHS_SMEM"); smem_links = (e && atoi(e) == 1) ? 1 : 0; }
-        if (smem_links && ctx->g.regular && bs == 128) {       // experimental: links staged in shared memory by bulk copies
+        if (smem_links && ctx->g.regular && bs == 128 && !A.clover) {       // experimental: links staged in shared memory by bulk copies
             const size_t smem = (size_t)4 * MS_WARP * sizeof(cplx) + 4 * sizeof(uint64_t) + 32;
             static bool attr_set = false;
             if (!attr_set) {
@@ -569,10 +574,12 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
             CUDA_TRY(ctx, cudaGetLastError());
             return LQCD_OK;
         }
-        const int R = wilson_group(nrhs);
+        int R = wilson_group(nrhs);
+        if (A.clover && R > 3) R = 3;                       // the clover epilogue needs the registers of the fourth right-hand side
         const dim3 grid(gx, (nrhs + R - 1) / R);
-#define WM(R_, MB_) do { if (dagger) wilson_mrhs_kernel<1, R_, MB_><<<grid, bs, 0, ctx->stream>>>(A); else wilson_mrhs_kernel<0, R_, MB_><<<grid, bs, 0, ctx->stream>>>(A); } while (0)
-        if (R == 2) WM(2, 3); else if (R == 3) WM(3, 2); else WM(4, 2);
+#define WM(R_, MB_, CL_) do { if (dagger) wilson_mrhs_kernel<1, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); else wilson_mrhs_kernel<0, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); } while (0)
+        if (A.clover) { if (R == 2) WM(2, 2, 1); else WM(3, 2, 1); }          // Wilson-clover: 2 or 3 right-hand sides per thread
+        else if (R == 2) WM(2, 3, 0); else if (R == 3) WM(3, 2, 0); else WM(4, 2, 0);
 #undef WM
     } else {
         const int R = staggered_group(nrhs);
@@ -615,9 +622,10 @@ static int check_fields(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys
     return LQCD_OK;
 }
 
-// the batched kernels cover: one rank, plain Wilson / staggered, full (not even-odd) fields, regular or irregular tiling
+// the batched kernels cover: one rank, Wilson (r = 1, with or without the clover term) / staggered, full (not even-odd) fields,
+// regular or irregular tiling
 static bool batched_ok(const lqcd_ctx *ctx, const lqcd_op *op) {
-    return ctx->nranks == 1 && !(op->kind == LQCD_WILSON && (op->csw != 0.0 || op->r != 1.0)) && !ctx->eo_active && 32 * ctx->g.wpc <= (op->kind == LQCD_WILSON ? 128 : 256);
+    return ctx->nranks == 1 && !(op->kind == LQCD_WILSON && op->r != 1.0) && !ctx->eo_active && 32 * ctx->g.wpc <= (op->kind == LQCD_WILSON ? 128 : 256);
 }
 
 extern "C" int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const xs[], int nrhs, int mode) {
