@@ -261,6 +261,7 @@ EXPERIMENTS = {
     "mrhs_r4": ({"LQCD_MRHS_R": "4"}, "12 right-hand sides, 4 per thread"),
     "mrhs_smem": ({"LQCD_MRHS_SMEM": "1"}, "12 right-hand sides, links staged in shared memory by cp.async.bulk (one CTA per SM)"),
     "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides per pass"),
+    "propagator": ({}, "12 point-source CGNR solves (measure_Pion_correlator.jl:333-409): lock-step lqcd_solve_multi vs 12 x lqcd_solve"),
     "clover": ({}, "Wilson-clover Dslash (csw = 1.5612)"),
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
     "staggered_even": ({}, "staggered CG on an even-site source: half-field solver vs full-lattice solver"),
@@ -371,6 +372,33 @@ def _experiment_body(name, dims, out):
         per_site = 672 if kind == L.STAGGERED else BYTES_PER_SITE
         out.update({"nrhs": nrhs, "ms_per_pass": ms, "ms_per_rhs": ms / nrhs, "ms_single_rhs_kernel": single, "speedup_per_rhs": single * nrhs / ms,
                     "equivalent_single_rhs_GB/s": per_site * V * nrhs / ms / 1e6})
+    elif name == "propagator":
+        ctx, op, x, y = setup(dims, eps=0.3)
+        nsrc = 12
+        bs, xs = [q.FermionField(ctx, L.WILSON) for _ in range(nsrc)], [q.FermionField(ctx, L.WILSON) for _ in range(nsrc)]
+        for i, b in enumerate(bs):                     # spin-colour point sources at the origin
+            q.clear_fermion_(b)
+            q.setindex_global_(b, 1.0, i // 4 + 1, 1, 1, 1, 1, i % 4 + 1)
+        hb = (C.c_void_p * nsrc)(*[f.h.value for f in bs])
+        hx = (C.c_void_p * nsrc)(*[f.h.value for f in xs])
+        its, rss = (C.c_int * nsrc)(), (C.c_double * nsrc)()
+        for f in xs:
+            q.clear_fermion_(f)
+        t0 = time.perf_counter()
+        ctx.call("lqcd_solve_multi", C.byref(op), hx, hb, nsrc, L.SOLVER_CGNR, L.OP_D, 1e-16, 3000, its, rss)
+        t_multi = time.perf_counter() - t0
+        it1, rs1 = C.c_int(0), C.c_double(0.0)
+        seq_iters = []
+        t0 = time.perf_counter()
+        for i in range(nsrc):
+            q.clear_fermion_(y)
+            ctx.call("lqcd_solve", C.byref(op), y.h, bs[i].h, L.SOLVER_CGNR, L.OP_D, 1e-16, 3000, C.byref(it1), C.byref(rs1), None)
+            seq_iters.append(it1.value)
+        t_seq = time.perf_counter() - t0
+        same = bool(np.array_equal(y.to_host(), xs[nsrc - 1].to_host()))
+        out["ok"] = list(its) == seq_iters and same
+        out.update({"iters": list(its), "same_iteration_counts": list(its) == seq_iters, "last_solution_bit_identical": same,
+                    "wall_ms_lock_step": t_multi * 1e3, "wall_ms_sequential": t_seq * 1e3, "speedup": t_seq / t_multi})
     elif name == "clover":
         ctx, op, x, y = setup(dims, csw=1.5612)
         ms = dslash_ms(ctx, op, y, x)
