@@ -12,6 +12,10 @@ argument order and meaning, same error behaviour, so the parity tests read like 
     mul_(y, D, x); mul_(y, adjoint(D), x); mul_(y, DdagD(D), x)                  # measure_Pion_correlator.jl:379
     solve_DinvX_(y, D, b)                                                        # measure_Pion_correlator.jl:399
     fa = FermiAction(D, {"Nf": 2}); calc_UdSfdU_(UdSfdU, fa, U, eta)              # universe.jl:138, AbstractMD.jl:129
+    U  = load_gaugefield("conf_00000100.ildg", (4, 4, 4, 4), "ILDG"); save_textdata(U, "out.txt")   # universe.jl:62-68, lqcd.jl:236-242
+    props, infos = calc_quark_propagators_point_source(D)                        # measure_Pion_correlator.jl:333-409 (one batched solve)
+    pbp, _, _ = measure_chiral_condensate(D, Nr=10)                              # measure_chiral_condensate.jl:164-204
+    accepted, dH, info = hmc_update_(U, beta, dtau, MDsteps, fa=fa)               # standardHMC.jl:41-91, trajectory on the device
 
 Link fields stay host numpy arrays in the Julia memory layout (the gauge sector keeps using them on the
 CPU, SURVEY.md 8b "Selection" option 1); they are mirrored to the device when an operator is built or
