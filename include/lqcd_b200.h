@@ -231,7 +231,7 @@ int lqcd_rational_apply(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *y, const
  *      leapfrog integrators of src/md/standardMD.jl:125-165 for NC = 3 and the plaquette action beta/2*(P + P^dag)
  *      (src/system/universe.jl:85-93), so that links, momenta and pseudofermions stay in HBM for a whole trajectory.
  *      Momenta: link-shaped device field of anti-Hermitian traceless matrices p = sum_a a_a i lambda_a/2 (host layout = link
- *      layout).  Single rank.
+ *      layout).  Single and multi rank (staples / plaquettes read the neighbour ranks' peer-mapped links; collective calls).
  *      lqcd_md_momenta_gaussian   gauss_distribution!(p)   (standardMD.jl:86): a_a ~ N(0,1), counter-based generator
  *      lqcd_md_kinetic            md.p * md.p / 2          (standardHMC.jl:47)
  *      lqcd_md_gauge_action       -evaluate_GaugeAction(gauge_action, U)/NC = -(beta/NC) sum_plaq Re tr U_p (standardHMC.jl:49-50)

@@ -16,7 +16,7 @@
 // The term depends on the links only: it is rebuilt when the gauge epoch or kappa*csw changes (once per D(U) rebinding),
 // never inside a solve.
 //
-// STATUS: compiled for sm_100a; not yet run on hardware (GPU budget of the round was spent) -- tests/test_gpu_clover.py.
+// Parity on hardware: tests/test_gpu_extended.py::test_clover_term_matches_oracle (1e-13 against the oracle's dense blocks).
 #include "lqcd_internal.cuh"
 #include "link_view.cuh"
 #include <complex>

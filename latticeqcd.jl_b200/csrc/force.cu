@@ -384,7 +384,9 @@ extern "C" int lqcd_fermion_force_xy(lqcd_ctx *ctx, const lqcd_op *op, const lqc
     LQCD_TRY(check_force_args(ctx, op, X, Y));
     if (X == Y) return lqcd_fail(ctx, LQCD_ERR_ARG, "force: X aliases Y");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return force_outer(ctx, op, X, Y, coef, accumulate, nullptr, nullptr);
+    LQCD_TRY(force_outer(ctx, op, X, Y, coef, accumulate, nullptr, nullptr));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // exported calls are blocking-on-return (include/lqcd_b200.h); internal callers use force_outer
+    return comm_check_error(ctx);
 }
 
 extern "C" int lqcd_fermion_force_download(lqcd_ctx *ctx, double *const out_mu[4], int ndw) {

@@ -16,7 +16,7 @@
 //     first half   (dagger = 0)   t_o = Dh_oe p_e                      reduces |t_o|^2 + m^2 |p_e|^2 = <p, A_ee p>   (norm form)
 //     second half  (dagger = 1)   q_e = m^2 p_e - Dh_eo t_o            with the solver's fused epilogue (r -= alpha q, |r|^2, <w, q>)
 //
-// Layout and link split: wilson_eo.cu (eo_common.cuh).  Single rank.  Pre-flighted under tests/emu; not yet run on hardware.
+// Layout and link split: wilson_eo.cu (eo_common.cuh).  Single rank.  Parity on hardware: tests/test_gpu_extended.py.
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"

@@ -7,8 +7,8 @@
 // cannot reach Wilson-clover, parameter parsed at src/system/parameter_structs.jl:125); the term is built by clover.cu.
 // Compulsory traffic 960 + 576 = 1536 B/site, 1368 + 504 flop/site.
 //
-// STATUS: compiled for sm_100a and checked on the CPU side only (oracle + numpy restatement of the same packing,
-// tests/test_clover.py); the GPU parity tests (tests/test_gpu_clover.py) have not run on hardware yet.
+// Parity: tests/test_gpu_extended.py (clover term, Dslash, CG against the oracle on hardware), tests/test_clover.py (oracle vs a numpy
+// restatement of the same packing).  The convention is the textbook one: the reference cannot reach clover, so nothing upstream pins it.
 #include "wilson_kernel.cuh"
 
 int launch_wilson_clover(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, int multi, int lh, int grid, int bs, cudaStream_t s) {

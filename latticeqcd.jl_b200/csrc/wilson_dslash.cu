@@ -17,8 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 
-int launch_wilson_dslash2(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash2.cu
-int launch_wilson_dslash3(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s);   // wilson_dslash3.cu (experimental)
+int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s, bool halo, bool self_pack);   // wilson_tmarch.cu
 
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                          const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo, const HaloOut *hout) {
@@ -57,48 +56,29 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         if (lh) { if (mu_ == 2) WLK(MT, MB, 2, 1); else if (mu_ == 1) WLK(MT, MB, 1, 1); else WLK(MT, MB, 0, 1); } \
         else    { if (mu_ == 2) WLK(MT, MB, 2, 0); else if (mu_ == 1) WLK(MT, MB, 1, 0); else WLK(MT, MB, 0, 0); } \
     } while (0)
-    // experiment (LQCD_PERSIST=1, default off): one wave of persistent CTAs drawing tiles from a queue -- self-packing
-    // multi-GPU launches and plain single-GPU launches of the default register budget only
-    static int persist = -1;
-    if (persist < 0) { const char *e = getenv("LQCD_PERSIST"); persist = (e && atoi(e) == 1) ? 1 : 0; }
     static int lh_env = -2;
     if (lh_env == -2) { const char *e = getenv("LQCD_LINK_HINT"); lh_env = e ? (atoi(e) != 0) : -1; }
     const int lh = lh_env >= 0 ? lh_env : (ctx->g.V <= (1 << 18));
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
-    // kernel family: 1 = one lane per site (this file, default), 2 = two lanes per site (wilson_dslash2.cu).
-    // Measured on B200 at 32^4: family 2 with 16/24/32 warps per SM runs 222/261/355 us against 192 us here --
-    // more resident warps LOWER the L1 hit rate and the kernel then saturates the ~10.8 TB/s L2->SM fabric
-    // (2.1 GB of L2 reads per application at 28 % L1 hits), so occupancy is not the lever; L2 traffic is.
+    // kernel family: 1 = one lane per site, register-resident hops (this file); 4 = t-marching kernel with TMA-staged spinor
+    // window and link stages (wilson_tmarch.cu), which falls through to family 1 when the geometry does not qualify.
+    // (Rounds 1 / 2 also measured a two-lanes-per-site kernel, 222-355 us at 32^4, and a first t-marching kernel with LDG links,
+    // 335-490 us: both removed.)
     static int family = -1;
-    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = (e && (atoi(e) == 2 || atoi(e) == 3)) ? atoi(e) : 1; }
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = e ? atoi(e) : 0; }
     if (A.clover) {                    // Wilson-clover: CLOVER = 1 instantiations live in wilson_clover.cu
         LQCD_TRY(launch_wilson_clover(ctx, A, dagger, (halo && hout) ? 2 : (halo ? 1 : 0), lh, grid, bs, s));
         ctx->launches++;
         return LQCD_OK;
     }
-    if (family == 3 && !halo && !sub) {        // experimental t-marching kernel; falls through when the geometry does not qualify
-        const int rc = launch_wilson_dslash3(ctx, A, dagger, s);
+    if (family != 1 && !sub) {                 // t-marching TMA kernel; LQCD_ERR_STATE = geometry does not qualify -> family 1
+        const int rc = launch_wilson_tmarch(ctx, A, dagger, s, halo != nullptr, hout != nullptr);
         if (rc != LQCD_ERR_STATE) return rc;
     }
-    if (family == 2 && !halo && !sub && bs <= 128 && !A.fuse.axpy_r) return launch_wilson_dslash2(ctx, A, dagger, s);
-    // measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM,
-    // 136 B spills) 204 us -- the kernel is latency bound (ncu: 57% long-scoreboard stalls), so 168 is the default.
-    if (persist && !sub && bs == 128 && lb == 0 && ((halo && hout) || !halo)) {
-        const int pgrid = grid < 3 * ctx->num_sms ? grid : 3 * ctx->num_sms;      // __launch_bounds__(128, 3): 3 CTAs per SM
-        A.fuse.queue = ctx->queue; A.fuse.queue_total = grid;
-#define WLP(MU_, LH_)                                                                           \
-    do {                                                                                        \
-        if (dagger) wilson_dslash_kernel<1, 128, 3, MU_, LH_, 0><<<pgrid, bs, 0, s>>>(A);       \
-        else        wilson_dslash_kernel<0, 128, 3, MU_, LH_, 0><<<pgrid, bs, 0, s>>>(A);       \
-    } while (0)
-        if (halo) { if (lh) WLP(3, 1); else WLP(3, 0); }
-        else      { if (lh) WLP(4, 1); else WLP(4, 0); }
-#undef WLP
-        ctx->launches++;
-        CUDA_TRY(ctx, cudaGetLastError());
-        return LQCD_OK;
-    }
+    // family 1, measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 158-168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM)
+    // 204-211 us; 144 regs (14 warps/SM) 206 us -- the kernel saturates the L2->SM fabric (2.29 GB at 11 TB/s), occupancy is no lever.
     if (lb == 12804 && bs <= 128) WL(128, 4);
+    else if (lb == 6407 && bs <= 64) WL(64, 7);          // 14 warps/SM, 144 registers: wave-count experiment
     else if (lb == 25602) WL(256, 2);
     else if (lb == 25601 || bs > 128) WL(256, 1);
     else WL(128, 3);

@@ -16,8 +16,8 @@
 // hops over V/2 sites each = 1536 B per full-lattice site (M costs 960) and converges in roughly half the iterations on
 // vectors of half the length.
 //
-// STATUS: compiled for sm_100a; index logic emulated on the CPU (tests/test_evenodd.py::test_checkerboard_index_emulation);
-// not yet run on hardware (tests/test_zz_gpu_unverified.py).
+// Parity on hardware: tests/test_gpu_extended.py (vs orc.eo_solve), tests/test_gpu_baseline_sizes.py (16^4, BASELINE configs[1]);
+// index logic also emulated on the CPU (tests/test_evenodd.py::test_checkerboard_index_emulation).
 #include "wilson_kernel.cuh"
 #include "eo_common.cuh"
 #include <cstring>

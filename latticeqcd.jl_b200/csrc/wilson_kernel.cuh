@@ -138,31 +138,18 @@ __device__ __forceinline__ void clover_apply(cplx (&ax)[12], const cplx *__restr
     }
 }
 
-// MULTI_: 0 single GPU | 1 fused halo (separate pack kernel) | 2 self-packing | 3 = 2 + PERSISTENT | 4 = 0 + PERSISTENT.
-// PERSISTENT (experiment, LQCD_PERSIST=1, off by default): the grid is one wave of CTAs (resident CTAs per SM x SMs) and
-// every CTA draws tile after tile from a device-side queue (pack tiles first, then interior, then face tiles) instead of
-// being bound to blockIdx -- no wave quantisation between the interior and the face phase, no tail of a part-filled last
-// wave.  The queue is a self-resetting atomicInc counter (wraps after ntiles + gridDim.x draws: every CTA draws exactly one
-// terminating index).  Reductions stay deterministic: one partial per TILE, summed in tile order by the last tile.
-template <int DAG, int MAXT, int MINB, int MULTI_, int LH, int CLOVER>
-__global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonArgs A) {
-    constexpr bool PERSIST = MULTI_ >= 3;
-    constexpr int MULTI = MULTI_ == 3 ? 2 : (MULTI_ == 4 ? 0 : MULTI_);
+// MULTI: 0 single GPU | 1 fused halo (separate pack kernel on the priority stream) | 2 self-packing (the leading CTAs of this
+// kernel ship the halo).  (A persistent-CTA tile-queue variant was measured in rounds 1 / 2: slower at every N, removed.)
+// register cap per launch-bounds variant: (128,3) -> 168, (128,4) / (256,2) -> 128, (256,1) -> 255, (64,7) -> 144 (14 warps per SM)
+constexpr int wilson_regs(int maxt, int minb) { int r = 65536 / (maxt * minb); r -= r % 8; return r > 255 ? 255 : r; }
+template <int DAG, int MAXT, int MINB, int MULTI, int LH, int CLOVER>
+__global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int queue_bid;
-  for (;;) {
     int bid = blockIdx.x, npack = 0;
-    if (PERSIST) {
-        __syncthreads();                                // everybody is done with the previous tile (shared scratch of the reduction)
-        if (threadIdx.x == 0) queue_bid = (int)atomicInc(A.fuse.queue, (unsigned)(A.fuse.queue_total + (int)gridDim.x - 1));
-        __syncthreads();
-        bid = queue_bid;
-        if (bid >= A.fuse.queue_total) return;
-    }
     if (MULTI == 2) {      // self-packing: the first npack CTAs ship this application's halo to the neighbours
         npack = A.hout.cta0[4];
-        if (bid < npack) { halo_pack_cta(A.g, LQCD_WILSON, DAG, A.in, A.gauge, A.hout, bid); if (PERSIST) continue; else return; }
+        if (bid < npack) { halo_pack_cta(A.g, LQCD_WILSON, DAG, A.in, A.gauge, A.hout, bid); return; }
         bid -= npack;
     }
     int cta = bid + A.fuse.cta_off;
@@ -233,9 +220,6 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_dslash_kernel(const WilsonA
         }
     }
     if (A.fuse.dot_with || A.fuse.want_norm)
-        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid,
-                              PERSIST ? (unsigned)(A.fuse.queue_total - npack) : gridDim.x - (unsigned)npack);
-    if (!PERSIST) break;
-  }
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid, gridDim.x - (unsigned)npack);
 }
 

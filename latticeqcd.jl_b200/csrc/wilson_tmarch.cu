@@ -1,0 +1,289 @@
+// wilson_tmarch.cu -- Wilson Dslash, fp64, sm_100a: t-marching kernel with ALL compulsory traffic staged through shared memory by
+// TMA bulk copies (cp.async.bulk + mbarrier).  Default Wilson path for regular geometries (x-line blocks, 4-warp (y,z) patches);
+// launch_wilson_tmarch returns LQCD_ERR_STATE for anything else and the caller falls back to the register-resident kernel
+// (wilson_kernel.cuh).
+//
+// Why (measured, profiles/r2a_*): the register-resident kernel moves 2.29 GB per 32^4 application from L2 to the SMs (2.2 KB/site,
+// L1 hit rate 22 %) at 11 TB/s -- that is the L2->SM fabric limit (probe: 10.8 TB/s), so it sits at 0.76 of the HBM roofline and no
+// occupancy variant (12 / 14 / 16 warps per SM) moves it.  A first t-marching kernel (round 1, spinor window only, links by LDG,
+// 12 warps/SM) cut the fabric traffic but ran at 383 us: every step waited on link LDGs.  Here
+//   * a CTA (4 warps = a 2x2 patch of 32-site blocks in (y,z)) marches along t, one persistent CTA per SM;
+//   * the spinor records of the patch for slices t-1, t, t+1 live in a 3-slot shared-memory window: the own spinor, both x
+//     neighbours, the in-patch y / z neighbours and both t neighbours are served from it (7 of 9 uses), each record is fetched
+//     from L2 once per chunk step by ONE 6 KB bulk copy issued a full step ahead;
+//   * the forward-link records of the patch (4 x 4.5 KB per block) live in four "planes", one per direction, refilled for the
+//     next slice as soon as the whole CTA is done with the direction: the forward hop, the in-patch backward hops (the
+//     neighbour's forward link) and the t-backward hop (the plane still holds slice t-1 when the step starts) read them from
+//     shared memory, so every link enters the SM once;
+//   * only the out-of-patch y / z neighbours (2 of 8 hops per site for a 2x2 patch) and their backward links use LDG.
+// L2 -> SM traffic: 24 KB (compulsory) + ~16.5 KB per block-step = 1.27 KB/site instead of 2.2 KB; bytes in flight per SM are
+// set by the copy schedule (~90 KB), not by registers or occupancy.
+//
+// Reference semantics: LinearAlgebra.mul!(y, D, x) / mul!(y, D', x) of LatticeDiracOperators.jl (upstream Wx!/Wdagx!, SURVEY.md
+// App. C.1); call sites src/md/AbstractMD.jl:129, src/updates/standardHMC.jl:69-71, measure_Pion_correlator.jl:379,399.
+#include "lqcd_internal.cuh"
+#include "reduce.cuh"
+#include "wilson_spin.cuh"
+#include "bulk_copy.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+#define TM_W 4                              // warps per CTA = blocks per patch
+#define TM_REC (12 * 32)                    // complex numbers per spinor record (one 32-site block)
+#define TM_REC_BYTES (TM_REC * 16)
+#define TM_SUB (9 * 32)                     // complex numbers per link sub-record (one direction of one block)
+#define TM_SUB_BYTES (TM_SUB * 16)
+#define TM_SMEM_BYTES ((3 * TM_W * TM_REC + 4 * TM_W * TM_SUB) * 16 + 64)
+
+struct TMArgs {
+    WilsonArgs A;
+    int Lc, nchunk, nsb, ntasks;            // t-steps per task, chunks per patch, blocks per t-slice, tasks = patches * chunks
+};
+
+// hop arithmetic on operands already in registers: p = neighbour spinor, u = link (row-major 3x3)
+template <int MU, int FWD, int DAG>
+__device__ __forceinline__ void hop_regs(cplx (&acc)[12], const cplx (&p)[12], const cplx (&u)[9], bool wrapped, double phase) {
+    constexpr int S = (FWD ^ DAG) ? -1 : +1;
+    cplx h0[3], h1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) project<MU, S>(h0[c], h1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
+    if (wrapped) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            if (FWD) { cfma(g0, u[a * 3 + b], h0[b]); cfma(g1, u[a * 3 + b], h1[b]); }
+            else     { cfmac(g0, u[b * 3 + a], h0[b]); cfmac(g1, u[b * 3 + a], h1[b]); }
+        }
+        reconstruct<MU, S>(acc, a, g0, g1);
+    }
+}
+
+__device__ __forceinline__ void ld_spinor_s(cplx (&p)[12], const cplx *s) {         // shared memory (window)
+#pragma unroll
+    for (int k = 0; k < 12; k++) p[k] = s[k * 32];
+}
+__device__ __forceinline__ void ld_spinor_g(cplx (&p)[12], const cplx *__restrict__ gp) {   // global (out-of-patch neighbour)
+#pragma unroll
+    for (int k = 0; k < 12; k++) p[k] = __ldg(gp + k * 32);
+}
+__device__ __forceinline__ void ld_link_s(cplx (&u)[9], const cplx *s) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = s[e * 32];
+}
+__device__ __forceinline__ void ld_link_g(cplx (&u)[9], const cplx *__restrict__ gp) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) u[e] = __ldg(gp + e * 32);
+}
+
+template <int DAG>
+__global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
+    const WilsonArgs &A = K.A;
+    if (A.fuse.use_state && A.red.st->done) return;
+    extern __shared__ __align__(128) unsigned char tm_smem[];
+    cplx *const win = reinterpret_cast<cplx *>(tm_smem);                     // [3][W][12][32]
+    cplx *const plane = win + 3 * TM_W * TM_REC;                             // [4 (mu)][W][9][32]
+    uint64_t *const wbar = reinterpret_cast<uint64_t *>(plane + 4 * TM_W * TM_SUB);   // [3] window slots
+    uint64_t *const pbar = wbar + 3;                                         // [4] link planes
+    const Geom &g = A.g;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nsb = K.nsb, T = g.T, Lc = K.Lc;
+    const int npatch = g.nt[0] * g.nt[1] * g.nt[2];
+
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 3; j++) mbar_init(&wbar[j], TM_W);
+        for (int j = 0; j < 4; j++) mbar_init(&pbar[j], TM_W);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t wph = 0, pph = 0;            // parity to wait for next, one bit per barrier (every thread waits on every completion)
+    auto wait_w = [&](int j) { mbar_wait(&wbar[j], (wph >> j) & 1u); wph ^= 1u << j; };
+    auto wait_p = [&](int j) { mbar_wait(&pbar[j], (pph >> j) & 1u); pph ^= 1u << j; };
+
+    const int w0 = w % g.c[0], w1 = (w / g.c[0]) % g.c[1], w2 = w / (g.c[0] * g.c[1]);
+    double red[3] = {0.0, 0.0, 0.0};
+    const double mk = -A.kappa;
+    const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
+    cplx *const dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
+
+    for (int task = blockIdx.x; task < K.ntasks; task += gridDim.x) {
+        // tasks are numbered chunk-major: the CTAs in flight sweep the lattice in t together, so the out-of-patch neighbours and
+        // the next slice are L2 hits (each record comes from HBM once per application)
+        const int patch = task % npatch, chunk = task / npatch;
+        const int p0 = patch % g.nt[0], p1 = (patch / g.nt[0]) % g.nt[1], p2 = patch / (g.nt[0] * g.nt[1]);
+        const int bslice = (p0 * g.c[0] + w0) + g.nb[0] * ((p1 * g.c[1] + w1) + g.nb[1] * (p2 * g.c[2] + w2));
+        const int t0 = chunk * Lc;
+
+        // t-invariant spatial neighbour tables of this lane: block in the slice, lane, patch position (-1 = out of patch), wrap
+        const int ssl = bslice * 32 + lane;
+        int nbl[6], nl[6], nw[6];
+        bool wr[6];
+        {
+            const int coord[3] = {ssl % g.X, (ssl / g.X) % g.Y, ssl / (g.X * g.Y)}, dim[3] = {g.X, g.Y, g.Z}, stride[3] = {1, g.X, g.X * g.Y};
+#pragma unroll
+            for (int mu = 0; mu < 3; mu++) {
+#pragma unroll
+                for (int f = 0; f < 2; f++) {                        // f = 0: forward (+mu), f = 1: backward (-mu)
+                    const int d = mu * 2 + f;
+                    const bool wrapd = f == 0 ? (coord[mu] == dim[mu] - 1) : (coord[mu] == 0);
+                    const int nssl = f == 0 ? (wrapd ? ssl - (dim[mu] - 1) * stride[mu] : ssl + stride[mu])
+                                            : (wrapd ? ssl + (dim[mu] - 1) * stride[mu] : ssl - stride[mu]);
+                    wr[d] = wrapd;
+                    nbl[d] = nssl >> 5; nl[d] = nssl & 31;
+                    const int q0 = nbl[d] % g.nb[0], q1 = (nbl[d] / g.nb[0]) % g.nb[1], q2 = nbl[d] / (g.nb[0] * g.nb[1]);
+                    const bool inp = q0 >= p0 * g.c[0] && q0 < (p0 + 1) * g.c[0] && q1 >= p1 * g.c[1] && q1 < (p1 + 1) * g.c[1] &&
+                                     q2 >= p2 * g.c[2] && q2 < (p2 + 1) * g.c[2];
+                    nw[d] = inp ? (q0 - p0 * g.c[0]) + g.c[0] * ((q1 - p1 * g.c[1]) + g.c[1] * (q2 - p2 * g.c[2])) : -1;
+                }
+            }
+        }
+
+        __syncthreads();                  // everybody is done reading the previous task's window and planes
+        if (lane == 0) {
+            for (int rel = 0; rel < 3; rel++) {                                  // slices t0-1, t0, t0+1 -> slots 0, 1, 2
+                const int tt = (t0 - 1 + rel + T) % T;
+                mbar_arrive_expect_tx(&wbar[rel], TM_REC_BYTES);
+                bulk_g2s(win + ((size_t)rel * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)tt * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel]);
+            }
+            const size_t b0 = (size_t)bslice + (size_t)t0 * nsb, bm = (size_t)bslice + (size_t)((t0 - 1 + T) % T) * nsb;
+            for (int mu = 0; mu < 3; mu++) {                                     // spatial forward links of slice t0
+                mbar_arrive_expect_tx(&pbar[mu], TM_SUB_BYTES);
+                bulk_g2s(plane + ((size_t)mu * TM_W + w) * TM_SUB, A.gauge + (b0 * 4 + mu) * TM_SUB, TM_SUB_BYTES, &pbar[mu]);
+            }
+            mbar_arrive_expect_tx(&pbar[3], TM_SUB_BYTES);                       // t links of slice t0-1 (backward hop of the first step)
+            bulk_g2s(plane + ((size_t)3 * TM_W + w) * TM_SUB, A.gauge + (bm * 4 + 3) * TM_SUB, TM_SUB_BYTES, &pbar[3]);
+        }
+
+        for (int r = 1; r <= Lc; r++) {
+            const int t = t0 + r - 1;
+            const size_t blk = (size_t)bslice + (size_t)t * nsb;
+            const cplx *cur = win + (size_t)(r % 3) * TM_W * TM_REC;
+            const cplx *up = win + (size_t)((r + 1) % 3) * TM_W * TM_REC;
+            const cplx *dn = win + (size_t)((r - 1) % 3) * TM_W * TM_REC;
+            const size_t base = blk * TM_REC + lane;
+            if (A.fuse.axpy_r || A.fuse.dot_with || A.fuse.shift_src) {          // epilogue operands: start them towards L2 now
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    if (A.fuse.axpy_r) prefetch_l2(A.fuse.axpy_r + base + k * 32);
+                    if (A.fuse.dot_with) prefetch_l2(A.fuse.dot_with + base + k * 32);
+                    if (A.fuse.shift_src) prefetch_l2(A.fuse.shift_src + base + k * 32);
+                }
+            }
+            cplx acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
+            cplx p[12], u[9];
+
+            // ---- t backward: slice t-1 from the window, its t links still in plane 3 -------------------------------------------
+            if (r == 1) { wait_w(0); wait_w(1); wait_p(3); }      // later steps: plane 3 was waited for by the previous step's forward hop
+            ld_spinor_s(p, dn + (size_t)w * TM_REC + lane);
+            ld_link_s(u, plane + ((size_t)3 * TM_W + w) * TM_SUB + lane);
+            hop_regs<3, 0, DAG>(acc, p, u, t == 0, A.bc[3]);
+            __syncthreads();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&pbar[3], TM_SUB_BYTES);                   // t links of slice t (forward hop at the end of the step)
+                bulk_g2s(plane + ((size_t)3 * TM_W + w) * TM_SUB, A.gauge + (blk * 4 + 3) * TM_SUB, TM_SUB_BYTES, &pbar[3]);
+                if (r + 2 <= Lc + 1) {                                           // slice t+2 into the slot slice t-1 just left
+                    const int rel = r + 2, tt = (t0 - 1 + rel) % T;
+                    mbar_arrive_expect_tx(&wbar[rel % 3], TM_REC_BYTES);
+                    bulk_g2s(win + ((size_t)(rel % 3) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)tt * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel % 3]);
+                }
+            }
+
+            // ---- spatial directions: plane mu holds the forward links of slice t for the whole patch ---------------------------
+#define TM_SPATIAL(MU)                                                                                                      \
+            {                                                                                                               \
+                wait_p(MU);                                                                                                 \
+                const int df = MU * 2, db = MU * 2 + 1;                                                                     \
+                const cplx *pl = plane + (size_t)MU * TM_W * TM_SUB;                                                        \
+                if (nw[df] >= 0) ld_spinor_s(p, cur + (size_t)nw[df] * TM_REC + nl[df]);                                    \
+                else             ld_spinor_g(p, A.in + ((size_t)nbl[df] + (size_t)t * nsb) * TM_REC + nl[df]);              \
+                ld_link_s(u, pl + (size_t)w * TM_SUB + lane);                                                               \
+                hop_regs<MU, 1, DAG>(acc, p, u, wr[df], A.bc[MU]);                                                          \
+                if (nw[db] >= 0) { ld_spinor_s(p, cur + (size_t)nw[db] * TM_REC + nl[db]); ld_link_s(u, pl + (size_t)nw[db] * TM_SUB + nl[db]); } \
+                else {                                                                                                      \
+                    ld_spinor_g(p, A.in + ((size_t)nbl[db] + (size_t)t * nsb) * TM_REC + nl[db]);                           \
+                    ld_link_g(u, A.gauge + (((size_t)nbl[db] + (size_t)t * nsb) * 4 + MU) * TM_SUB + nl[db]);               \
+                }                                                                                                           \
+                hop_regs<MU, 0, DAG>(acc, p, u, wr[db], A.bc[MU]);                                                          \
+                __syncthreads();                                                                                            \
+                if (lane == 0 && r < Lc) {                                       /* forward links of slice t+1 */           \
+                    mbar_arrive_expect_tx(&pbar[MU], TM_SUB_BYTES);                                                         \
+                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM_SUB, A.gauge + ((blk + nsb) * 4 + MU) * TM_SUB, TM_SUB_BYTES, &pbar[MU]); \
+                }                                                                                                           \
+            }
+            TM_SPATIAL(0) TM_SPATIAL(1) TM_SPATIAL(2)
+#undef TM_SPATIAL
+
+            // ---- t forward: slice t+1 from the window, t links of slice t (requested after the backward hop) -------------------
+            wait_w((r + 1) % 3);
+            wait_p(3);
+            ld_spinor_s(p, up + (size_t)w * TM_REC + lane);
+            ld_link_s(u, plane + ((size_t)3 * TM_W + w) * TM_SUB + lane);
+            hop_regs<3, 1, DAG>(acc, p, u, t == T - 1, A.bc[3]);
+
+            // ---- epilogue: y = x - kappa * hops (+ fused shift / CG residual update / reductions), as wilson_kernel.cuh ----------
+            const cplx *own = cur + (size_t)w * TM_REC + lane;
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const cplx xi = own[k * 32];
+                cplx yk = cmake(fma(mk, acc[k].x, xi.x), fma(mk, acc[k].y, xi.y));
+                if (A.fuse.shift_src) {
+                    const cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
+                    yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
+                }
+                if (A.fuse.axpy_r) {
+                    const cplx rv = A.fuse.axpy_r[base + k * 32];
+                    yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
+                }
+                if (A.fuse.dot_with) {
+                    const cplx wv = ldg128(A.fuse.dot_with + base + k * 32);
+                    red[0] = fma(wv.x, yk.x, red[0]); red[0] = fma(wv.y, yk.y, red[0]);
+                    red[1] = fma(wv.x, yk.y, red[1]); red[1] = fma(-wv.y, yk.x, red[1]);
+                }
+                red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
+                dst[base + k * 32] = yk;
+            }
+        }
+    }
+    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
+}
+
+// LQCD_OK if launched; LQCD_ERR_STATE if the geometry / variant does not qualify (caller falls back to the register-resident kernel)
+int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s, bool halo, bool self_pack) {
+    const Geom &g = ctx->g;
+    (void)self_pack;
+    if (halo || ctx->nranks != 1 || A.clover) return LQCD_ERR_STATE;
+    if (!g.regular || g.s[3] != 1 || g.c[3] != 1 || g.c[0] * g.c[1] * g.c[2] != TM_W || g.T < 2) return LQCD_ERR_STATE;
+    const int npatch = g.nt[0] * g.nt[1] * g.nt[2];
+    // chunks per patch: minimise rounds x (steps + ~1 step of pipeline fill per task) over the divisors of T
+    int nchunk = 1;
+    {
+        double best = 1e300;
+        for (int c = 1; c <= g.T / 2; c++) {
+            if (g.T % c) continue;
+            const int tasks = npatch * c, grid = tasks < ctx->num_sms ? tasks : ctx->num_sms;
+            const double cost = (double)((tasks + grid - 1) / grid) * (g.T / c + 1.0);
+            if (cost < best) { best = cost; nchunk = c; }
+        }
+        if (const char *e = getenv("LQCD_TM_CHUNKS")) { int v = atoi(e); if (v >= 1 && g.T % v == 0) nchunk = v; }
+    }
+    TMArgs K;
+    K.A = A; K.Lc = g.T / nchunk; K.nchunk = nchunk; K.nsb = g.nb[0] * g.nb[1] * g.nb[2]; K.ntasks = npatch * nchunk;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = K.ntasks < ctx->num_sms ? K.ntasks : ctx->num_sms;
+    if (dagger) wilson_tmarch_kernel<1><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+    else        wilson_tmarch_kernel<0><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return LQCD_OK;
+}

@@ -23,6 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __align__(n) alignas(n)
 #define LQCD_EMU 1

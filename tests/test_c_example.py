@@ -62,7 +62,6 @@ def check_against_oracle(exe, golden_dir, tmp_path, env=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="C client of lqcd_solve_multi / lqcd_gauge_load: verified under tests/emu only, not yet run on hardware", strict=False)
 def test_c_example_on_the_device(tmp_path, golden_dir):
     exe = _compile(tmp_path, ROOT / "latticeqcd.jl_b200", "liblqcd_b200.so")
     check_against_oracle(exe, golden_dir, tmp_path)

@@ -48,7 +48,7 @@ def test_translation_rejects_unknown_constructs():
 
 def test_gpu_suite_under_emulation(emu_lib):
     """every single-rank `-m gpu` test, xfail markers ignored (--runxfail): the not-yet-on-hardware kernels must pass here"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_reference_regressions.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x",
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_rhmc.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_reference_regressions.py", "tests/test_gpu_extended.py", "-m", "gpu", "-q", "-x",
            "--runxfail", "-p", "no:cacheprovider", "-n", "4",
            "--deselect", "tests/test_gpu_parity.py::test_16_4_size_independent_properties"]      # 2 min under emulation
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_TEST_NTRAJ="2", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4", LQCD_TEST_CONFIG1_DIMS="8x4x4x4", LQCD_TEST_CONFIG2_DIMS="12x6x4x4"), capture_output=True, text=True, timeout=1500)
@@ -62,7 +62,7 @@ def test_gpu_suite_is_schedule_independent_under_emulation(emu_lib):
     """the single-rank `-m gpu` suite again with the CTAs of every launch executed in DESCENDING blockIdx order and the threads of
     a CTA resumed from the highest index down: a kernel whose CTAs exchange data within one launch (in-place stencil, missing
     double buffer) or that misses a barrier between a shared-memory write and another thread's read fails in one of the orders"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q",
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_md.py", "tests/test_gauge_io.py", "tests/test_gpu_extended.py", "-m", "gpu", "-q",
            "-x", "--runxfail", "-p", "no:cacheprovider", "-n", "4",
            "-k", "not size_independent and not cgnr_matches_single and not multi_rhs_cg_on and not pipelined_host"]
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_CTA_ORDER="reverse", LQCD_EMU_THREAD_ORDER="reverse", OMP_NUM_THREADS="1", LQCD_TEST_FULL_DIMS="8x8x4x4", LQCD_TEST_CONFIG1_DIMS="8x4x4x4", LQCD_TEST_CONFIG2_DIMS="12x6x4x4"),
@@ -87,14 +87,16 @@ def test_multirank_under_emulation(emu_lib, dims, pg, kind):
 
 
 @pytest.mark.parametrize("bulk", ["early", "late"])
-def test_tmarch_kernel_under_emulation(emu_lib, bulk):
-    """experimental t-marching kernel (cp.async.bulk window + mbarriers, modelled by tests/emu): bulk copies completing at
+@pytest.mark.parametrize("chunks", ["auto", "1", "2"])
+def test_tmarch_kernel_under_emulation(emu_lib, bulk, chunks):
+    """t-marching TMA kernel (cp.async.bulk window + link planes on mbarriers, modelled by tests/emu): bulk copies completing at
     issue (earliest) and only when somebody waits on their mbarrier (latest) -- a missing wait or a premature slot refill
-    shows up as NaNs / mismatches in one of the two"""
-    r = subprocess.run([sys.executable, "tests/k3_worker.py"], cwd=ROOT, capture_output=True, text=True, timeout=900,
-                       env=_env(emu_lib, LQCD_WILSON_KERNEL="3", LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1"))
-    assert r.returncode == 0 and "K3 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
-    m = re.search(r"launches wilson_dslash3_kernel\s+(\d+)", r.stderr)
+    shows up as NaNs / mismatches in one of the two; chunks = tasks per patch (window re-priming, persistent task loop)"""
+    extra = {} if chunks == "auto" else {"LQCD_TM_CHUNKS": chunks}
+    r = subprocess.run([sys.executable, "tests/tmarch_worker.py"], cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=_env(emu_lib, LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1", **extra))
+    assert r.returncode == 0 and "TMARCH OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    m = re.search(r"launches wilson_tmarch_kernel\s+(\d+)", r.stderr)
     assert m and int(m.group(1)) > 500 and "launches wilson_dslash_kernel" not in r.stderr, r.stderr[-2000:]
 
 
@@ -102,25 +104,12 @@ def test_tmarch_kernel_under_emulation(emu_lib, bulk):
 def test_mrhs_smem_links_kernel_under_emulation(emu_lib, bulk):
     """LQCD_MRHS_SMEM=1: multi-RHS Wilson kernel with the links staged in shared memory by cp.async.bulk + mbarrier (both completion
     schedules of the bulk-copy model): bit-identical to the single-RHS kernel, propagators equal the oracle's"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_zz_gpu_unverified.py", "-m", "gpu", "-q", "-x", "--runxfail", "-p", "no:cacheprovider",
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_extended.py", "-m", "gpu", "-q", "-x", "--runxfail", "-p", "no:cacheprovider",
            "-k", "multi_rhs_dslash or point_source_propagators"]
     r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_MRHS_SMEM="1", LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     m = re.search(r"launches wilson_mrhs_smem_kernel\s+(\d+)", r.stderr)
     assert m and int(m.group(1)) > 50, r.stderr[-2000:]
-
-
-def test_persistent_queue_variant_under_emulation(emu_lib):
-    """LQCD_PERSIST=1 (persistent CTAs drawing tiles from a self-resetting queue): single-rank solver tests + a 2-rank worker"""
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-           "-k", "wilson_dslash_fixture or cg_matches or solve_D or multishift or odd_shapes"]
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_PERSIST="1"), capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(33500 + (os.getpid() % 2000)), "tests/mp_worker.py", "4x4x4x8", "1x1x1x2", "Wilson"]
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(emu_lib, LQCD_EMU_SHM="1", LQCD_COMM_TIMEOUT_S="120", LQCD_PERSIST="1"),
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 @pytest.mark.parametrize("action", ["wilson", "rhmc"])
@@ -163,7 +152,7 @@ def test_bench_experiments_leg_under_emulation(emu_lib, monkeypatch):
     bad = {k: v for k, v in res.items() if not v.get("ok")}
     assert not bad, bad
     assert res["mrhs_r3"]["bit_identical_to_single_rhs"] and res["staggered_mrhs"]["bit_identical_to_single_rhs"]
-    assert res["wilson_kernel3"]["max_rel_dev_vs_default"] < 1e-13
+    assert res["register_kernel"]["max_rel_dev_vs_default"] < 1e-13
 
 
 def test_bench_multirank_experiments_leg_under_emulation(emu_lib):

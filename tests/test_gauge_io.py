@@ -128,7 +128,6 @@ def test_errors_are_reported(tmp_path, golden_dir):
 
 # ---- device ----------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="file <-> device link path: verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4), (32, 4, 2, 2)])
 @pytest.mark.parametrize("fmt", ["ILDG", "BridgeText"])
 def test_device_load_and_save(tmp_path, dims, fmt):

@@ -1,15 +1,13 @@
 """
-GPU parity tests of device code that was written AFTER the round's GPU budget was spent: compiled for sm_100a and checked
-on the CPU side (oracle, numpy restatements, emulations) but never executed on hardware.  They run last (file name) and are
-marked xfail(strict=False): a failure is reported as "xfailed" and does not hide the verified suite, a pass shows up as
-"xpassed".  Remove the marker once a B200 run has confirmed them.
+GPU parity tests (through the C ABI) of the wider path: Wilson-clover, even-odd, multi-RHS, staggered half-field solves, RHMC
+plumbing, BASELINE-size checks.  First hardware run: round-1 driver GPU tier (all passed); plain strict tests since round 2.
 """
 import numpy as np
 import pytest
 
 from oracle import oracle as orc
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on hardware (written after the round's GPU budget was spent)", strict=False)]
+pytestmark = [pytest.mark.gpu]
 
 CSW = 1.5612        # src/system/parameter_structs.jl:125
 
@@ -112,16 +110,18 @@ def test_evenodd_beats_full_solve_and_keeps_plain_path():
     assert np.abs(out[True][1] - out[False][1]).max() < 1e-8
 
 
-# ---- experimental t-marching Wilson kernel (csrc/wilson_dslash3.cu, off by default) ------------------------------------
-def test_tmarch_kernel_matches_oracle():
+# ---- t-marching TMA Wilson kernel (csrc/wilson_tmarch.cu, default on regular geometries) vs the register-resident kernel ----------
+@pytest.mark.parametrize("env", [{}, {"LQCD_TM_CHUNKS": "1"}, {"LQCD_TM_CHUNKS": "2"}, {"LQCD_WILSON_KERNEL": "1"}],
+                         ids=["tmarch-auto", "tmarch-1chunk", "tmarch-2chunks", "register-kernel"])
+def test_wilson_kernel_families_match_oracle(env):
     import os
     import subprocess
     import sys
     from pathlib import Path
     root = Path(__file__).resolve().parents[1]
-    r = subprocess.run([sys.executable, "tests/k3_worker.py"], cwd=root, capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, LQCD_WILSON_KERNEL="3", LQCD_COMM_TIMEOUT_S="5"))
-    assert r.returncode == 0 and "K3 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "tests/tmarch_worker.py"], cwd=root, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LQCD_COMM_TIMEOUT_S="5", **env))
+    assert r.returncode == 0 and "TMARCH OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 # ---- pipelined host-field mul! (csrc/host_pipeline.cu) -----------------------------------------------------------------

@@ -1,7 +1,7 @@
 """Gauge-sector molecular dynamics: the steps of src/md/AbstractMD.jl:78-135 and the leapfrog
 integrators of src/md/standardMD.jl:125-165.  CPU: the oracle's restatement is pinned by what an integrator must satisfy
 whatever the generator normalisation -- energy conservation at O(dtau^2) (a wrong force factor breaks the scaling) and
-reversibility.  GPU (staged: written after the round's GPU budget was spent, verified under tests/emu): device steps and a
+reversibility.  GPU (hardware-verified since the round-1 driver run): device steps and a
 whole Sexton-Weingarten trajectory against the oracle composed step by step."""
 import numpy as np
 import pytest
@@ -156,11 +156,9 @@ def test_dynamical_leapfrog_energy_scaling(Uw, kind):
 
 
 # ---- device ----------------------------------------------------------------------------------------------------------------
-staged = pytest.mark.xfail(reason="gauge-sector MD kernels: verified under tests/emu only, not yet run on hardware", strict=False)
 
 
 @pytest.mark.gpu
-@staged
 @pytest.mark.parametrize("dims", [(4, 4, 4, 4), (8, 4, 6, 4)])
 def test_md_steps_match_oracle(dims):
     import lqcd_b200 as q
@@ -197,7 +195,6 @@ def test_md_steps_match_oracle(dims):
 
 
 @pytest.mark.gpu
-@staged
 def test_sw_trajectory_matches_oracle(Uw):
     """runMD_QPQ_sw! on the device == the oracle's steps composed in the same order (test/test_wilson.toml integrator with a
     shorter trajectory): links and momenta after the trajectory, and Delta H"""
@@ -227,7 +224,6 @@ def test_sw_trajectory_matches_oracle(Uw):
 
 
 @pytest.mark.gpu
-@staged
 def test_hmc_update_accepts_and_moves_links(Uw):
     """update!(StandardHMC, U) with the MD on the device (standardHMC.jl:41-91): a short trajectory is accepted with
     |Delta H| << 1, the links change, stay in SU(3), and the plaquette stays in the reference's 10 % window around the
@@ -249,7 +245,6 @@ def test_hmc_update_accepts_and_moves_links(Uw):
 
 
 @pytest.mark.gpu
-@staged
 def test_rhmc_trajectory_matches_oracle(golden_dir):
     """runMD! with the RHMC pseudofermion action on the device (lqcd_md_trajectory_rational: one multi-shift CG + accumulated outer
     products per fermion force) == the oracle's steps composed in the same order; then hmc_update_ with FermiAction(D, Nf = 2)"""

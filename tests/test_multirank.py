@@ -77,7 +77,6 @@ def test_multirank_parity(dims, pg, kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="multi-rank fermion force + multi-shift (force halo slots): verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("dims,pg,kind", [("8x8x8x16", "1x1x1x2", "Wilson"), ("8x8x8x8", "1x1x2x2", "staggered")])
 def test_multirank_force_parity(dims, pg, kind):
     """same worker as test_multirank_parity; kept as a separate staged test because the worker now also checks the multi-rank
@@ -89,7 +88,6 @@ def test_multirank_force_parity(dims, pg, kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="multi-rank Wilson-clover: verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("dims,pg", [("8x8x8x16", "1x1x1x2"), ("8x8x8x8", "1x1x2x2")])
 def test_multirank_clover_parity(dims, pg):
     """Wilson-clover across ranks: the clover leaves read the neighbours' links through peer-mapped link arrays (clover.cu)"""
@@ -100,7 +98,6 @@ def test_multirank_clover_parity(dims, pg):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="multi-rank device-resident MD trajectory: verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("dims,pg,action", [("8x8x8x16", "1x1x1x2", "wilson"), ("8x8x8x8", "1x1x2x2", "wilson"), ("8x8x8x8", "1x1x1x2", "rhmc")])
 def test_multirank_md_trajectory(dims, pg, action):
     """Sexton-Weingarten trajectory across ranks (tests/mp_md_worker.py): Wilson pseudofermions, and the staggered Nf = 2 RHMC
@@ -112,7 +109,6 @@ def test_multirank_md_trajectory(dims, pg, action):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="multi-rank gauge file I/O (lqcd_gauge_load / _save): verified under tests/emu only, not yet run on hardware", strict=False)
 def test_multirank_gauge_io():
     """every rank loads only its block of a global ILDG / BridgeText file; collective ILDG save is byte-identical (tests/mp_io_worker.py)"""
     res = run_ranks(2, ROOT / "tests" / "mp_io_worker.py", "8x8x8x8", "1x1x1x2", timeout=240)

@@ -6,7 +6,7 @@ Each test there is `plaq = run_LQCD("<toml>")`: start from the thermalised confi
 trajectories with the toml's integrator, return the plaquette of the final configuration, and compare with the stored value.
 Here the same runs are made (i) on the CPU oracle -- this is what pins the oracle's operator / solver / force / integrator chain to
 the numbers the reference's test-suite holds, as tightly as the reference pins itself -- and (ii) on the device through the
-reference-facing mirror (`hmc_update_`), staged for hardware and pre-flighted under tests/emu.  The reference's RNG stream (Julia
+reference-facing mirror (`hmc_update_`), hardware-verified since the round-1 driver run, pre-flighted under tests/emu.  The reference's RNG stream (Julia
 MersenneTwister seeded with 111, lqcd.jl:61) cannot be reproduced, so like the reference's own window the comparison is at the
 ensemble level; additionally every trajectory must conserve H to the accuracy its step size implies and the acceptance must be
 what a correct force gives (a wrong force weight shows up as |dH| >> 1 and zero acceptance)."""
@@ -98,7 +98,6 @@ def test_reference_plaquette_regression_on_the_oracle(golden_dir, toml):
 
 # ---- device ----------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="device-resident HMC trajectories: verified under tests/emu only, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("toml", sorted(CASES))
 def test_reference_plaquette_regression_on_the_device(golden_dir, toml):
     """the same runs through update!(StandardHMC, U)'s mirror with the whole trajectory on the device"""

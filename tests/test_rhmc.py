@@ -117,7 +117,6 @@ def test_rhmc_force_finite_difference(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="FermiAction Nf dispatch (even-site Nf=4, RHMC force accumulation): verified under tests/emu only, not yet run on hardware", strict=False)
 def test_fermi_action_nf_dispatch_on_b200(golden_dir):
     """FermiAction(D, {"Nf": ..}) as the wrapper builds it (universe.jl:106-110,138): Nf = 8 plain, Nf = 4 even-site
     pseudofermions, Nf = 2 RHMC; heat bath, action and MD force of each against the oracle."""

@@ -1,7 +1,7 @@
-"""Correctness worker for the experimental t-marching Wilson kernel (csrc/wilson_dslash3.cu, LQCD_WILSON_KERNEL=3): operator
-applications and a CG solve (fused |Dp|^2 / residual-update epilogues) against the oracle on lattices whose tiling qualifies
-for the kernel.  The library caches the kernel choice per process, hence a worker: the caller sets LQCD_WILSON_KERNEL=3
-(tests/test_emu_preflight.py under emulation, tests/test_zz_gpu_unverified.py on the B200)."""
+"""Correctness worker for the t-marching TMA Wilson kernel (csrc/wilson_tmarch.cu, the default Wilson path on regular geometries):
+operator applications and a CG solve (fused |Dp|^2 / residual-update epilogues) against the oracle on lattices whose tiling
+qualifies for the kernel, with several chunkings (LQCD_TM_CHUNKS).  The library caches its knobs per process, hence a worker
+(tests/test_emu_preflight.py under emulation with both bulk-copy completion schedules, tests/test_gpu_extended.py on the B200)."""
 import sys
 from pathlib import Path
 
@@ -28,7 +28,7 @@ def main():
             q.mul_(y, A, x)
             want = orc.apply(op, orc.WILSON, m, Uh, src)
             err = np.abs(y.to_host() - want).max() / np.abs(want).max()
-            print(f"k3 {dims} {nm}: rel err {err:.2e}", flush=True)
+            print(f"tmarch {dims} {nm}: rel err {err:.2e}", flush=True)
             ok &= bool(err < 1e-13)
         sol = q.similar(x)
         q.clear_fermion_(sol)
@@ -36,9 +36,9 @@ def main():
         info = q.solve_DinvX_(sol, q.DdagD(D), x)
         ref = orc.cg(op, orc.WILSON, Uh, src, eps=1e-18)
         dev = np.abs(sol.to_host() - ref["x"]).max() / np.abs(ref["x"]).max()
-        print(f"k3 {dims} CG iters {info['iters']} (oracle {ref['iters']}), solution rel dev {dev:.2e}", flush=True)
+        print(f"tmarch {dims} CG iters {info['iters']} (oracle {ref['iters']}), solution rel dev {dev:.2e}", flush=True)
         ok &= info["iters"] == ref["iters"] and bool(dev < 1e-10)
-    print("K3 OK" if ok else "K3 MISMATCH", flush=True)
+    print("TMARCH OK" if ok else "TMARCH MISMATCH", flush=True)
     sys.exit(0 if ok else 1)
 
 
