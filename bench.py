@@ -47,7 +47,7 @@ STAG_BYTES_PER_SITE = 672     # 576 links + 48 in + 48 out
 STAG_FLOP_PER_SITE = 582
 # N-independent fingerprints of the bench workload (hot links seed 111, Gaussian sources seed 112, kappa 0.12 / mass 0.5): measured
 # at N = 1 where the same run compares y = D x with the oracle; every N must reproduce them to 1e-12 (deterministic reductions).
-EXPECTED = {"32x32x32x32": {"norm_Dx_sq": 15486702.150002183, "staggered_norm_Dx_sq": None, "cg_converged_iters_eps1e-10": 43}}
+EXPECTED = {"32x32x32x32": {"norm_Dx_sq": 15490456.52178676, "staggered_norm_Dx_sq": 7083744.73603815, "cg_converged_iters_eps1e-10": 43}}
 KAPPA = 0.12
 BC = [1, 1, 1, -1]
 
@@ -288,13 +288,15 @@ def probe_pipe_isolated(lattice, local_rank):
 # ---------------------------------------------------------------------------------------------------
 EXPERIMENTS = {
     # name: (environment of the child, what it measures)
-    "default": ({}, "default Wilson kernel = t-marching TMA kernel (reference for the rows below; writes the 16^4 comparison vector)"),
-    "register_kernel": ({"LQCD_WILSON_KERNEL": "1"}, "register-resident one-thread-per-site Wilson kernel (round-1 default, fallback for irregular geometries)"),
+    "default": ({}, "default Wilson kernel: register-resident, one thread per site, two-row links (reference for the rows below; writes the 16^4 comparison vector)"),
+    "tmarch_kernel": ({"LQCD_WILSON_KERNEL": "4"}, "t-marching kernel with TMA-staged spinor window and link planes (wilson_tmarch.cu, experimental)"),
     "mrhs_r2": ({"LQCD_MRHS_R": "2"}, "12 right-hand sides, 2 per thread (lqcd_dslash_multi)"),
     "mrhs_r3": ({"LQCD_MRHS_R": "3"}, "12 right-hand sides, 3 per thread"),
-    "mrhs_r4": ({"LQCD_MRHS_R": "4"}, "12 right-hand sides, 4 per thread"),
-    "mrhs_smem": ({"LQCD_MRHS_SMEM": "1"}, "12 right-hand sides, links staged in shared memory by cp.async.bulk (one CTA per SM)"),
-    "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides per pass"),
+    "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides, default grouping (4 per thread)"),
+    "staggered_mrhs_r2": ({"LQCD_MRHS_R_STAGGERED": "2"}, "staggered, 2 right-hand sides per thread"),
+    "staggered_mrhs_r3": ({"LQCD_MRHS_R_STAGGERED": "3"}, "staggered, 3 right-hand sides per thread"),
+    "staggered_mrhs_r6": ({"LQCD_MRHS_R_STAGGERED": "6"}, "staggered, 6 right-hand sides per thread"),
+    "links_full": ({"LQCD_LINKS12": "0"}, "Dslash kernels reading the full 3x3 links instead of the two-row copy (links12.cu)"),
     "propagator": ({}, "12 point-source CGNR solves (measure_Pion_correlator.jl:333-409): lock-step lqcd_solve_multi vs 12 x lqcd_solve"),
     "clover": ({}, "Wilson-clover Dslash (csw = 1.5612)"),
     "evenodd": ({}, "even-odd preconditioned CGNR vs full CGNR, 16^4"),
@@ -351,7 +353,7 @@ def _experiment_body(name, dims, out):
         ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
         return mean.value
 
-    if name in ("default", "register_kernel"):
+    if name in ("default", "register_kernel", "links_full", "tmarch_kernel"):
         ctx, op, x, y = setup(small)
         ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
         got = y.to_host()
@@ -385,8 +387,8 @@ def _experiment_body(name, dims, out):
             res[key] = {"ms_outer_product_kernel": t, "GB/s_nominal (links + force + X, Y at the site and its 4 forward neighbours)": (576 + 576 + 2 * (192 if kind == L.WILSON else 48) * 5) * V / t / 1e6}
         out["ok"] = True
         out.update(res)
-    elif name.startswith("mrhs_") or name == "staggered_mrhs":
-        kind = L.STAGGERED if name == "staggered_mrhs" else L.WILSON
+    elif name.startswith("mrhs_") or name.startswith("staggered_mrhs"):
+        kind = L.STAGGERED if name.startswith("staggered_mrhs") else L.WILSON
         nrhs = 12
         ctx, op, x, y = setup(dims, kind)
         xs = [x] + [q.FermionField(ctx, kind) for _ in range(nrhs - 1)]
@@ -571,11 +573,14 @@ def run_experiments(lattice, local_rank, budget_s):
 # host plumbing only) on a different port, create contexts, connect over CUDA IPC and time the Dslash and a CG with the knob set
 # in their environment.  The parents only wait.  Same isolation argument as above.
 EXPERIMENTS_MULTI = {       # most informative first: the leg stops starting new ones when its time budget is used up
-    "default": ({}, "defaults (reference for the rows below)"),
-    "halo_poll_relaxed": ({"LQCD_HALO_POLL": "relaxed"}, "face CTAs poll the halo flags with ld.relaxed.sys instead of ld.acquire.sys"),
-    "pack_fence_gpu": ({"LQCD_PACK_FENCE": "g"}, "gpu-scope fence per pack CTA, one system fence by the last"),
-    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream (default with >= 2 partitioned directions)"),
-    "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel (default with one partitioned direction, small local volume)"),
+    "default": ({}, "defaults: Wilson Dslash + CG (reference for the knob rows), BASELINE configs[3] (32^4 Wilson-clover CG) and, on 8 ranks, "
+                    "configs[4] (32^3 x 64 staggered Nf = 2 RHMC trajectory, 12 poles)"),
+    "timeline": ({"LQCD_COMM_TIMING": "1"}, "in-kernel phase stamps of the Wilson Dslash (pack / interior / face tiles / flag waits)"),
+    "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel"),
+    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream"),
+    "tmarch_kernel": ({"LQCD_WILSON_KERNEL": "4"}, "t-marching TMA Wilson kernel (cyclic march: the two halo slices come last)"),
+    "links_full": ({"LQCD_LINKS12": "0"}, "full 3x3 links instead of the two-row copy"),
+    "pack_fence_sys": ({"LQCD_PACK_FENCE": "sys"}, "system-scope fence per pack CTA (round-1 default)"),
 }
 
 
@@ -621,13 +626,93 @@ def experiment_multi_child(name, dims):
     import torch
     t = torch.tensor([ms, cg_s], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    V = int(np.prod(dims))
+    out = {"name": name, "ok": True, "n_gpus": world, "procgrid": list(pg), "ms_per_apply": float(t[0]), "GFLOP/s": FLOP_PER_SITE * V / float(t[0]) / 1e6,
+           "cg_iters_per_s": it.value / float(t[1]), "norm_Dx_sq": norm_y, "cg_iters": it.value, "resid_sq": rs.value}
+    if name == "default":
+        try:
+            out["config4_wilson_clover_cg"] = _config4_clover_cg(ctx, dist, q, L, x, sol, V)
+        except Exception as exc:
+            out["config4_wilson_clover_cg"] = {"ok": False, "error": repr(exc)[:300]}
+        if world == 8 and os.environ.get("LQCD_EXP_CONFIG5", "1") != "0":
+            try:
+                out["config5_staggered_rhmc_trajectory"] = _config5_rhmc_trajectory(dist, q, L, pg, rank, dev)
+            except Exception as exc:
+                out["config5_staggered_rhmc_trajectory"] = {"ok": False, "error": repr(exc)[:300]}
     if rank == 0:
-        V = int(np.prod(dims))
-        out = {"name": name, "ok": True, "n_gpus": world, "procgrid": list(pg), "ms_per_apply": float(t[0]), "GFLOP/s": FLOP_PER_SITE * V / float(t[0]) / 1e6,
-               "cg_iters_per_s": it.value / float(t[1]), "norm_Dx_sq": norm_y, "cg_iters": it.value, "resid_sq": rs.value}
         print("EXPERIMENT " + json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _config4_clover_cg(ctx, dist, q, L, x, sol, V):
+    """BASELINE configs[3]: Wilson-clover CG (csw = 1.5612, src/system/parameter_structs.jl:125) on the decomposed lattice: iteration
+    count (must equal the single-GPU count, EXPECTED), iterations/s, true-residual check through the operator itself"""
+    op = L.LqcdOp()
+    op.kind, op.kappa, op.r, op.csw = L.WILSON, KAPPA, 1.0, 1.5612
+    for i, b in enumerate(BC):
+        op.bc[i] = b
+    ctx.barrier()
+    ctx.call("lqcd_clover_term", C.byref(op), None)         # leaves reach into the neighbour ranks' links (peer mapped)
+    ctx.barrier()
+    it, rs = C.c_int(0), C.c_double(0.0)
+    q.clear_fermion_(sol)
+    ctx.call("lqcd_solve", C.byref(op), sol.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 1e-10, 3000, C.byref(it), C.byref(rs), None)     # warm-up + count
+    n_conv = it.value
+    q.clear_fermion_(sol)
+    dist.barrier()
+    t0 = time.perf_counter()
+    ctx.call("lqcd_solve", C.byref(op), sol.h, x.h, L.SOLVER_CG, L.OP_DDAGD, 1e-10, 3000, C.byref(it), C.byref(rs), None)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    chk = q.FermionField(ctx, L.WILSON)
+    ctx.call("lqcd_dslash", C.byref(op), chk.h, sol.h, L.OP_DDAGD)
+    q.add_(chk, -1.0, x)
+    true_rr = q.dot(chk, chk).real
+    return {"ok": bool(true_rr < 1e-8 and it.value == n_conv), "csw": 1.5612, "cg_iters_eps1e-10": it.value, "resid_sq": rs.value, "true_resid_sq": true_rr,
+            "cg_iters_per_s": it.value / dt, "ms_per_solve": dt * 1e3}
+
+
+def _config5_rhmc_trajectory(dist, q, L, pg, rank, dev):
+    """BASELINE configs[4]: one molecular-dynamics trajectory of staggered Nf = 2 RHMC (test/test_Nf2.toml scaled to 32^3 x 64): x^(-1/4)
+    with 12 poles, every fermion force = ONE multi-shift CG + 12 accumulated outer products, leapfrog, all device resident
+    (lqcd_md_trajectory_rational); reports dH, the multi-shift iterations and the wall time"""
+    import numpy as np
+    from lqcd_b200 import rhmc
+    dims5 = tuple(int(v) for v in os.environ.get("LQCD_EXP_CONFIG5_DIMS", "32x32x32x64").split("x"))
+    ctx = q.get_context(dims5, procgrid=pg, rank=rank, device=dev)
+    q.connect_ranks(ctx, dist)
+    ra = rhmc.rational_approx(-2 / 8.0, 12, 0.22, 17.0)              # mass 0.5: spec(DdagD) in [0.25, 16.25]
+    al = np.ascontiguousarray(ra.alpha, dtype=np.float64)
+    sh = np.ascontiguousarray(ra.beta, dtype=np.float64)
+    pa, ps = al.ctypes.data_as(L.pdbl), sh.ctypes.data_as(L.pdbl)
+    op = L.LqcdOp()
+    op.kind, op.mass = L.STAGGERED, 0.5
+    for i, b in enumerate(BC):
+        op.bc[i] = b
+    eta, tmp = q.FermionField(ctx, L.STAGGERED), q.FermionField(ctx, L.STAGGERED)
+    q.gauss_distribution_fermion_(eta, 112)
+    its, it1, S = C.c_longlong(0), C.c_int(0), C.c_double(0.0)
+    steps, dtau = int(os.environ.get("LQCD_EXP_CONFIG5_STEPS", "5")), 0.02
+    ctx.call("lqcd_gauge_random", 111, 0.3)
+    ctx.call("lqcd_md_momenta_gaussian", 7)
+    K, G = C.c_double(), C.c_double()
+    H = []
+    wall = 0.0
+    for leg in range(2):
+        ctx.call("lqcd_md_kinetic", C.byref(K)); ctx.call("lqcd_md_gauge_action", 5.7, C.byref(G))
+        ctx.call("lqcd_rational_apply", C.byref(op), tmp.h, eta.h, float(ra.alpha0), pa, ps, len(al), 1e-18, 3000, C.byref(it1), C.byref(S))
+        H.append(K.value + G.value + S.value)
+        if leg == 0:
+            dist.barrier()
+            t0 = time.perf_counter()
+            ctx.call("lqcd_md_trajectory_rational", C.byref(op), eta.h, pa, ps, len(al), 5.7, dtau, steps, 0, 1e-18, 3000, C.byref(its))
+            ctx.synchronize()
+            wall = time.perf_counter() - t0
+    dH = H[1] - H[0]
+    return {"ok": bool(abs(dH) < 0.05 * abs(S.value) and its.value > 0), "lattice": "x".join(map(str, dims5)), "poles": len(al), "md_steps": steps, "dtau": dtau,
+            "dH": dH, "S_f": S.value, "multishift_cg_iters_total": its.value, "action_solve_iters": it1.value, "ms_per_trajectory": wall * 1e3,
+            "rational_max_rel_err": ra.max_rel_err}
 
 
 def run_experiments_multi(lattice, rank, local_rank, world, budget_s, barrier):
@@ -637,7 +722,7 @@ def run_experiments_multi(lattice, rank, local_rank, world, budget_s, barrier):
     t_start = time.perf_counter()
     for idx, (name, (env_extra, what)) in enumerate(EXPERIMENTS_MULTI.items()):
         barrier()                                       # all parents decide together (rank 0's clock is not shared: fixed schedule)
-        if (idx + 1) * 34 > budget_s:
+        if 60 + (idx + 1) * 34 > budget_s:
             results[name] = {"skipped": "time budget of the experiments leg", "what": what}
             continue
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
@@ -648,10 +733,13 @@ def run_experiments_multi(lattice, rank, local_rank, world, budget_s, barrier):
         res = {"ok": False}
         try:
             r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--experiment-multi", name, "--lattice", lattice], env=env,
-                               capture_output=True, text=True, timeout=75)
+                               capture_output=True, text=True, timeout=150 if name == "default" else 75)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("EXPERIMENT ")]
             if line:
                 res = json.loads(line[-1][len("EXPERIMENT "):])
+                tl = [ln for ln in r.stderr.splitlines() if ln.startswith("[lqcd comm timeline")]
+                if tl:
+                    res["timeline_rank0"] = tl[-1]
             elif rank == 0:
                 tail = (r.stdout + r.stderr).strip().splitlines()[-1:] or [""]
                 res["error"] = f"exit {r.returncode}: {tail[0][:200]}"
@@ -814,6 +902,7 @@ def run_b200(args, dims):
         D = q.DiracOperator.__new__(q.DiracOperator)                  # operator bound to the links already on the device
         D.op, D.ctx, D.kind, D.mode = op, ctx, L.WILSON, L.OP_D
         D.eps, D.maxsteps, D.verbose, D.method, D.last = 0.0, args.cg_iters, 1, "bicg", {}
+        D._bound_epoch = getattr(ctx, "binding_epoch", None)           # bound to what the device holds (no host copy of these links)
         hxn, hyn = hx.numpy(), hy.numpy()
 
         def e2e_step_3call():

@@ -11,7 +11,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "liblqcd_b200.so"
-SOURCES = ["context.cu", "wilson_dslash.cu", "wilson_tmarch.cu", "staggered_dslash.cu", "blas.cu", "solvers.cu", "comm.cu", "force.cu", "clover.cu", "wilson_clover.cu", "wilson_eo.cu", "host_pipeline.cu", "gauge_md.cu", "mrhs.cu", "gauge_io.cu", "staggered_eo.cu", "wilson_general_r.cu", "clover_force.cu"]
+SOURCES = ["context.cu", "wilson_dslash.cu", "wilson_tmarch.cu", "links12.cu", "staggered_dslash.cu", "blas.cu", "solvers.cu", "comm.cu", "force.cu", "clover.cu", "wilson_clover.cu", "wilson_eo.cu", "host_pipeline.cu", "gauge_md.cu", "mrhs.cu", "gauge_io.cu", "staggered_eo.cu", "wilson_general_r.cu", "clover_force.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -17,6 +17,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef LQCD_MBAR_ASM_LOOP
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -26,4 +27,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra K3_WAIT;\n"
         "K3_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+#endif
 }

@@ -45,6 +45,8 @@
 #include <cstdlib>
 #include <vector>
 
+#define LQCD_TIMING_SLOTS 1024
+
 struct HandleBlob {
     uint32_t magic;
     int32_t rank;
@@ -76,8 +78,8 @@ struct CommState {
     int face[4];                      // face sites per direction
     int nbr[4][2];                    // neighbour ranks [mu][0 lower, 1 upper]
     unsigned long long halo_seq;
-    int *bsites;                      // device table of boundary sites (ascending site index)
-    int nbsites;
+    unsigned long long *timing;       // LQCD_COMM_TIMING=1: [LQCD_TIMING_SLOTS][8] phase stamps (see comm_timing_report)
+    unsigned long long timing_first;  // halo_seq of slot 0
     int *cta_order;                   // Dslash CTA permutation: tiles without face sites first, face tiles last
     int n_interior;
     const cplx *gauge_peer[LQCD_MAX_RANKS];   // every rank's link array (nullptr where the mapping failed)
@@ -121,20 +123,6 @@ static int comm_alloc(lqcd_ctx *ctx) {
     if (e != cudaSuccess) { delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMalloc(comm %zu) -> %s", off, cudaGetErrorString(e)); }
     e = cudaMemset(c->base, 0, c->bytes);
     if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cudaMemset(comm) -> %s", cudaGetErrorString(e)); }
-    {   // boundary-site table: sites with a coordinate on a face of a partitioned direction
-        std::vector<int> bs;
-        for (int s = 0; s < g.V; s++) {
-            int r = s, cc[4];
-            for (int i = 0; i < 4; i++) { cc[i] = r % d[i]; r /= d[i]; }
-            bool b = false;
-            for (int i = 0; i < 4; i++) if (g.part[i] && (cc[i] == 0 || cc[i] == d[i] - 1)) b = true;
-            if (b) bs.push_back(s);
-        }
-        c->nbsites = (int)bs.size();
-        e = cudaMalloc(&c->bsites, sizeof(int) * (bs.size() + 1));
-        if (e == cudaSuccess) e = cudaMemcpy(c->bsites, bs.data(), sizeof(int) * bs.size(), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "boundary table -> %s", cudaGetErrorString(e)); }
-    }
     {   // CTA order for the fused-halo Dslash kernels
         const int ncta = (g.nblk + g.wpc - 1) / g.wpc;
         std::vector<int> inner, face;
@@ -155,7 +143,7 @@ static int comm_alloc(lqcd_ctx *ctx) {
         inner.insert(inner.end(), face.begin(), face.end());
         e = cudaMalloc(&c->cta_order, sizeof(int) * (inner.size() + 1));
         if (e == cudaSuccess) e = cudaMemcpy(c->cta_order, inner.data(), sizeof(int) * inner.size(), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(c->base); cudaFree(c->bsites); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cta order table -> %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { cudaFree(c->base); delete c; return lqcd_fail(ctx, LQCD_ERR_CUDA, "cta order table -> %s", cudaGetErrorString(e)); }
     }
     c->peer[ctx->rank] = c->base;
     ctx->comm = c;
@@ -170,7 +158,7 @@ int comm_destroy(lqcd_ctx *ctx) {
     for (int r = 0; r < ctx->nranks; r++)
         if (c->gauge_opened[r]) cudaIpcCloseMemHandle((void *)c->gauge_peer[r]);
     cudaFree(c->base);
-    cudaFree(c->bsites);
+    cudaFree(c->timing);
     cudaFree(c->cta_order);
     delete c;
     ctx->comm = nullptr;
@@ -297,26 +285,13 @@ int comm_check_error(lqcd_ctx *ctx) {
 
 // ---- kernels -------------------------------------------------------------------------------------------
 struct HaloArgs {
-    const cplx *in;            // pack: source spinor.  exterior: unused
-    cplx *out;                 // exterior: y (read-modify-write)
+    const cplx *in;            // source spinor
     const cplx *gauge;
     Geom g;
     int kind, dagger;
-    double coef;               // Wilson: -kappa ; staggered: sign
-    double bc[4];
-    int pfirst[4], plast[4];   // this rank sits on the global low / high boundary in mu
-    HaloOut hout;              // pack: destinations, flags, CTA prefix, ticket, seq
-    const cplx *recv[4][2];    // exterior: [mu][0] data from lower nbr (for my low face), [1] from upper nbr (for my high face)
-    const unsigned long long *recv_flag[4][2];
-    unsigned long long seq;
-    int *err;
+    HaloOut hout;              // destinations, flags, CTA prefix, ticket, seq
     const SolverState *st;
     int use_state;
-    const int *bsites;         // exterior: table of boundary sites (on at least one partitioned face)
-    int nbsites;
-    DslashFuse fuse;           // exterior: fused epilogue (reductions finished here)
-    Reduce red;
-    unsigned int part_offset;  // exterior: partials deposited by the interior kernel precede ours
 };
 
 __global__ void __launch_bounds__(128) halo_pack_kernel(const HaloArgs A) {
@@ -324,324 +299,123 @@ __global__ void __launch_bounds__(128) halo_pack_kernel(const HaloArgs A) {
     halo_pack_cta(A.g, A.kind, A.dagger, A.in, A.gauge, A.hout, blockIdx.x);
 }
 
-// Wilson: add the off-rank hop(s) of direction MU at face site s into acc (12 complex, in units of "hopping sum").
-template <int MU>
-__device__ __forceinline__ void wilson_ext_dir(const HaloArgs &A, cplx (&acc)[12], int s, int side, int f) {
-    const cplx *src = A.recv[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
-    cplx h0[3], h1[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) { h0[c] = __ldcg(src + c * 32); h1[c] = __ldcg(src + (3 + c) * 32); }
-    const double phase = side == 0 ? (A.pfirst[MU] ? A.bc[MU] : 1.0) : (A.plast[MU] ? A.bc[MU] : 1.0);
-    if (phase != 1.0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
-    }
-    if (side == 0) {                        // my low face, backward hop: data is already U^dag P psi
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            if (A.dagger) reconstruct<MU, -1>(acc, a, h0[a], h1[a]);
-            else          reconstruct<MU, +1>(acc, a, h0[a], h1[a]);
-        }
-    } else {                                // my high face, forward hop: apply U_mu(n)
-        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            cplx g0 = cmake(0, 0), g1 = cmake(0, 0);
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                cplx u = ldg128(lk + (a * 3 + b) * 32);
-                cfma(g0, u, h0[b]); cfma(g1, u, h1[b]);
-            }
-            if (A.dagger) reconstruct<MU, +1>(acc, a, g0, g1);
-            else          reconstruct<MU, -1>(acc, a, g0, g1);
-        }
-    }
-}
+bool wilson_tmarch_ok(const lqcd_ctx *ctx, const lqcd_op *op);      // wilson_tmarch.cu
 
-template <int MU>
-__device__ __forceinline__ void stag_ext_dir(const HaloArgs &A, cplx (&acc)[3], int s, int side, int f, double eta) {
-    const cplx *src = A.recv[MU][side] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
-    cplx h[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) h[c] = __ldcg(src + c * 32);
-    if (side == 0) {
-        const double cf = -0.5 * eta * (A.pfirst[MU] ? A.bc[MU] : 1.0);
-#pragma unroll
-        for (int c = 0; c < 3; c++) { acc[c].x = fma(cf, h[c].x, acc[c].x); acc[c].y = fma(cf, h[c].y, acc[c].y); }
-    } else {
-        const double cf = 0.5 * eta * (A.plast[MU] ? A.bc[MU] : 1.0);
-        const cplx *lk = A.gauge + ((size_t)(s >> 5) * 4 + MU) * (9 * 32) + (s & 31);
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            cplx g = cmake(0, 0);
-#pragma unroll
-            for (int b = 0; b < 3; b++) cfma(g, ldg128(lk + (a * 3 + b) * 32), h[b]);
-            acc[a].x = fma(cf, g.x, acc[a].x); acc[a].y = fma(cf, g.y, acc[a].y);
-        }
-    }
-}
-
-#define EXT_DIR_W(MU, coord, dim)                                                            \
-    if (A.g.part[MU]) {                                                                      \
-        if ((coord) == 0) wilson_ext_dir<MU>(A, acc, s, 0, face_index<MU>(A.g, x, y, z, t)); \
-        if ((coord) == (dim)-1) wilson_ext_dir<MU>(A, acc, s, 1, face_index<MU>(A.g, x, y, z, t)); \
-    }
-#define EXT_DIR_S(MU, coord, dim, eta)                                                       \
-    if (A.g.part[MU]) {                                                                      \
-        if ((coord) == 0) stag_ext_dir<MU>(A, acc, s, 0, face_index<MU>(A.g, x, y, z, t), eta); \
-        if ((coord) == (dim)-1) stag_ext_dir<MU>(A, acc, s, 1, face_index<MU>(A.g, x, y, z, t), eta); \
-    }
-
-// One thread per BOUNDARY site (precomputed table): all its off-rank hops are added in registers and y is
-// updated once, so sites on several faces (edges/corners of a T x Z decomposition) have no write race, and the
-// fused <w,y>, |y|^2 reductions of these sites are finished here together with the interior kernel's partials.
-__global__ void __launch_bounds__(128) halo_exterior_kernel(const HaloArgs A) {
-    if (A.use_state && A.st->done) return;
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        int good = 1;
-        for (int m = 0; m < 4 && good; m++) {
-            if (!A.g.part[m]) continue;
-            for (int side = 0; side < 2 && good; side++)
-                while (ld_acquire_sys(A.recv_flag[m][side]) < A.seq)
-                    if (clock64() - t0 > A.red.cr.timeout_cycles) { good = 0; *A.err = 1; break; }
-        }
-        ok = good;
-    }
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double red[3] = {0.0, 0.0, 0.0};
-    if (ok && i < A.nbsites) {
-        const int s = A.bsites[i];
-        int r = s;
-        const int x = r % A.g.X; r /= A.g.X;
-        const int y = r % A.g.Y; r /= A.g.Y;
-        const int z = r % A.g.Z;
-        const int t = r / A.g.Z;
-        if (A.kind == LQCD_WILSON) {
-            cplx acc[12];
-#pragma unroll
-            for (int k = 0; k < 12; k++) acc[k] = cmake(0, 0);
-            EXT_DIR_W(0, x, A.g.X) EXT_DIR_W(1, y, A.g.Y) EXT_DIR_W(2, z, A.g.Z) EXT_DIR_W(3, t, A.g.T)
-            const size_t base = (size_t)(s >> 5) * (12 * 32) + (s & 31);
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                cplx v = A.out[base + k * 32];
-                v.x = fma(A.coef, acc[k].x, v.x); v.y = fma(A.coef, acc[k].y, v.y);
-                A.out[base + k * 32] = v;
-                if (A.fuse.dot_with) {
-                    cplx w = ldg128(A.fuse.dot_with + base + k * 32);
-                    red[0] = fma(w.x, v.x, red[0]); red[0] = fma(w.y, v.y, red[0]);
-                    red[1] = fma(w.x, v.y, red[1]); red[1] = fma(-w.y, v.x, red[1]);
-                }
-                red[2] = fma(v.x, v.x, red[2]); red[2] = fma(v.y, v.y, red[2]);
-            }
-        } else {
-            cplx acc[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) acc[k] = cmake(0, 0);
-            const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
-            EXT_DIR_S(0, x, A.g.X, 1.0)
-            EXT_DIR_S(1, y, A.g.Y, ((gx & 1) ? -1.0 : 1.0))
-            EXT_DIR_S(2, z, A.g.Z, (((gx + gy) & 1) ? -1.0 : 1.0))
-            EXT_DIR_S(3, t, A.g.T, (((gx + gy + gz) & 1) ? -1.0 : 1.0))
-            const size_t base = (size_t)(s >> 5) * (3 * 32) + (s & 31);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                cplx v = A.out[base + k * 32];
-                v.x = fma(A.coef, acc[k].x, v.x); v.y = fma(A.coef, acc[k].y, v.y);
-                A.out[base + k * 32] = v;
-                if (A.fuse.dot_with) {
-                    cplx w = ldg128(A.fuse.dot_with + base + k * 32);
-                    red[0] = fma(w.x, v.x, red[0]); red[0] = fma(w.y, v.y, red[0]);
-                    red[1] = fma(w.x, v.y, red[1]); red[1] = fma(-w.y, v.x, red[1]);
-                }
-                red[2] = fma(v.x, v.x, red[2]); red[2] = fma(v.y, v.y, red[2]);
-            }
-        }
-    }
-    if (A.fuse.dot_with || A.fuse.want_norm)
-        grid_reduce_finish<3>(red, A.red, A.fuse.finish, A.part_offset, A.part_offset + gridDim.x, 1);
-}
-
+// One operator application across ranks.  The halo producer (halo_pack.cuh) either leads the Dslash kernel itself ("self-pack":
+// the first npack CTAs of the grid) or runs as its own kernel on the highest-priority stream; the Dslash kernel consumes the
+// neighbours' slots in its face tiles, which are last in the CTA order and wait on the sequence flags.  (Round 1 also had a
+// three-kernel form with a separate exterior kernel and host-timed variants of it: slower at every N, removed in round 2.)
 int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
     CommState *c = ctx->comm;
     if (!c || !c->connected) return lqcd_fail(ctx, LQCD_ERR_COMM, "multi-rank context is not connected (lqcd_comm_export / lqcd_comm_connect)");
     const Geom &g = ctx->g;
-    HaloArgs A;
-    memset(&A, 0, sizeof A);
-    A.in = x; A.out = y; A.gauge = ctx->gauge; A.g = g; A.kind = op->kind; A.dagger = dagger;
-    A.coef = (op->kind == LQCD_WILSON) ? -op->kappa : (dagger ? -1.0 : 1.0);
     const unsigned long long seq = ++c->halo_seq;
     const int slot = (int)(seq & 1);
-    A.seq = seq;
-    A.hout.seq = seq;
-    {
-        static int gf = -1;
-        if (gf < 0) { const char *e = getenv("LQCD_PACK_FENCE"); gf = (e && e[0] == 'g') ? 1 : 0; }
-        A.hout.gpu_fence = gf;
+    // measured on 2 / 8 B200 (profiles/r1g_*, round-1 experiments leg): a gpu-scope fence per pack CTA with ONE cumulative system
+    // fence by the last pack CTA is faster than a system fence per CTA at every N (N = 2: 0.115 vs 0.125 ms, N = 8: 0.042 vs 0.045 ms)
+    static int sys_fence = -1, timing = -1, self_pack_env = -2;
+    if (sys_fence < 0) { const char *e = getenv("LQCD_PACK_FENCE"); sys_fence = (e && e[0] == 's') ? 1 : 0; }
+    if (timing < 0) { const char *e = getenv("LQCD_COMM_TIMING"); timing = (e && atoi(e) >= 1) ? 1 : 0; }
+    if (self_pack_env == -2) { const char *e = getenv("LQCD_SELF_PACK"); self_pack_env = e ? (atoi(e) != 0) : -1; }
+    unsigned long long *tm = nullptr;
+    if (timing) {
+        if (!c->timing) {
+            CUDA_TRY(ctx, cudaMalloc(&c->timing, sizeof(unsigned long long) * 8 * LQCD_TIMING_SLOTS));
+            std::vector<unsigned long long> init(8 * LQCD_TIMING_SLOTS, 0ull);
+            for (int i = 0; i < LQCD_TIMING_SLOTS; i++) { init[i * 8 + 0] = init[i * 8 + 2] = init[i * 8 + 4] = ~0ull; }
+            CUDA_TRY(ctx, cudaMemcpy(c->timing, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+            c->timing_first = seq;
+        }
+        if (seq - c->timing_first < LQCD_TIMING_SLOTS) tm = c->timing + (seq - c->timing_first) * 8;
     }
-    A.hout.ticket = (unsigned int *)(c->base + c->off_ticket);
-    A.err = (int *)(c->base + c->off_err);
-    A.st = ctx->red.st; A.use_state = fuse ? fuse->use_state : 0;
-    A.bsites = c->bsites; A.nbsites = c->nbsites;
-    A.red = ctx->red;
+    const bool tmarch = op->kind == LQCD_WILSON && wilson_tmarch_ok(ctx, op);     // consumes the slots itself, fed by the separate pack kernel
+    const int npart = g.part[0] + g.part[1] + g.part[2] + g.part[3];
+    const int self_pack = tmarch ? 0 : (self_pack_env >= 0 ? self_pack_env : (g.V <= (1 << 18) && (npart == 1 || g.V < (1 << 15))));
+    const int pbs = self_pack ? 32 * g.wpc : 128;                                   // threads per pack CTA
+    HaloOut O;
+    HaloIn H;
+    memset(&O, 0, sizeof O);
+    memset(&H, 0, sizeof H);
+    O.seq = seq; O.gpu_fence = !sys_fence; O.ticket = (unsigned int *)(c->base + c->off_ticket); O.timing = tm;
+    H.seq = seq; H.err = (int *)(c->base + c->off_err); H.cta_order = c->cta_order; H.n_interior = c->n_interior;
+    H.timeout_cycles = ctx->red.cr.timeout_cycles; H.timing = tm;
     int ncta = 0;
     for (int mu = 0; mu < 4; mu++) {
-        A.bc[mu] = op->bc[mu];
-        A.pfirst[mu] = ctx->pcoord[mu] == 0; A.plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
-        A.hout.cta0[mu] = ncta;      // number of CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
+        H.pfirst[mu] = ctx->pcoord[mu] == 0; H.plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
+        O.cta0[mu] = ncta;           // number of pack CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
         if (!g.part[mu]) continue;
-        ncta += (2 * c->face[mu] + 127) / 128;
+        ncta += (2 * c->face[mu] + pbs - 1) / pbs;
         const int lo = c->nbr[mu][0], hi = c->nbr[mu][1];
         // my low face feeds the LOWER neighbour's "from upper" (side 1) slot; my high face the UPPER neighbour's side 0
-        A.hout.send[mu][0] = (cplx *)(c->peer[lo] + c->halo_off[mu][1][slot]);
-        A.hout.send[mu][1] = (cplx *)(c->peer[hi] + c->halo_off[mu][0][slot]);
-        A.hout.send_flag[mu][0] = (unsigned long long *)(c->peer[lo] + c->off_halo_flags) + (mu * 2 + 1) * 2 + slot;
-        A.hout.send_flag[mu][1] = (unsigned long long *)(c->peer[hi] + c->off_halo_flags) + (mu * 2 + 0) * 2 + slot;
+        O.send[mu][0] = (cplx *)(c->peer[lo] + c->halo_off[mu][1][slot]);
+        O.send[mu][1] = (cplx *)(c->peer[hi] + c->halo_off[mu][0][slot]);
+        O.send_flag[mu][0] = (unsigned long long *)(c->peer[lo] + c->off_halo_flags) + (mu * 2 + 1) * 2 + slot;
+        O.send_flag[mu][1] = (unsigned long long *)(c->peer[hi] + c->off_halo_flags) + (mu * 2 + 0) * 2 + slot;
         for (int side = 0; side < 2; side++) {
-            A.recv[mu][side] = (const cplx *)(c->base + c->halo_off[mu][side][slot]);
-            A.recv_flag[mu][side] = (const unsigned long long *)(c->base + c->off_halo_flags) + (mu * 2 + side) * 2 + slot;
+            H.recv[mu][side] = (const cplx *)(c->base + c->halo_off[mu][side][slot]);
+            H.recv_flag[mu][side] = (const unsigned long long *)(c->base + c->off_halo_flags) + (mu * 2 + side) * 2 + slot;
         }
     }
-    A.hout.cta0[4] = ncta;
-    // Default: SELF-PACKING Dslash kernel -- the first npack CTAs of the kernel itself ship this application's halo
-    // (halo_pack.cuh), the interior tiles follow, the face tiles (last) consume the neighbours' slots: one launch,
-    // no second stream, no events.  LQCD_SELF_PACK=0 falls back to a separate pack kernel on the priority stream.
-    // Measured (2xB200): local volume 32.32.16.8 -> 39.0 us self-packing vs 41.7 us separate pack; local volume
-    // 32.32.32.16 -> 122.5-126.5 vs 119.9 us (the leading pack CTAs delay the first interior wave).  8xB200, grid 1.1.2.4 (two
-    // partitioned directions, local volume 32.32.16.8): 52.0 us / 5257 CG it/s self-packing vs 51.1 us / 5658 it/s separate pack
-    // (profiles/r1g_scale_n8{,_sep}.json; identical iterates) -- with two face pairs the leading pack phase is twice as long.
-    // Default: self-pack for local volumes up to 2^18 sites when ONE direction is partitioned (and for tiny local volumes below
-    // 2^15 sites, where the difference is noise and the hardware-verified test configurations stay exactly as verified),
-    // separate pack kernel otherwise; LQCD_SELF_PACK=0/1 forces either.
-    static int relaxed_poll = -1;
-    if (relaxed_poll < 0) { const char *e = getenv("LQCD_HALO_POLL"); relaxed_poll = (e && e[0] == 'r') ? 1 : 0; }
-    static int self_pack_env = -2;
-    if (self_pack_env == -2) { const char *e = getenv("LQCD_SELF_PACK"); self_pack_env = e ? (atoi(e) != 0) : -1; }
-    const int npart = g.part[0] + g.part[1] + g.part[2] + g.part[3];
-    const int self_pack = self_pack_env >= 0 ? self_pack_env : (g.V <= (1 << 18) && (npart == 1 || g.V < (1 << 15)));
+    O.cta0[4] = ncta;
+    // Self-packing (one launch, no second stream) for small local volumes with ONE partitioned direction, the separate pack kernel
+    // otherwise -- measured on 2 / 8 B200 in round 1: local volume 32.32.16.8 with one partitioned direction 39.0 us self-packing vs
+    // 41.7 us separate; 32.32.32.16: 122.5-126.5 vs 119.9 us; 8 GPUs, two partitioned directions: 52.0 vs 51.1 us.  LQCD_SELF_PACK=0/1 forces.
     if (self_pack) {
-        const int bs = 32 * g.wpc;
-        HaloOut O = A.hout;
-        int np = 0;
-        for (int mu = 0; mu < 4; mu++) { O.cta0[mu] = np; if (g.part[mu]) np += (2 * c->face[mu] + bs - 1) / bs; }
-        O.cta0[4] = np;
-        HaloIn H;
-        memset(&H, 0, sizeof H);
-        for (int mu = 0; mu < 4; mu++) {
-            H.pfirst[mu] = A.pfirst[mu]; H.plast[mu] = A.plast[mu];
-            for (int side = 0; side < 2; side++) { H.recv[mu][side] = A.recv[mu][side]; H.recv_flag[mu][side] = A.recv_flag[mu][side]; }
-        }
-        H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
-        H.timeout_cycles = ctx->red.cr.timeout_cycles;
-        H.relaxed_poll = relaxed_poll;
         if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
         return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
     }
-    // pack on the second stream (overlaps the interior kernel); it needs x, which earlier main-stream work produced
-    static int two_streams = -1, timing = -1;
-    static cudaEvent_t te[4];
-    static double tacc[3] = {0, 0, 0};
-    static long tcount = 0;
-    if (two_streams < 0) { const char *e = getenv("LQCD_PACK_STREAM"); two_streams = (e && atoi(e) == 0) ? 0 : 1; }
-    // LQCD_COMM_TIMING=2: non-intrusive timeline (events recorded on both streams, no host sync until 200 samples)
-    static const int TLN = 200;
-    static cudaEvent_t tl[4][TLN];      // 0 pack start, 1 pack end, 2 dslash start, 3 dslash end
-    static int tln = 0, timeline = 0;
-    if (timing < 0) {
-        const char *e = getenv("LQCD_COMM_TIMING"); timing = (e && atoi(e) == 1) ? 1 : 0;
-        timeline = (e && atoi(e) == 2) ? 1 : 0;
-        if (timing) { two_streams = 0; for (int i = 0; i < 4; i++) cudaEventCreate(&te[i]); }
-        if (timeline) for (int i = 0; i < 4; i++) for (int j = 0; j < TLN; j++) cudaEventCreate(&tl[i][j]);
-    }
-    const bool tlrec = timeline && tln < TLN;
-    if (timing) cudaEventRecord(te[0], ctx->stream);
-    cudaStream_t ps = two_streams ? ctx->stream2 : ctx->stream;
-    if (two_streams) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_int, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->ev_int, 0));
-    }
-    if (tlrec) cudaEventRecord(tl[0][tln], ps);
-    halo_pack_kernel<<<ncta, 128, 0, ps>>>(A);
+    // pack on the priority stream (overlaps the interior tiles); it needs x, which earlier main-stream work produced
+    HaloArgs A;
+    memset(&A, 0, sizeof A);
+    A.in = x; A.gauge = ctx->gauge; A.g = g; A.kind = op->kind; A.dagger = dagger; A.hout = O;
+    A.st = ctx->red.st; A.use_state = fuse ? fuse->use_state : 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_int, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_int, 0));
+    halo_pack_kernel<<<ncta, 128, 0, ctx->stream2>>>(A);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    if (tlrec) cudaEventRecord(tl[1][tln], ps);
-    if (two_streams) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pack, ps));
-    if (timing) cudaEventRecord(te[1], ctx->stream);
-    static int fused = -1;
-    if (fused < 0) { const char *e = getenv("LQCD_FUSED_HALO"); fused = (e && atoi(e) == 0) ? 0 : 1; }
-    if (fused) {
-        // ONE kernel on the critical path: the Dslash kernel itself consumes the halo slots (face tiles run last and
-        // wait on the neighbours' flags in-kernel); reductions finish there as on a single GPU.
-        HaloIn H;
-        memset(&H, 0, sizeof H);
-        for (int mu = 0; mu < 4; mu++) {
-            H.pfirst[mu] = A.pfirst[mu]; H.plast[mu] = A.plast[mu];
-            for (int side = 0; side < 2; side++) { H.recv[mu][side] = A.recv[mu][side]; H.recv_flag[mu][side] = A.recv_flag[mu][side]; }
-        }
-        H.seq = seq; H.err = A.err; H.cta_order = c->cta_order; H.n_interior = c->n_interior;
-        H.timeout_cycles = ctx->red.cr.timeout_cycles;
-        H.relaxed_poll = relaxed_poll;
-        if (tlrec) cudaEventRecord(tl[2][tln], ctx->stream);
-        if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
-        else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
-        if (tlrec) {
-            cudaEventRecord(tl[3][tln], ctx->stream);
-            if (++tln == TLN) {
-                cudaEventSynchronize(tl[3][TLN - 1]); cudaEventSynchronize(tl[1][TLN - 1]);
-                double a[6] = {0, 0, 0, 0, 0, 0};
-                int n = 0;
-                for (int k = TLN / 2; k < TLN; k++, n++) {          // second half: steady state
-                    float ms;
-                    cudaEventElapsedTime(&ms, tl[0][k], tl[1][k]); a[0] += ms;          // pack duration
-                    cudaEventElapsedTime(&ms, tl[2][k], tl[3][k]); a[1] += ms;          // dslash duration
-                    cudaEventElapsedTime(&ms, tl[3][k - 1], tl[2][k]); a[2] += ms;      // gap: previous dslash end -> this start
-                    cudaEventElapsedTime(&ms, tl[2][k], tl[0][k]); a[3] += ms;          // pack start relative to dslash start
-                    cudaEventElapsedTime(&ms, tl[2][k], tl[1][k]); a[4] += ms;          // pack end relative to dslash start
-                    cudaEventElapsedTime(&ms, tl[3][k - 1], tl[3][k]); a[5] += ms;      // period
-                }
-                fprintf(stderr, "[lqcd timeline rank %d] pack %.1f us | dslash %.1f us | gap %.1f us | pack start %+.1f us, end %+.1f us after dslash start | period %.1f us\n",
-                        ctx->rank, 1e3 * a[0] / n, 1e3 * a[1] / n, 1e3 * a[2] / n, 1e3 * a[3] / n, 1e3 * a[4] / n, 1e3 * a[5] / n);
-            }
-        }
-        if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
-        if (timing) {
-            cudaEventRecord(te[2], ctx->stream);
-            cudaEventSynchronize(te[2]);
-            for (int i = 0; i < 2; i++) { float ms; cudaEventElapsedTime(&ms, te[i], te[i + 1]); tacc[i] += ms; }
-            if (++tcount % 64 == 0)
-                fprintf(stderr, "[lqcd comm timing rank %d] pack %.1f us  fused dslash %.1f us (mean of %ld)\n",
-                        ctx->rank, 1e3 * tacc[0] / tcount, 1e3 * tacc[1] / tcount, tcount);
-        }
-        return LQCD_OK;
-    }
-    if (fuse && fuse->axpy_r)
-        return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_FUSED_HALO=0 (separate exterior kernel) needs LQCD_CG_FUSE=0 as well");
-    // interior: all sites with off-rank hops masked; reductions over non-face sites deposited as partials
-    const bool want_red = fuse && (fuse->dot_with || fuse->want_norm);
-    DslashFuse f2 = DslashFuse();
-    if (fuse) f2 = *fuse;
-    f2.interior_only = 1;
-    if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
-    else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, &f2, ctx->stream));
-    if (timing) cudaEventRecord(te[2], ctx->stream);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream2));
+    if (op->kind == LQCD_WILSON) LQCD_TRY(launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
+    else                         LQCD_TRY(launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H));
     // x must not be overwritten by later main-stream kernels before the pack has read it
-    if (two_streams) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
-    A.fuse = f2; A.fuse.interior_only = 0;
-    A.part_offset = want_red ? (unsigned int)((g.nblk + g.wpc - 1) / g.wpc) : 0u;
-    halo_exterior_kernel<<<(c->nbsites + 127) / 128, 128, 0, ctx->stream>>>(A);
-    ctx->launches++;
-    CUDA_TRY(ctx, cudaGetLastError());
-    if (timing) {       // development aid: serialises the host; prints the mean split every 64 applications
-        cudaEventRecord(te[3], ctx->stream);
-        cudaEventSynchronize(te[3]);
-        for (int i = 0; i < 3; i++) { float ms; cudaEventElapsedTime(&ms, te[i], te[i + 1]); tacc[i] += ms; }
-        if (++tcount % 64 == 0)
-            fprintf(stderr, "[lqcd comm timing rank %d] pack %.1f us  interior %.1f us  exterior %.1f us (mean of %ld)\n",
-                    ctx->rank, 1e3 * tacc[0] / tcount, 1e3 * tacc[1] / tcount, 1e3 * tacc[2] / tcount, tcount);
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pack, 0));
+    return LQCD_OK;
+}
+
+// LQCD_COMM_TIMING=1: per-application phase stamps (%globaltimer, ns) written by the kernels themselves -- pack CTAs, interior
+// tiles, face tiles, time spent waiting for the neighbours' flags -- averaged over the recorded applications.  No host
+// synchronisation is added, so the timeline is the one of the timed run.
+int comm_timing_report(lqcd_ctx *ctx, const char *what) {
+    CommState *c = ctx->comm;
+    if (!c || !c->timing) return LQCD_OK;
+    std::vector<unsigned long long> h(8 * LQCD_TIMING_SLOTS);
+    CUDA_TRY(ctx, cudaMemcpy(h.data(), c->timing, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double a[7] = {0, 0, 0, 0, 0, 0, 0}, period = 0.0;
+    int n = 0;
+    unsigned long long prev_end = 0;
+    const long long used = (long long)(c->halo_seq - c->timing_first + 1);
+    const int last = (int)(used < LQCD_TIMING_SLOTS ? used : LQCD_TIMING_SLOTS);
+    for (int i = last / 2; i < last; i++) {                      // second half: steady state
+        const unsigned long long *s = &h[(size_t)i * 8];
+        if (s[2] == ~0ull && s[4] == ~0ull) continue;
+        unsigned long long t0 = s[0] < s[2] ? s[0] : s[2];
+        if (s[4] < t0) t0 = s[4];
+        const unsigned long long end = s[5] > s[3] ? s[5] : s[3];
+        if (s[0] != ~0ull) { a[0] += (double)(s[0] - t0); a[1] += (double)(s[1] - t0); }
+        if (s[2] != ~0ull) a[2] += (double)(s[3] - t0);
+        if (s[4] != ~0ull) { a[3] += (double)(s[4] - t0); a[4] += (double)(s[5] - t0); }
+        a[5] += (double)s[6]; a[6] += (double)s[7];
+        if (prev_end && end > prev_end) period += (double)(end - prev_end);
+        prev_end = end;
+        n++;
     }
+    if (n > 1)
+        fprintf(stderr, "[lqcd comm timeline rank %d, %s, mean of %d applications, us after the first CTA started] pack %.1f..%.1f | interior tiles end %.1f | "
+                        "face tiles %.1f..%.1f | flag wait: max %.1f, sum over face CTAs %.1f | period %.1f\n",
+                ctx->rank, what, n, 1e-3 * a[0] / n, 1e-3 * a[1] / n, 1e-3 * a[2] / n, 1e-3 * a[3] / n, 1e-3 * a[4] / n, 1e-3 * a[6] / n, 1e-3 * a[5] / n,
+                1e-3 * period / (n - 1));
+    cudaFree(c->timing);
+    c->timing = nullptr;
     return LQCD_OK;
 }
 

@@ -99,6 +99,7 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     ctx->eo = nullptr; ctx->eo_active = 0; ctx->stag_even_solve = 0; ctx->pipe = nullptr; ctx->queue = nullptr; ctx->mrhs = nullptr;
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_k = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
+    ctx->links12 = nullptr; ctx->links12_epoch = ~0ull; ctx->links12_ok = false; ctx->links12_dev = 0.0; ctx->links12_scratch = nullptr;
 #define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
     CT(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -151,6 +152,7 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     mrhs_destroy(ctx);
     for (int k = 0; k < 2; k++)
         for (auto *f : ctx->scratch[k]) if (f) { cudaFree(f->d); delete f; }
+    cudaFree(ctx->links12); cudaFree(ctx->links12_scratch);
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover); cudaFree(ctx->clover_k);
     cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);

@@ -92,6 +92,7 @@ __device__ __forceinline__ void stag_pack_site(const cplx *__restrict__ in, cons
 // Work of pack CTA number `pcta` (0 <= pcta < H.cta0[4]) with blockDim.x threads; all threads of the CTA must call it.
 __device__ __forceinline__ void halo_pack_cta(const Geom &g, int kind, int dagger, const cplx *__restrict__ in,
                                               const cplx *__restrict__ gauge, const HaloOut &H, int pcta) {
+    const unsigned long long ts0 = (H.timing && threadIdx.x == 0) ? global_ns() : 0ull;
     int mu = 0;
     while (mu < 3 && pcta >= H.cta0[mu + 1]) mu++;
     const int d[4] = {g.X, g.Y, g.Z, g.T};
@@ -134,4 +135,5 @@ __device__ __forceinline__ void halo_pack_cta(const Geom &g, int kind, int dagge
         __threadfence_system();
         if (g.part[m]) st_release_sys(H.send_flag[m][side], H.seq);
     }
+    if (H.timing && threadIdx.x == 0) stamp_span(H.timing, 0, ts0, global_ns());
 }

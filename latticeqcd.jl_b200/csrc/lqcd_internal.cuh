@@ -95,13 +95,16 @@ struct Reduce {
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// relaxed system-scope load: coherent at L2, no acquire fence (no L1 invalidation on this SM).  Round-2 experiment
-// knob LQCD_HALO_POLL=relaxed: safe together with halo data read through __ldcg (never cached in L1) because the spin
-// loop's control dependency keeps the data loads behind the flag observation.
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ unsigned long long global_ns() {           // %globaltimer: one clock for all SMs (phase stamps)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamps of one application (LQCD_COMM_TIMING=1): [0,1] pack CTAs first start / last end, [2,3] interior tiles, [4,5] face
+// tiles, [6] ns all face CTAs spent waiting for the neighbours' flags, [7] the longest such wait
+__device__ __forceinline__ void stamp_span(unsigned long long *tm, int cls, unsigned long long t0, unsigned long long t1) {
+    atomicMin(tm + 2 * cls, t0);
+    atomicMax(tm + 2 * cls + 1, t1);
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
@@ -147,6 +150,10 @@ struct lqcd_ctx {
     cudaEvent_t ev0, ev1, ev_pack, ev_int, ev_poll[2];
     cplx *gauge;               // AoSoA-32 links
     bool gauge_valid;
+    // "two-row" copy of the links for the Dslash kernels (links12.cu): rows 0 and 1 of every SU(3) matrix, the third row is
+    // rebuilt in registers as conj(row0 x row1).  Valid for (links12_epoch == gauge_epoch); links12_ok says whether the links
+    // passed the unitarity test (|U[2][b] - conj(row0 x row1)[b]| <= 1e-13 everywhere) -- if not, the kernels read the full links.
+    cplx *links12; uint64_t links12_epoch; bool links12_ok; double links12_dev; double *links12_scratch;
     // staging
     void *stage; size_t stage_bytes;
     // reductions
@@ -232,7 +239,6 @@ struct DslashFuse {
     int use_state;             // kernels early-exit when st->done
     double shift;              // y += shift * x  (multi-shift base system: (DdagD + s) )
     const cplx *shift_src;     // field multiplied by `shift` (the input of the first hop of DdagD)
-    int interior_only;         // multi-GPU interior pass: reduce over non-boundary sites, deposit partials only
     cplx *axpy_r;              // CG: do not store y; instead r <- r - alpha*y (alpha from SolverState) and reduce |r|^2 in red2
     int cta_off, cta_count;    // single-rank sub-range launch (host_pipeline.cu): CTAs [cta_off, cta_off + cta_count) of the
                                // t-slowest tile order = a slab of t-slices; cta_count = 0 -> whole lattice.  No reductions.
@@ -252,7 +258,7 @@ struct HaloIn {
     const int *cta_order;
     int n_interior;
     long long timeout_cycles;
-    int relaxed_poll;                           // 1: poll the flags with ld.relaxed.sys (experiment, default 0 = acquire)
+    unsigned long long *timing;                 // LQCD_COMM_TIMING=1: this application's 8 phase stamps (comm.cu), else null
 };
 
 struct HaloOut {
@@ -262,12 +268,14 @@ struct HaloOut {
     unsigned int *ticket;                // last-pack-CTA detector (self resetting)
     unsigned long long seq;              // application number published in the flags
     int gpu_fence;                       // 1: pack CTAs fence at gpu scope only; the LAST pack CTA's system fence (cumulative) covers them
+    unsigned long long *timing;          // LQCD_COMM_TIMING=1: phase stamps of this application, else null
 };
 
 struct WilsonArgs {
     cplx *out;
     const cplx *in;
     const cplx *gauge;
+    const cplx *links12;  // two-row links (G12 kernels), else unused
     Geom g;
     double kappa;
     double bc[4];
@@ -295,6 +303,8 @@ struct ForceHalo {
 };
 int comm_force_halo(lqcd_ctx *ctx, ForceHalo *out);      // comm.cu: bumps the force sequence number
 
+// links12.cu: (re)builds ctx->links12 if stale; *use = 1 if the Dslash kernels may read it (SU(3) links, not switched off)
+int ensure_links12(lqcd_ctx *ctx, int *use);
 int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
                          const DslashFuse *fuse, cudaStream_t s, const HaloIn *halo = nullptr, const HaloOut *hout = nullptr);
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,

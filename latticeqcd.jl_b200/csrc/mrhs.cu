@@ -25,7 +25,6 @@
 #include "reduce.cuh"
 #include "site_map.cuh"
 #include "wilson_kernel.cuh"      // clover_apply (site-local clover term of the single-RHS kernel)
-#include "bulk_copy.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -39,6 +38,7 @@ struct MrhsArgs {
     cplx *out[LQCD_MAX_RHS];
     MrhsRed red[LQCD_MAX_RHS];
     const cplx *gauge;
+    const cplx *links12; // two-row links (links12.cu) when the links are SU(3), else null: same choice as the single-RHS kernels
     const cplx *clover;  // Wilson-clover: packed clover blocks (wilson_kernel.cuh), else null
     Geom g;
     double kappa, mass, sign;
@@ -72,10 +72,8 @@ __device__ __forceinline__ unsigned live_mask(const MrhsArgs &A, int rhs0) {
 template <int MU, int FWD, int DAG, int R>
 __device__ __forceinline__ void hop_m(cplx (&acc)[R][12], const MrhsArgs &A, int rhs0, unsigned mask, int ns, int ls, bool wrapped, double phase) {
     constexpr int S = (FWD ^ DAG) ? -1 : +1;
-    const cplx *lk = A.gauge + ((size_t)(ls >> 5) * 4 + MU) * (9 * 32) + (ls & 31);
     cplx u[9];
-#pragma unroll
-    for (int e = 0; e < 9; e++) u[e] = __ldg(lk + e * 32);
+    if (A.links12) load_link<MU, 1, 0>(u, A.links12, ls); else load_link<MU, 0, 0>(u, A.gauge, ls);      // grid-uniform
     const size_t so = (size_t)(ns >> 5) * (12 * 32) + (ns & 31);
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -172,136 +170,11 @@ __global__ void __launch_bounds__(128, MINB) wilson_mrhs_kernel(const MrhsArgs A
 }
 
 
-// ---- Wilson, links staged in shared memory by bulk copies (LQCD_MRHS_SMEM=1, experimental) ------------------------------------
-// The register-resident version above shares a link between R = 3 right-hand sides.  Here a warp stages ALL links its 32-site
-// block needs -- its own 18 KB record (the four forward links of every site) and, per direction, the 4.5 KB mu-slab of the block
-// one step back (the backward links) -- in shared memory with five cp.async.bulk copies that complete on an mbarrier, and then runs
-// over all nrhs right-hand sides reading links from shared memory and spinors from global memory: 36 KB of link traffic per
-// block whatever nrhs is (1152/nrhs B per site and right-hand side, of which only the own record is compulsory HBM traffic:
-// the neighbour slabs are L2 hits), + 384 B of spinors -> 432 B at nrhs = 12.  The per-RHS arithmetic and reductions are those of
-// wilson_mrhs_kernel (bit-identical results).  One CTA of 4 warps holds 4 x 36 KB = 144 KB: one CTA per SM, the loads of a whole
-// right-hand side (96 x 128-bit per thread) are independent and in flight together.  Regular tilings only.
-#define MS_OWN (36 * 32)                    // complex numbers of a block's link record
-#define MS_SLAB (9 * 32)                    // ... of one direction's slab
-#define MS_WARP (MS_OWN + 4 * MS_SLAB)      // per-warp staging area (36 864 B)
-
-template <int MU, int FWD, int DAG>
-__device__ __forceinline__ void hop_sm(cplx (&acc)[12], const cplx *__restrict__ sp, const cplx *lk, bool wrapped, double phase) {
-    constexpr int S = (FWD ^ DAG) ? -1 : +1;      // sp: neighbour spinor (global, lane applied); lk: link element 0 (shared, lane applied)
-    cplx h0[3], h1[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        cplx p0 = __ldg(sp + (0 + c) * 32), p1 = __ldg(sp + (3 + c) * 32);
-        cplx p2 = __ldg(sp + (6 + c) * 32), p3 = __ldg(sp + (9 + c) * 32);
-        project<MU, S>(h0[c], h1[c], p0, p1, p2, p3);
-    }
-    if (wrapped) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            if (FWD) { const cplx u = lk[(a * 3 + b) * 32]; cfma(g0, u, h0[b]); cfma(g1, u, h1[b]); }
-            else     { const cplx u = lk[(b * 3 + a) * 32]; cfmac(g0, u, h0[b]); cfmac(g1, u, h1[b]); }
-        }
-        reconstruct<MU, S>(acc, a, g0, g1);
-    }
-}
-
-template <int DAG>
-__global__ void __launch_bounds__(128, 1) wilson_mrhs_smem_kernel(const MrhsArgs A) {
-    extern __shared__ __align__(128) unsigned char ms_smem[];
-    const Geom &g = A.g;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    cplx *own = reinterpret_cast<cplx *>(ms_smem) + (size_t)warp * MS_WARP;
-    cplx *slab = own + MS_OWN;                                                      // [4][9][32]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ms_smem + (size_t)4 * MS_WARP * sizeof(cplx)) + warp;
-    const int blk = block_of_warp(g, blockIdx.x, warp);
-    const bool active = blk < g.nblk;
-    // block-lattice coordinates and the blocks one step back in every direction
-    int bc[4], r = blk;
-    for (int i = 0; i < 3; i++) { bc[i] = r % g.nb[i]; r /= g.nb[i]; }
-    bc[3] = r;
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (active) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(MS_WARP * sizeof(cplx)));
-            bulk_g2s(own, A.gauge + (size_t)blk * MS_OWN, (uint32_t)(MS_OWN * sizeof(cplx)), bar);
-            int stride = 1;
-            for (int mu = 0; mu < 4; mu++) {
-                const int nbk = blk + (bc[mu] == 0 ? (g.nb[mu] - 1) : -1) * stride;
-                bulk_g2s(slab + mu * MS_SLAB, A.gauge + ((size_t)nbk * 4 + mu) * MS_SLAB, (uint32_t)(MS_SLAB * sizeof(cplx)), bar);
-                stride *= g.nb[mu];
-            }
-        }
-    }
-    __syncwarp();
-    int x = 0, y = 0, z = 0, t = 0, s = 0;
-    const cplx *lkb[4];                       // backward link of direction mu for this lane (element 0)
-    if (active) {
-        s = blk * 32 + lane;
-        site_coords(g, s, x, y, z, t);
-        // position inside the block: lane = l0 + s0 (l1 + s1 (l2 + s2 l3))
-        int l[4], q = lane, st = 1;
-        for (int i = 0; i < 3; i++) { l[i] = q % g.s[i]; q /= g.s[i]; }
-        l[3] = q;
-        for (int mu = 0; mu < 4; mu++) {
-            lkb[mu] = l[mu] > 0 ? own + mu * MS_SLAB + (lane - st) : slab + mu * MS_SLAB + (lane + (g.s[mu] - 1) * st);
-            st *= g.s[mu];
-        }
-        mbar_wait(bar, 0);
-    }
-    const size_t base = (size_t)blk * (12 * 32) + lane;
-    const double mk = -A.kappa;
-    bool reduced = false;
-    for (int j = 0; j < A.nrhs; j++) {
-        if (A.use_state && A.red[j].st->done) continue;             // CTA-uniform
-        double red[3] = {0.0, 0.0, 0.0};
-        if (active) {
-            const cplx *in = A.in[j];
-            cplx acc[12];
-#pragma unroll
-            for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
-#define MS_PAIR(MU, coord, dim, strd)                                                                                     \
-            {                                                                                                             \
-                const bool wf = (coord == dim - 1), wb = (coord == 0);                                                    \
-                const int nf = wf ? s - (dim - 1) * (strd) : s + (strd), nb_ = wb ? s + (dim - 1) * (strd) : s - (strd);  \
-                hop_sm<MU, 1, DAG>(acc, in + (size_t)(nf >> 5) * (12 * 32) + (nf & 31), own + MU * MS_SLAB + lane, wf, A.bc[MU]);   \
-                hop_sm<MU, 0, DAG>(acc, in + (size_t)(nb_ >> 5) * (12 * 32) + (nb_ & 31), lkb[MU], wb, A.bc[MU]);         \
-            }
-            MS_PAIR(0, x, g.X, 1)
-            MS_PAIR(1, y, g.Y, g.X)
-            MS_PAIR(2, z, g.Z, g.X * g.Y)
-            MS_PAIR(3, t, g.T, g.X * g.Y * g.Z)
-#undef MS_PAIR
-            cplx *dst = A.out[j];
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                const cplx xi = __ldg(in + base + k * 32);
-                const cplx yk = cmake(fma(mk, acc[k].x, xi.x), fma(mk, acc[k].y, xi.y));
-                red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
-                dst[base + k * 32] = yk;
-            }
-        }
-        if (A.want_norm) {
-            if (reduced) __syncthreads();
-            grid_reduce_finish<3>(red, reduce_of(A.red[j]), A.finish);
-            reduced = true;
-        }
-    }
-}
-
 // ---- staggered -------------------------------------------------------------------------------------------------------------
 template <int MU, int FWD, int R>
 __device__ __forceinline__ void shop_m(cplx (&acc)[R][3], const MrhsArgs &A, int rhs0, unsigned mask, int ns, int ls, double coef) {
-    const cplx *lk = A.gauge + ((size_t)(ls >> 5) * 4 + MU) * (9 * 32) + (ls & 31);
     cplx u[9];
-#pragma unroll
-    for (int e = 0; e < 9; e++) u[e] = __ldg(lk + e * 32);
+    if (A.links12) load_link<MU, 1, 0>(u, A.links12, ls); else load_link<MU, 0, 0>(u, A.gauge, ls);      // grid-uniform
     const size_t so = (size_t)(ns >> 5) * (3 * 32) + (ns & 31);
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -521,20 +394,22 @@ static void fill_red(const MrhsWork *w, MrhsRed *red) {
     }
 }
 
-// right-hand sides per thread: Wilson 2 / 3 / 4 (LQCD_MRHS_R).  ptxas (sm_100a): R = 2 fits the single-RHS kernel's 168-register
-// budget (100 B of spills), R = 3 needs __launch_bounds__(128, 2) (255 registers, no spills), R = 4 spills 528 B at 255.
-// Default 3 where it divides the work evenly (12 sources -> 4 groups).  Staggered 4 / 8 / 12 (no spills): the smallest covering nrhs.
+// right-hand sides per thread.  Wilson 2 / 3 (LQCD_MRHS_R): R = 2 fits the single-RHS kernel's 168-register budget, R = 3 needs
+// __launch_bounds__(128, 2) (255 registers, no spills).  Measured on B200 at 32^4, 12 right-hand sides, full links (round 2,
+// profiles/r2a_experiments_n1.json): R = 2 0.99x, R = 3 1.04x per right-hand side against the single-RHS kernel; R = 4 (528 B of
+// spills) 0.56x and a variant with the links staged in shared memory by bulk copies (one CTA per SM) 0.71x -- both removed.
+// Staggered 2 / 3 / 4 / 6 / 8 / 12 (LQCD_MRHS_R_STAGGERED, no spills); default 4.
 static int wilson_group(int nrhs) {
     static int env = -1;
     if (env < 0) { const char *e = getenv("LQCD_MRHS_R"); env = e ? atoi(e) : 0; }
-    if (env == 2 || env == 3 || env == 4) return env;
-    return nrhs == 2 ? 2 : ((nrhs % 3 == 0 || nrhs == 5) ? 3 : (nrhs % 4 == 0 ? 4 : 3));
+    if (env == 2 || env == 3) return env;
+    return (nrhs == 2 || nrhs == 4) ? 2 : 3;
 }
 static int staggered_group(int nrhs) {
     static int env = -1;
     if (env < 0) { const char *e = getenv("LQCD_MRHS_R_STAGGERED"); env = e ? atoi(e) : 0; }
-    if (env == 4 || env == 8 || env == 12) return env;
-    return nrhs <= 4 ? 4 : (nrhs <= 8 ? 8 : 12);
+    if (env == 2 || env == 3 || env == 4 || env == 6 || env == 8 || env == 12) return env;
+    return nrhs <= 2 ? 2 : (nrhs == 3 ? 3 : 4);          // measured at 32^4, 12 right-hand sides (B200, round 2): R = 4 1.39x, 6 1.12x, 12 0.81x per RHS
 }
 
 // one Dslash of all right-hand sides: out[j] = D in[j] (dagger: D^dag); want_norm -> |out[j]|^2 reduced, `finish` applied per RHS
@@ -549,6 +424,9 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
         A.in[j] = in[j]; A.out[j] = out[j];
     }
     fill_red(w, A.red);
+    int g12 = 0;
+    LQCD_TRY(ensure_links12(ctx, &g12));
+    A.links12 = g12 ? ctx->links12 : nullptr;
     A.gauge = ctx->gauge; A.g = ctx->g; A.kappa = op->kappa; A.mass = op->mass; A.sign = dagger ? -1.0 : 1.0;
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     A.nrhs = nrhs; A.want_norm = want_norm; A.finish = finish; A.use_state = use_state;
@@ -558,33 +436,19 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
         if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
         if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "multi-RHS Wilson kernel: LQCD_WPC > 4 is not supported");
         if (op->csw != 0.0) { LQCD_TRY(ensure_clover(ctx, op)); A.clover = ctx->clover; }
-        static int smem_links = -1;
-        if (smem_links < 0) { const char *e = getenv("LQCD_MRHS_SMEM"); smem_links = (e && atoi(e) == 1) ? 1 : 0; }
-        if (smem_links && ctx->g.regular && bs == 128 && !A.clover) {       // experimental: links staged in shared memory by bulk copies
-            const size_t smem = (size_t)4 * MS_WARP * sizeof(cplx) + 4 * sizeof(uint64_t) + 32;
-            static bool attr_set = false;
-            if (!attr_set) {
-                CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_mrhs_smem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_mrhs_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
-            }
-            if (dagger) wilson_mrhs_smem_kernel<1><<<gx, bs, smem, ctx->stream>>>(A);
-            else        wilson_mrhs_smem_kernel<0><<<gx, bs, smem, ctx->stream>>>(A);
-            ctx->launches++;
-            CUDA_TRY(ctx, cudaGetLastError());
-            return LQCD_OK;
-        }
         int R = wilson_group(nrhs);
-        if (A.clover && R > 3) R = 3;                       // the clover epilogue needs the registers of the fourth right-hand side
         const dim3 grid(gx, (nrhs + R - 1) / R);
 #define WM(R_, MB_, CL_) do { if (dagger) wilson_mrhs_kernel<1, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); else wilson_mrhs_kernel<0, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); } while (0)
         if (A.clover) { if (R == 2) WM(2, 2, 1); else WM(3, 2, 1); }          // Wilson-clover: 2 or 3 right-hand sides per thread
-        else if (R == 2) WM(2, 3, 0); else if (R == 3) WM(3, 2, 0); else WM(4, 2, 0);
+        else if (R == 2) WM(2, 3, 0); else WM(3, 2, 0);
 #undef WM
     } else {
         const int R = staggered_group(nrhs);
         const dim3 grid(gx, (nrhs + R - 1) / R);
-        if (R == 4) staggered_mrhs_kernel<4><<<grid, bs, 0, ctx->stream>>>(A);
+        if (R == 2) staggered_mrhs_kernel<2><<<grid, bs, 0, ctx->stream>>>(A);
+        else if (R == 3) staggered_mrhs_kernel<3><<<grid, bs, 0, ctx->stream>>>(A);
+        else if (R == 4) staggered_mrhs_kernel<4><<<grid, bs, 0, ctx->stream>>>(A);
+        else if (R == 6) staggered_mrhs_kernel<6><<<grid, bs, 0, ctx->stream>>>(A);
         else if (R == 8) staggered_mrhs_kernel<8><<<grid, bs, 0, ctx->stream>>>(A);
         else staggered_mrhs_kernel<12><<<grid, bs, 0, ctx->stream>>>(A);
     }

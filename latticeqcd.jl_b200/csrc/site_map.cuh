@@ -41,13 +41,15 @@ __host__ __device__ __forceinline__ int face_index(const Geom &g, int x, int y, 
 __device__ __forceinline__ void wait_halo_flags(const Geom &g, const HaloIn &H) {
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
+        const unsigned long long w0 = H.timing ? global_ns() : 0ull;
         bool good = true;
         for (int m = 0; m < 4 && good; m++) {
             if (!g.part[m]) continue;
             for (int side = 0; side < 2 && good; side++)
-                while ((H.relaxed_poll ? ld_relaxed_sys(H.recv_flag[m][side]) : ld_acquire_sys(H.recv_flag[m][side])) < H.seq)
+                while (ld_acquire_sys(H.recv_flag[m][side]) < H.seq)
                     if (clock64() - t0 > H.timeout_cycles) { good = false; *H.err = 1000000 + (m * 2 + side) * 100000 + (int)(H.seq % 100000); break; }
         }
+        if (H.timing) { const unsigned long long dt = global_ns() - w0; atomicAdd(H.timing + 6, dt); atomicMax(H.timing + 7, dt); }
     }
     __syncthreads();
 }

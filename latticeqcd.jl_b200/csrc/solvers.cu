@@ -27,6 +27,7 @@ int blas_bi_p(lqcd_ctx *ctx, cplx *p, const cplx *r, const cplx *v, size_t n);
 int blas_ms_update_xp(lqcd_ctx *ctx, const MSPtrs &P, const cplx *r, size_t n, int it);
 int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse);   // comm.cu
 int comm_check_error(lqcd_ctx *ctx);
+int comm_timing_report(lqcd_ctx *ctx, const char *what);
 
 static int check_op(const lqcd_ctx *ctx, const lqcd_op *op) {
     if (!op) return lqcd_fail(ctx, LQCD_ERR_ARG, "null operator descriptor");
@@ -315,6 +316,7 @@ extern "C" int lqcd_time_dslash(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         if (ms_mean) *ms_mean = ms / reps;
         if (ms_min) *ms_min = ms / reps;
+        if (ctx->nranks > 1) LQCD_TRY(comm_timing_report(ctx, op->kind == LQCD_WILSON ? "Wilson Dslash" : "staggered Dslash"));
         return comm_check_error(ctx);
     }
     for (int i = 0; i < reps; i++) {

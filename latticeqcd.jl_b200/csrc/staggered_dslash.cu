@@ -13,12 +13,14 @@
 #include "reduce.cuh"
 #include "site_map.cuh"
 #include "halo_pack.cuh"
+#include "link_load.cuh"
 #include <cstring>
 
 struct StagArgs {
     cplx *out;
     const cplx *in;
     const cplx *gauge;
+    const cplx *links12;   // two-row links (G12 kernels, links12.cu), else unused
     Geom g;
     double mass;
     double sign;      // +1 D, -1 D^dag
@@ -29,20 +31,21 @@ struct StagArgs {
     HaloOut hout;     // MULTI == 2 (self-packing) only
 };
 
-template <int MU, int FWD>
+template <int MU, int FWD, int G12>
 __device__ __forceinline__ void shop(cplx (&acc)[3], const cplx *__restrict__ in, const cplx *__restrict__ gauge,
                                      int ns, int ls, double coef) {
     const cplx *sp = in + (size_t)(ns >> 5) * (3 * 32) + (ns & 31);
+    cplx u[9];
+    load_link<MU, G12, 0>(u, gauge, ls);
     cplx v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) v[c] = cscale(coef, ldg128(sp + c * 32));
-    const cplx *lk = gauge + ((size_t)(ls >> 5) * 4 + MU) * (9 * 32) + (ls & 31);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
 #pragma unroll
         for (int b = 0; b < 3; b++) {
-            if (FWD) cfma(acc[a], ldg128(lk + (a * 3 + b) * 32), v[b]);
-            else     cfmac(acc[a], ldg128(lk + (b * 3 + a) * 32), v[b]);
+            if (FWD) cfma(acc[a], u[a * 3 + b], v[b]);
+            else     cfmac(acc[a], u[b * 3 + a], v[b]);
         }
     }
 }
@@ -71,26 +74,27 @@ __device__ __forceinline__ void halo_shop(cplx (&acc)[3], const StagArgs &A, int
     }
 }
 
-template <int MU, int MULTI>
+template <int MU, int MULTI, int G12>
 __device__ __forceinline__ void shop_pair(cplx (&acc)[3], const StagArgs &A, int s, int coord, int dim, int stride, double eta,
                                           int x, int y, int z, int t) {
+    const cplx *links = G12 ? A.links12 : A.gauge;
     {
         bool w = (coord == dim - 1);
         int ns = w ? s - (dim - 1) * stride : s + stride;
         double coef = 0.5 * eta * (w ? A.bc[MU] : 1.0);
-        if (!(w && A.g.part[MU])) shop<MU, 1>(acc, A.in, A.gauge, ns, s, coef);
+        if (!(w && A.g.part[MU])) shop<MU, 1, G12>(acc, A.in, links, ns, s, coef);
         else if (MULTI) halo_shop<MU, 1>(acc, A, s, face_index<MU>(A.g, x, y, z, t), eta);
     }
     {
         bool w = (coord == 0);
         int ns = w ? s + (dim - 1) * stride : s - stride;
         double coef = -0.5 * eta * (w ? A.bc[MU] : 1.0);
-        if (!(w && A.g.part[MU])) shop<MU, 0>(acc, A.in, A.gauge, ns, ns, coef);
+        if (!(w && A.g.part[MU])) shop<MU, 0, G12>(acc, A.in, links, ns, ns, coef);
         else if (MULTI) halo_shop<MU, 0>(acc, A, s, face_index<MU>(A.g, x, y, z, t), eta);
     }
 }
 
-template <int MULTI>
+template <int MULTI, int G12>
 __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -101,8 +105,10 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
         bid -= npack;
     }
     int cta = bid + A.fuse.cta_off;
+    unsigned long long ts0 = 0ull;
     if (MULTI) {
         cta = A.halo.cta_order[bid];
+        if (A.halo.timing && threadIdx.x == 0) ts0 = global_ns();
         if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
     }
     const int blk = block_of_warp(A.g, cta, warp);
@@ -112,18 +118,14 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
         const int s = blk * 32 + lane;
         int x, y, z, t;
         site_coords(A.g, s, x, y, z, t);
-        // multi-GPU interior pass: face sites are finished (and reduced) by the exterior kernel
-        const bool skip_red = A.fuse.interior_only &&
-            ((A.g.part[0] && (x == 0 || x == A.g.X - 1)) || (A.g.part[1] && (y == 0 || y == A.g.Y - 1)) ||
-             (A.g.part[2] && (z == 0 || z == A.g.Z - 1)) || (A.g.part[3] && (t == 0 || t == A.g.T - 1)));
         const int gx = x + A.g.o[0], gy = y + A.g.o[1], gz = z + A.g.o[2];
         cplx acc[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) acc[k] = cmake(0.0, 0.0);
-        shop_pair<0, MULTI>(acc, A, s, x, A.g.X, 1, 1.0, x, y, z, t);
-        shop_pair<1, MULTI>(acc, A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0, x, y, z, t);
-        shop_pair<2, MULTI>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, x, y, z, t);
-        shop_pair<3, MULTI>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, x, y, z, t);
+        shop_pair<0, MULTI, G12>(acc, A, s, x, A.g.X, 1, 1.0, x, y, z, t);
+        shop_pair<1, MULTI, G12>(acc, A, s, y, A.g.Y, A.g.X, (gx & 1) ? -1.0 : 1.0, x, y, z, t);
+        shop_pair<2, MULTI, G12>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, ((gx + gy) & 1) ? -1.0 : 1.0, x, y, z, t);
+        shop_pair<3, MULTI, G12>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, ((gx + gy + gz) & 1) ? -1.0 : 1.0, x, y, z, t);
         const size_t base = (size_t)blk * (3 * 32) + lane;
         cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
         const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
@@ -139,17 +141,18 @@ __global__ void __launch_bounds__(256) staggered_dslash_kernel(const StagArgs A)
                 cplx rv = A.fuse.axpy_r[base + k * 32];
                 yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
             }
-            if (A.fuse.dot_with && !skip_red) {
+            if (A.fuse.dot_with) {
                 cplx w = ldg128(A.fuse.dot_with + base + k * 32);
                 red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
                 red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
             }
-            if (!skip_red) { red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]); }
+            red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
             dst[base + k * 32] = yk;
         }
     }
+    if (MULTI && A.halo.timing && threadIdx.x == 0) stamp_span(A.halo.timing, bid >= A.halo.n_interior ? 2 : 1, ts0, global_ns());
     if (A.fuse.dot_with || A.fuse.want_norm)
-        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid, gridDim.x - (unsigned)npack);
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, 1, (unsigned)bid, gridDim.x - (unsigned)npack);
 }
 
 int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger,
@@ -166,9 +169,18 @@ int launch_staggered_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cpl
     const bool sub = A.fuse.cta_count > 0;               // slab launch (host_pipeline.cu): single rank, plain epilogue only
     if (sub && (halo || A.fuse.dot_with || A.fuse.want_norm || A.fuse.axpy_r)) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range Dslash launch: no halo / reductions");
     const int grid = sub ? A.fuse.cta_count : (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
-    if (halo && hout) staggered_dslash_kernel<2><<<grid, bs, 0, s>>>(A);
-    else if (halo) staggered_dslash_kernel<1><<<grid, bs, 0, s>>>(A);
-    else      staggered_dslash_kernel<0><<<grid, bs, 0, s>>>(A);
+    int g12 = 0;                                         // two-row links when the links are SU(3) (links12.cu): 480 instead of 672 B/site
+    LQCD_TRY(ensure_links12(ctx, &g12));
+    A.links12 = g12 ? ctx->links12 : nullptr;
+    if (g12) {
+        if (halo && hout) staggered_dslash_kernel<2, 1><<<grid, bs, 0, s>>>(A);
+        else if (halo) staggered_dslash_kernel<1, 1><<<grid, bs, 0, s>>>(A);
+        else      staggered_dslash_kernel<0, 1><<<grid, bs, 0, s>>>(A);
+    } else {
+        if (halo && hout) staggered_dslash_kernel<2, 0><<<grid, bs, 0, s>>>(A);
+        else if (halo) staggered_dslash_kernel<1, 0><<<grid, bs, 0, s>>>(A);
+        else      staggered_dslash_kernel<0, 0><<<grid, bs, 0, s>>>(A);
+    }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;

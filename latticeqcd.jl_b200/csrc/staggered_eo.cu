@@ -143,7 +143,7 @@ static int stag_hop(lqcd_ctx *ctx, EoState *e, const lqcd_op *op, int out_parity
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     A.fuse = fuse ? *fuse : DslashFuse();
     A.red = ctx->red;
-    if (A.fuse.shift_src || A.fuse.interior_only) return lqcd_fail(ctx, LQCD_ERR_ARG, "staggered even-site hop: unsupported fused epilogue");
+    if (A.fuse.shift_src) return lqcd_fail(ctx, LQCD_ERR_ARG, "staggered even-site hop: unsupported fused epilogue");
     const int bs = 32 * e->gh.wpc, grid = (e->gh.nblk + e->gh.wpc - 1) / e->gh.wpc;
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported");
     staggered_eo_hop_kernel<<<grid, bs, 0, ctx->stream>>>(A);

@@ -12,19 +12,21 @@
 #include "wilson_kernel.cuh"
 
 int launch_wilson_clover(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, int multi, int lh, int grid, int bs, cudaStream_t s) {
-    if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
-#define CK(MT, MB, MU_, LH_)                                                                      \
+    if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 4 is not supported by the Wilson kernel");
+    // two-row links as in the plain Wilson launcher (wilson_dslash.cu)
+    int g12 = 0;
+    LQCD_TRY(ensure_links12(ctx, &g12));
+    WilsonArgs B = A;
+    B.links12 = g12 ? ctx->links12 : nullptr;
+#define CK(MU_, LH_, G_)                                                                          \
     do {                                                                                          \
-        if (dagger) wilson_dslash_kernel<1, MT, MB, MU_, LH_, 1><<<grid, bs, 0, s>>>(A);          \
-        else        wilson_dslash_kernel<0, MT, MB, MU_, LH_, 1><<<grid, bs, 0, s>>>(A);          \
+        if (dagger) wilson_dslash_kernel<1, MU_, LH_, 1, G_><<<grid, bs, 0, s>>>(B);              \
+        else        wilson_dslash_kernel<0, MU_, LH_, 1, G_><<<grid, bs, 0, s>>>(B);              \
     } while (0)
-#define CL(MT, MB)                                                                                \
-    do {                                                                                          \
-        if (lh) { if (multi == 2) CK(MT, MB, 2, 1); else if (multi == 1) CK(MT, MB, 1, 1); else CK(MT, MB, 0, 1); } \
-        else    { if (multi == 2) CK(MT, MB, 2, 0); else if (multi == 1) CK(MT, MB, 1, 0); else CK(MT, MB, 0, 0); } \
-    } while (0)
-    if (bs > 128) CL(256, 1); else CL(128, 3);
-#undef CL
+#define CG(MU_, LH_) do { if (g12) CK(MU_, LH_, 1); else CK(MU_, LH_, 0); } while (0)
+    if (lh) { if (multi == 2) CG(2, 1); else if (multi == 1) CG(1, 1); else CG(0, 1); }
+    else    { if (multi == 2) CG(2, 0); else if (multi == 1) CG(1, 0); else CG(0, 0); }
+#undef CG
 #undef CK
     CUDA_TRY(ctx, cudaGetLastError());
     return LQCD_OK;

@@ -30,36 +30,28 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     A.red = ctx->red;
     if (halo) A.halo = *halo; else memset(&A.halo, 0, sizeof A.halo);
     if (hout) A.hout = *hout; else memset(&A.hout, 0, sizeof A.hout);
-    A.clover = nullptr;
+    A.clover = nullptr; A.links12 = nullptr;
     if (op->csw != 0.0) { LQCD_TRY(ensure_clover(ctx, op)); A.clover = ctx->clover; }
     const int bs = 32 * ctx->g.wpc;
     const bool sub = A.fuse.cta_count > 0;               // slab launch (host_pipeline.cu): single rank, plain epilogue only
     if (sub && (halo || A.fuse.dot_with || A.fuse.want_norm || A.fuse.axpy_r)) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range Dslash launch: no halo / reductions");
     const int grid = sub ? A.fuse.cta_count : (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc + (hout ? hout->cta0[4] : 0);
-    // register budget variants (tuning knob LQCD_LB = "maxthreads,minblocks"; default picked by measurement)
-    static int lb = -1;
-    if (lb < 0) {
-        lb = 0;
-        if (const char *e = getenv("LQCD_LB")) {
-            int a = 0, b = 0;
-            if (sscanf(e, "%d,%d", &a, &b) == 2) lb = a * 100 + b;
-        }
-    }
-#define WLK(MT, MB, MU_, LH_)                                                                   \
+#define WLK(MU_, LH_, G_)                                                                       \
     do {                                                                                        \
-        if (dagger) wilson_dslash_kernel<1, MT, MB, MU_, LH_, 0><<<grid, bs, 0, s>>>(A);           \
-        else        wilson_dslash_kernel<0, MT, MB, MU_, LH_, 0><<<grid, bs, 0, s>>>(A);           \
+        if (dagger) wilson_dslash_kernel<1, MU_, LH_, 0, G_><<<grid, bs, 0, s>>>(A);            \
+        else        wilson_dslash_kernel<0, MU_, LH_, 0, G_><<<grid, bs, 0, s>>>(A);            \
     } while (0)
-#define WL(MT, MB)                                                                              \
+#define WLG(MU_, LH_) do { if (g12) WLK(MU_, LH_, 1); else WLK(MU_, LH_, 0); } while (0)
+#define WL()                                                                                    \
     do {                                                                                        \
         const int mu_ = (halo && hout) ? 2 : (halo ? 1 : 0);                                    \
-        if (lh) { if (mu_ == 2) WLK(MT, MB, 2, 1); else if (mu_ == 1) WLK(MT, MB, 1, 1); else WLK(MT, MB, 0, 1); } \
-        else    { if (mu_ == 2) WLK(MT, MB, 2, 0); else if (mu_ == 1) WLK(MT, MB, 1, 0); else WLK(MT, MB, 0, 0); } \
+        if (lh) { if (mu_ == 2) WLG(2, 1); else if (mu_ == 1) WLG(1, 1); else WLG(0, 1); }      \
+        else    { if (mu_ == 2) WLG(2, 0); else if (mu_ == 1) WLG(1, 0); else WLG(0, 0); }      \
     } while (0)
     static int lh_env = -2;
     if (lh_env == -2) { const char *e = getenv("LQCD_LINK_HINT"); lh_env = e ? (atoi(e) != 0) : -1; }
     const int lh = lh_env >= 0 ? lh_env : (ctx->g.V <= (1 << 18));
-    if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported by the Wilson kernel");
+    if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 4 is not supported by the Wilson kernel");
     // kernel family: 1 = one lane per site, register-resident hops (this file); 4 = t-marching kernel with TMA-staged spinor
     // window and link stages (wilson_tmarch.cu), which falls through to family 1 when the geometry does not qualify.
     // (Rounds 1 / 2 also measured a two-lanes-per-site kernel, 222-355 us at 32^4, and a first t-marching kernel with LDG links,
@@ -71,18 +63,18 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         ctx->launches++;
         return LQCD_OK;
     }
-    if (family != 1 && !sub) {                 // t-marching TMA kernel; LQCD_ERR_STATE = geometry does not qualify -> family 1
+    if (family == 4 && !sub) {                 // t-marching TMA kernel; LQCD_ERR_STATE = geometry does not qualify -> family 1
         const int rc = launch_wilson_tmarch(ctx, A, dagger, s, halo != nullptr, hout != nullptr);
         if (rc != LQCD_ERR_STATE) return rc;
     }
-    // family 1, measured on B200, 32^4: 206 regs (8 warps/SM) 236 us; 158-168 regs (12 warps/SM) 200 us; 128 regs (16 warps/SM)
-    // 204-211 us; 144 regs (14 warps/SM) 206 us -- the kernel saturates the L2->SM fabric (2.29 GB at 11 TB/s), occupancy is no lever.
-    if (lb == 12804 && bs <= 128) WL(128, 4);
-    else if (lb == 6407 && bs <= 64) WL(64, 7);          // 14 warps/SM, 144 registers: wave-count experiment
-    else if (lb == 25602) WL(256, 2);
-    else if (lb == 25601 || bs > 128) WL(256, 1);
-    else WL(128, 3);
+    // two-row links (links12.cu) when the links are SU(3): 768 instead of 960 B/site from HBM, 1.8 instead of 2.2 KB/site over the
+    // L2 -> SM fabric (the binding limit of this kernel: 2.29 GB per 32^4 application at 11 TB/s, profiles/r2a_wilson_k1_ncu_full.csv)
+    int g12 = 0;
+    LQCD_TRY(ensure_links12(ctx, &g12));
+    A.links12 = g12 ? ctx->links12 : nullptr;
+    WL();
 #undef WL
+#undef WLG
 #undef WLK
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -68,31 +68,31 @@ __global__ void __launch_bounds__(MAXT, MINB) wilson_eo_hop_kernel(const EoArgs 
         {   // x direction: the neighbour of the other parity sits at the same xh or one step away
             const bool wf = odd_row && (xh == Xh - 1);           // x == X-1
             const int nf = odd_row ? (wf ? h - (Xh - 1) : h + 1) : h;
-            hop<0, 1, DAG, LH>(acc, A.in, A.g_out, nf, h, wf, A.bc[0]);
+            hop<0, 1, DAG, LH, 0>(acc, A.in, A.g_out, nf, h, wf, A.bc[0]);
             const bool wb = !odd_row && (xh == 0);               // x == 0
             const int nb = odd_row ? h : (wb ? h + (Xh - 1) : h - 1);
-            hop<0, 0, DAG, LH>(acc, A.in, A.g_in, nb, nb, wb, A.bc[0]);
+            hop<0, 0, DAG, LH, 0>(acc, A.in, A.g_in, nb, nb, wb, A.bc[0]);
         }
         {
             const int st = Xh;
             const bool wf = (y == A.gh.Y - 1), wb = (y == 0);
             const int nf = wf ? h - (A.gh.Y - 1) * st : h + st, nb = wb ? h + (A.gh.Y - 1) * st : h - st;
-            hop<1, 1, DAG, LH>(acc, A.in, A.g_out, nf, h, wf, A.bc[1]);
-            hop<1, 0, DAG, LH>(acc, A.in, A.g_in, nb, nb, wb, A.bc[1]);
+            hop<1, 1, DAG, LH, 0>(acc, A.in, A.g_out, nf, h, wf, A.bc[1]);
+            hop<1, 0, DAG, LH, 0>(acc, A.in, A.g_in, nb, nb, wb, A.bc[1]);
         }
         {
             const int st = Xh * A.gh.Y;
             const bool wf = (z == A.gh.Z - 1), wb = (z == 0);
             const int nf = wf ? h - (A.gh.Z - 1) * st : h + st, nb = wb ? h + (A.gh.Z - 1) * st : h - st;
-            hop<2, 1, DAG, LH>(acc, A.in, A.g_out, nf, h, wf, A.bc[2]);
-            hop<2, 0, DAG, LH>(acc, A.in, A.g_in, nb, nb, wb, A.bc[2]);
+            hop<2, 1, DAG, LH, 0>(acc, A.in, A.g_out, nf, h, wf, A.bc[2]);
+            hop<2, 0, DAG, LH, 0>(acc, A.in, A.g_in, nb, nb, wb, A.bc[2]);
         }
         {
             const int st = Xh * A.gh.Y * A.gh.Z;
             const bool wf = (t == A.gh.T - 1), wb = (t == 0);
             const int nf = wf ? h - (A.gh.T - 1) * st : h + st, nb = wb ? h + (A.gh.T - 1) * st : h - st;
-            hop<3, 1, DAG, LH>(acc, A.in, A.g_out, nf, h, wf, A.bc[3]);
-            hop<3, 0, DAG, LH>(acc, A.in, A.g_in, nb, nb, wb, A.bc[3]);
+            hop<3, 1, DAG, LH, 0>(acc, A.in, A.g_out, nf, h, wf, A.bc[3]);
+            hop<3, 0, DAG, LH, 0>(acc, A.in, A.g_in, nb, nb, wb, A.bc[3]);
         }
         cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
         const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
@@ -187,7 +187,7 @@ static int eo_hop(lqcd_ctx *ctx, EoState *e, const lqcd_op *op, int dagger, int 
     for (int i = 0; i < 4; i++) A.bc[i] = op->bc[i];
     A.fuse = fuse ? *fuse : DslashFuse();
     A.red = ctx->red;
-    if (A.fuse.shift_src || A.fuse.interior_only) return lqcd_fail(ctx, LQCD_ERR_ARG, "even-odd hop: unsupported fused epilogue");
+    if (A.fuse.shift_src) return lqcd_fail(ctx, LQCD_ERR_ARG, "even-odd hop: unsupported fused epilogue");
     const int bs = 32 * e->gh.wpc, grid = (e->gh.nblk + e->gh.wpc - 1) / e->gh.wpc;
     if (bs > 256) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 8 is not supported");
     const int lh = e->gh.V <= (1 << 17);

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) wilson_rterm_kernel(const RTermArgs A) {
 int wilson_dslash_general_r(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int dagger, const DslashFuse *fuse) {
     if (ctx->nranks > 1) return lqcd_fail(ctx, LQCD_ERR_ARG, "the Wilson operator with r != 1 (r = %g) is implemented for a single rank", op->r);
     if (fuse && fuse->shift_src) return lqcd_fail(ctx, LQCD_ERR_ARG, "multi-shift CG is implemented for the Wilson operator with r = 1 only (got r = %g)", op->r);
-    if (fuse && (fuse->cta_count > 0 || fuse->interior_only)) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range launch with r != 1");
+    if (fuse && fuse->cta_count > 0) return lqcd_fail(ctx, LQCD_ERR_ARG, "sub-range launch with r != 1");
     lqcd_fermion *z = nullptr;
     LQCD_TRY(get_scratch(ctx, LQCD_WILSON, SCR_RTERM, &z));
     if (z->d == x || z->d == y) return lqcd_fail(ctx, LQCD_ERR_STATE, "r-term scratch field aliases an operand");

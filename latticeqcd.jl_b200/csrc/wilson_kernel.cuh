@@ -7,29 +7,18 @@
 #include "site_map.cuh"
 #include "wilson_spin.cuh"
 #include "halo_pack.cuh"
+#include "link_load.cuh"
 
-// Cache policy of the link loads.  Links have at most one reuse (as the backward link of the +mu neighbour), spinors up
-// to nine.  Measured on B200 (tools/quick_bench.py): marking link lines evict-first in L1 helps when the local lattice is
-// L2 resident (32.32.16.8: 34.4 -> 31.3 us) and hurts at 32^4 (203 -> 228 us: the backward-link L1 hits are lost and L2
-// is already the bottleneck); L1::no_allocate / spinor evict_last variants were slower in both regimes.  So LH = 1 is
-// selected only for local volumes <= 2^18 sites (the strong-scaling regime).
-template <int LH>
-__device__ __forceinline__ cplx ldlink(const cplx *p) {
-    if (LH == 1) {
-        cplx v;
-        asm("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-        return v;
-    }
-    return __ldg(p);
-}
 __device__ __forceinline__ cplx ldspinor(const cplx *p) { return __ldg(p); }
 
 // one of the eight hops.  FWD=1: U_mu(n) x(n+mu) with link at `ls` = n;  FWD=0: U_mu^dag(n-mu) x(n-mu), ls = n-mu.
-template <int MU, int FWD, int DAG, int LH>
+template <int MU, int FWD, int DAG, int LH, int G12>
 __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in, const cplx *__restrict__ gauge,
                                     int ns, int ls, bool wrapped, double phase) {
     constexpr int S = (FWD ^ DAG) ? -1 : +1;     // D: forward (1-g), backward (1+g); D^dag swaps
     const cplx *sp = in + (size_t)(ns >> 5) * (12 * 32) + (ns & 31);
+    cplx u[9];
+    load_link<MU, G12, LH>(u, gauge, ls);
     cplx h0[3], h1[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -41,19 +30,13 @@ __device__ __forceinline__ void hop(cplx (&acc)[12], const cplx *__restrict__ in
 #pragma unroll
         for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
     }
-    const cplx *lk = gauge + ((size_t)(ls >> 5) * 4 + MU) * (9 * 32) + (ls & 31);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
 #pragma unroll
         for (int b = 0; b < 3; b++) {
-            if (FWD) {
-                cplx u = ldlink<LH>(lk + (a * 3 + b) * 32);
-                cfma(g0, u, h0[b]); cfma(g1, u, h1[b]);
-            } else {
-                cplx u = ldlink<LH>(lk + (b * 3 + a) * 32);
-                cfmac(g0, u, h0[b]); cfmac(g1, u, h1[b]);
-            }
+            if (FWD) { cfma(g0, u[a * 3 + b], h0[b]); cfma(g1, u[a * 3 + b], h1[b]); }
+            else     { cfmac(g0, u[b * 3 + a], h0[b]); cfmac(g1, u[b * 3 + a], h1[b]); }
         }
         reconstruct<MU, S>(acc, a, g0, g1);
     }
@@ -91,21 +74,22 @@ __device__ __forceinline__ void halo_hop(cplx (&acc)[12], const WilsonArgs &A, i
     }
 }
 
-template <int MU, int DAG, int MULTI, int LH>
+template <int MU, int DAG, int MULTI, int LH, int G12>
 __device__ __forceinline__ void hop_pair(cplx (&acc)[12], const WilsonArgs &A, int s, int coord, int dim, int stride,
                                          int x, int y, int z, int t) {
+    const cplx *links = G12 ? A.links12 : A.gauge;
     // forward
     {
         bool w = (coord == dim - 1);
         int ns = w ? s - (dim - 1) * stride : s + stride;
-        if (!(w && A.g.part[MU])) hop<MU, 1, DAG, LH>(acc, A.in, A.gauge, ns, s, w, A.bc[MU]);
+        if (!(w && A.g.part[MU])) hop<MU, 1, DAG, LH, G12>(acc, A.in, links, ns, s, w, A.bc[MU]);
         else if (MULTI) halo_hop<MU, 1, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
     // backward
     {
         bool w = (coord == 0);
         int ns = w ? s + (dim - 1) * stride : s - stride;
-        if (!(w && A.g.part[MU])) hop<MU, 0, DAG, LH>(acc, A.in, A.gauge, ns, ns, w, A.bc[MU]);
+        if (!(w && A.g.part[MU])) hop<MU, 0, DAG, LH, G12>(acc, A.in, links, ns, ns, w, A.bc[MU]);
         else if (MULTI) halo_hop<MU, 0, DAG>(acc, A, s, face_index<MU>(A.g, x, y, z, t));
     }
 }
@@ -140,10 +124,14 @@ __device__ __forceinline__ void clover_apply(cplx (&ax)[12], const cplx *__restr
 
 // MULTI: 0 single GPU | 1 fused halo (separate pack kernel on the priority stream) | 2 self-packing (the leading CTAs of this
 // kernel ship the halo).  (A persistent-CTA tile-queue variant was measured in rounds 1 / 2: slower at every N, removed.)
-// register cap per launch-bounds variant: (128,3) -> 168, (128,4) / (256,2) -> 128, (256,1) -> 255, (64,7) -> 144 (14 warps per SM)
-constexpr int wilson_regs(int maxt, int minb) { int r = 65536 / (maxt * minb); r -= r % 8; return r > 255 ? 255 : r; }
-template <int DAG, int MAXT, int MINB, int MULTI, int LH, int CLOVER>
-__global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wilson_dslash_kernel(const WilsonArgs A) {
+// G12: links read from the two-row copy (links12.cu).  __launch_bounds__(128, 3): <= 168 registers, 12 warps per SM.  Measured
+// alternatives (B200, round 2, profiles/r2a_kernel_sweep.txt): 144 registers / 14 warps 206 us, 128 registers / 16 warps 211 us
+// against 202 us at 32^4 (29.5 / 31.5 / 31.3 us on the 8-GPU local volume): occupancy is not the lever, bytes are.
+#ifndef LQCD_WILSON_MINB
+#define LQCD_WILSON_MINB 3          // experiment builds: LQCD_BUILD_DEFS=-DLQCD_WILSON_MINB=4 (128 registers, 16 warps per SM)
+#endif
+template <int DAG, int MULTI, int LH, int CLOVER, int G12>
+__global__ void __launch_bounds__(128, LQCD_WILSON_MINB) wilson_dslash_kernel(const WilsonArgs A) {
     if (A.fuse.use_state && A.red.st->done) return;     // grid-uniform: set only by an earlier kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bid = blockIdx.x, npack = 0;
@@ -153,8 +141,10 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wil
         bid -= npack;
     }
     int cta = bid + A.fuse.cta_off;
+    unsigned long long ts0 = 0ull;
     if (MULTI) {
         cta = A.halo.cta_order[bid];
+        if (A.halo.timing && threadIdx.x == 0) ts0 = global_ns();
         if (bid >= A.halo.n_interior) wait_halo_flags(A.g, A.halo);
     }
     const int blk = block_of_warp(A.g, cta, warp);
@@ -164,10 +154,6 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wil
         const int s = blk * 32 + lane;
         int x, y, z, t;
         site_coords(A.g, s, x, y, z, t);
-        // multi-GPU interior pass: face sites are finished (and reduced) by the exterior kernel
-        const bool skip_red = A.fuse.interior_only &&
-            ((A.g.part[0] && (x == 0 || x == A.g.X - 1)) || (A.g.part[1] && (y == 0 || y == A.g.Y - 1)) ||
-             (A.g.part[2] && (z == 0 || z == A.g.Z - 1)) || (A.g.part[3] && (t == 0 || t == A.g.T - 1)));
         cplx acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
@@ -187,10 +173,10 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wil
                 }
             }
         }
-        hop_pair<0, DAG, MULTI, LH>(acc, A, s, x, A.g.X, 1, x, y, z, t);
-        hop_pair<1, DAG, MULTI, LH>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
-        hop_pair<2, DAG, MULTI, LH>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
-        hop_pair<3, DAG, MULTI, LH>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
+        hop_pair<0, DAG, MULTI, LH, G12>(acc, A, s, x, A.g.X, 1, x, y, z, t);
+        hop_pair<1, DAG, MULTI, LH, G12>(acc, A, s, y, A.g.Y, A.g.X, x, y, z, t);
+        hop_pair<2, DAG, MULTI, LH, G12>(acc, A, s, z, A.g.Z, A.g.X * A.g.Y, x, y, z, t);
+        hop_pair<3, DAG, MULTI, LH, G12>(acc, A, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z, x, y, z, t);
         const size_t base = (size_t)blk * (12 * 32) + lane;
         const double mk = -A.kappa;
         cplx *dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
@@ -210,16 +196,17 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(wilson_regs(MAXT, MINB)) wil
                 cplx rv = A.fuse.axpy_r[base + k * 32];
                 yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
             }
-            if (A.fuse.dot_with && !skip_red) {
+            if (A.fuse.dot_with) {
                 cplx w = ldg128(A.fuse.dot_with + base + k * 32);
                 red[0] = fma(w.x, yk.x, red[0]); red[0] = fma(w.y, yk.y, red[0]);
                 red[1] = fma(w.x, yk.y, red[1]); red[1] = fma(-w.y, yk.x, red[1]);
             }
-            if (!skip_red) { red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]); }
+            red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
             dst[base + k * 32] = yk;
         }
     }
+    if (MULTI && A.halo.timing && threadIdx.x == 0) stamp_span(A.halo.timing, bid >= A.halo.n_interior ? 2 : 1, ts0, global_ns());
     if (A.fuse.dot_with || A.fuse.want_norm)
-        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, !A.fuse.interior_only, (unsigned)bid, gridDim.x - (unsigned)npack);
+        grid_reduce_finish<3>(red, A.red, A.fuse.finish, 0, 0, 1, (unsigned)bid, gridDim.x - (unsigned)npack);
 }
 

@@ -25,6 +25,10 @@
 #include "reduce.cuh"
 #include "wilson_spin.cuh"
 #include "bulk_copy.cuh"
+#include "site_map.cuh"
+#ifdef TM_DEBUG
+#include "../../tools/debug/tm_debug.cuh"
+#endif
 #include <cstdio>
 #include <cstdlib>
 
@@ -80,7 +84,40 @@ __device__ __forceinline__ void ld_link_g(cplx (&u)[9], const cplx *__restrict__
     for (int e = 0; e < 9; e++) u[e] = __ldg(gp + e * 32);
 }
 
-template <int DAG>
+// off-rank hop (multi-GPU): the neighbour rank's pack kernel delivered the spin-projected half spinor of face site f into our halo
+// slot (forward hop: P psi(n+mu), the local link u = U_mu(n) is applied here; backward hop: U^dag P psi(n-mu), complete).
+// Same arithmetic as halo_hop() of wilson_kernel.cuh.
+template <int MU, int FWD, int DAG>
+__device__ __forceinline__ void halo_hop_regs(cplx (&acc)[12], const WilsonArgs &A, int f, const cplx (&u)[9]) {
+    constexpr int S = (FWD ^ DAG) ? -1 : +1;
+    const cplx *src = A.halo.recv[MU][FWD] + (size_t)(f >> 5) * (6 * 32) + (f & 31);
+    cplx h0[3], h1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { h0[c] = __ldcg(src + c * 32); h1[c] = __ldcg(src + (3 + c) * 32); }
+    const double phase = FWD ? (A.halo.plast[MU] ? A.bc[MU] : 1.0) : (A.halo.pfirst[MU] ? A.bc[MU] : 1.0);
+    if (phase != 1.0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
+    if (FWD) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < 3; b++) { cfma(g0, u[a * 3 + b], h0[b]); cfma(g1, u[a * 3 + b], h1[b]); }
+            reconstruct<MU, S>(acc, a, g0, g1);
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++) reconstruct<MU, S>(acc, a, h0[a], h1[a]);
+    }
+}
+
+// MULTI = 1: one rank of a process grid.  Hops that leave the local lattice in a partitioned direction read the halo slots the
+// neighbours' pack kernels fill over NVLink (comm.cu); a CTA waits for the sequence flags right before its first such hop.  With
+// T partitioned the march is cyclic and starts at t = 1, so the two slices that need the t halos (t = T-1, then t = 0) come
+// LAST in every patch and the NVLink transfer is hidden behind the T-2 interior slices.
+template <int DAG, int MULTI>
 __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
     const WilsonArgs &A = K.A;
     if (A.fuse.use_state && A.red.st->done) return;
@@ -101,10 +138,21 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
     }
     __syncthreads();
     uint32_t wph = 0, pph = 0;            // parity to wait for next, one bit per barrier (every thread waits on every completion)
+#ifdef TM_DEBUG
+    __shared__ int tm_abort;
+    if (threadIdx.x == 0) tm_abort = 0;
+    __syncthreads();
+    int dbg_r = 0, dbg_task = 0;
+    auto wait_w = [&](int j) { tm_wait_dbg(wbar, j, (wph >> j) & 1u, 100 + j, dbg_r, dbg_task, &tm_abort); wph ^= 1u << j; };
+    auto wait_p = [&](int j) { tm_wait_dbg(wbar, 3 + j, (pph >> j) & 1u, 200 + j, dbg_r, dbg_task, &tm_abort); pph ^= 1u << j; };
+#else
     auto wait_w = [&](int j) { mbar_wait(&wbar[j], (wph >> j) & 1u); wph ^= 1u << j; };
     auto wait_p = [&](int j) { mbar_wait(&pbar[j], (pph >> j) & 1u); pph ^= 1u << j; };
+#endif
 
     const int w0 = w % g.c[0], w1 = (w / g.c[0]) % g.c[1], w2 = w / (g.c[0] * g.c[1]);
+    const int tshift = (MULTI && g.part[3]) ? 1 : 0;
+    bool halo_ready = false;              // CTA-uniform: the neighbours' flags of this application have been seen
     double red[3] = {0.0, 0.0, 0.0};
     const double mk = -A.kappa;
     const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
@@ -116,14 +164,16 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
         const int patch = task % npatch, chunk = task / npatch;
         const int p0 = patch % g.nt[0], p1 = (patch / g.nt[0]) % g.nt[1], p2 = patch / (g.nt[0] * g.nt[1]);
         const int bslice = (p0 * g.c[0] + w0) + g.nb[0] * ((p1 * g.c[1] + w1) + g.nb[1] * (p2 * g.c[2] + w2));
-        const int t0 = chunk * Lc;
+        const int t0 = chunk * Lc + tshift;                                      // slice of step r: (t0 + r - 1) mod T
+        auto slice_of = [&](int rel) { return (t0 - 1 + rel + T) % T; };         // rel = step index (0 = the slice before the first step)
 
         // t-invariant spatial neighbour tables of this lane: block in the slice, lane, patch position (-1 = out of patch), wrap
         const int ssl = bslice * 32 + lane;
+        const int cx = ssl % g.X, cy = (ssl / g.X) % g.Y, cz = ssl / (g.X * g.Y);
         int nbl[6], nl[6], nw[6];
         bool wr[6];
         {
-            const int coord[3] = {ssl % g.X, (ssl / g.X) % g.Y, ssl / (g.X * g.Y)}, dim[3] = {g.X, g.Y, g.Z}, stride[3] = {1, g.X, g.X * g.Y};
+            const int coord[3] = {cx, cy, cz}, dim[3] = {g.X, g.Y, g.Z}, stride[3] = {1, g.X, g.X * g.Y};
 #pragma unroll
             for (int mu = 0; mu < 3; mu++) {
 #pragma unroll
@@ -143,13 +193,19 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
         }
 
         __syncthreads();                  // everybody is done reading the previous task's window and planes
+        if (MULTI && !halo_ready) {       // a patch on a partitioned spatial face needs its halos from the first step on
+            bool need = false;
+            const int pc[3] = {p0, p1, p2};
+            for (int mu = 0; mu < 3; mu++) need = need || (g.part[mu] && (pc[mu] == 0 || pc[mu] == g.nt[mu] - 1));
+            if (need) { wait_halo_flags(g, A.halo); halo_ready = true; }
+        }
         if (lane == 0) {
             for (int rel = 0; rel < 3; rel++) {                                  // slices t0-1, t0, t0+1 -> slots 0, 1, 2
-                const int tt = (t0 - 1 + rel + T) % T;
+                const int tt = slice_of(rel);
                 mbar_arrive_expect_tx(&wbar[rel], TM_REC_BYTES);
                 bulk_g2s(win + ((size_t)rel * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)tt * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel]);
             }
-            const size_t b0 = (size_t)bslice + (size_t)t0 * nsb, bm = (size_t)bslice + (size_t)((t0 - 1 + T) % T) * nsb;
+            const size_t b0 = (size_t)bslice + (size_t)slice_of(1) * nsb, bm = (size_t)bslice + (size_t)slice_of(0) * nsb;
             for (int mu = 0; mu < 3; mu++) {                                     // spatial forward links of slice t0
                 mbar_arrive_expect_tx(&pbar[mu], TM_SUB_BYTES);
                 bulk_g2s(plane + ((size_t)mu * TM_W + w) * TM_SUB, A.gauge + (b0 * 4 + mu) * TM_SUB, TM_SUB_BYTES, &pbar[mu]);
@@ -159,8 +215,12 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
         }
 
         for (int r = 1; r <= Lc; r++) {
-            const int t = t0 + r - 1;
+            const int t = slice_of(r);
+#ifdef TM_DEBUG
+            dbg_r = r; dbg_task = task;
+#endif
             const size_t blk = (size_t)bslice + (size_t)t * nsb;
+            if (MULTI && !halo_ready && g.part[3] && (t == T - 1 || t == 0)) { wait_halo_flags(g, A.halo); halo_ready = true; }
             const cplx *cur = win + (size_t)(r % 3) * TM_W * TM_REC;
             const cplx *up = win + (size_t)((r + 1) % 3) * TM_W * TM_REC;
             const cplx *dn = win + (size_t)((r - 1) % 3) * TM_W * TM_REC;
@@ -180,15 +240,23 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
 
             // ---- t backward: slice t-1 from the window, its t links still in plane 3 -------------------------------------------
             if (r == 1) { wait_w(0); wait_w(1); wait_p(3); }      // later steps: plane 3 was waited for by the previous step's forward hop
-            ld_spinor_s(p, dn + (size_t)w * TM_REC + lane);
-            ld_link_s(u, plane + ((size_t)3 * TM_W + w) * TM_SUB + lane);
-            hop_regs<3, 0, DAG>(acc, p, u, t == 0, A.bc[3]);
+            // (accumulated apart and added LAST: the hop sum then has the order x+ x- y+ y- z+ z- t+ t- of the register-resident
+            //  kernel, and the two kernel families, the multi-RHS and the slab-pipelined paths stay bit-identical)
+            cplx acct[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acct[k] = cmake(0.0, 0.0);
+            if (MULTI && g.part[3] && t == 0) halo_hop_regs<3, 0, DAG>(acct, A, face_index<3>(g, cx, cy, cz, t), u);
+            else {
+                ld_spinor_s(p, dn + (size_t)w * TM_REC + lane);
+                ld_link_s(u, plane + ((size_t)3 * TM_W + w) * TM_SUB + lane);
+                hop_regs<3, 0, DAG>(acct, p, u, t == 0, A.bc[3]);
+            }
             __syncthreads();
             if (lane == 0) {
                 mbar_arrive_expect_tx(&pbar[3], TM_SUB_BYTES);                   // t links of slice t (forward hop at the end of the step)
                 bulk_g2s(plane + ((size_t)3 * TM_W + w) * TM_SUB, A.gauge + (blk * 4 + 3) * TM_SUB, TM_SUB_BYTES, &pbar[3]);
                 if (r + 2 <= Lc + 1) {                                           // slice t+2 into the slot slice t-1 just left
-                    const int rel = r + 2, tt = (t0 - 1 + rel) % T;
+                    const int rel = r + 2, tt = slice_of(rel);
                     mbar_arrive_expect_tx(&wbar[rel % 3], TM_REC_BYTES);
                     bulk_g2s(win + ((size_t)(rel % 3) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)tt * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel % 3]);
                 }
@@ -200,20 +268,24 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
                 wait_p(MU);                                                                                                 \
                 const int df = MU * 2, db = MU * 2 + 1;                                                                     \
                 const cplx *pl = plane + (size_t)MU * TM_W * TM_SUB;                                                        \
-                if (nw[df] >= 0) ld_spinor_s(p, cur + (size_t)nw[df] * TM_REC + nl[df]);                                    \
-                else             ld_spinor_g(p, A.in + ((size_t)nbl[df] + (size_t)t * nsb) * TM_REC + nl[df]);              \
                 ld_link_s(u, pl + (size_t)w * TM_SUB + lane);                                                               \
-                hop_regs<MU, 1, DAG>(acc, p, u, wr[df], A.bc[MU]);                                                          \
-                if (nw[db] >= 0) { ld_spinor_s(p, cur + (size_t)nw[db] * TM_REC + nl[db]); ld_link_s(u, pl + (size_t)nw[db] * TM_SUB + nl[db]); } \
+                if (MULTI && wr[df] && g.part[MU]) halo_hop_regs<MU, 1, DAG>(acc, A, face_index<MU>(g, cx, cy, cz, t), u);  \
+                else {                                                                                                      \
+                    if (nw[df] >= 0) ld_spinor_s(p, cur + (size_t)nw[df] * TM_REC + nl[df]);                                \
+                    else             ld_spinor_g(p, A.in + ((size_t)nbl[df] + (size_t)t * nsb) * TM_REC + nl[df]);          \
+                    hop_regs<MU, 1, DAG>(acc, p, u, wr[df], A.bc[MU]);                                                      \
+                }                                                                                                           \
+                if (MULTI && wr[db] && g.part[MU]) halo_hop_regs<MU, 0, DAG>(acc, A, face_index<MU>(g, cx, cy, cz, t), u);  \
+                else if (nw[db] >= 0) { ld_spinor_s(p, cur + (size_t)nw[db] * TM_REC + nl[db]); ld_link_s(u, pl + (size_t)nw[db] * TM_SUB + nl[db]); } \
                 else {                                                                                                      \
                     ld_spinor_g(p, A.in + ((size_t)nbl[db] + (size_t)t * nsb) * TM_REC + nl[db]);                           \
                     ld_link_g(u, A.gauge + (((size_t)nbl[db] + (size_t)t * nsb) * 4 + MU) * TM_SUB + nl[db]);               \
                 }                                                                                                           \
-                hop_regs<MU, 0, DAG>(acc, p, u, wr[db], A.bc[MU]);                                                          \
+                if (!(MULTI && wr[db] && g.part[MU])) hop_regs<MU, 0, DAG>(acc, p, u, wr[db], A.bc[MU]);                    \
                 __syncthreads();                                                                                            \
                 if (lane == 0 && r < Lc) {                                       /* forward links of slice t+1 */           \
                     mbar_arrive_expect_tx(&pbar[MU], TM_SUB_BYTES);                                                         \
-                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM_SUB, A.gauge + ((blk + nsb) * 4 + MU) * TM_SUB, TM_SUB_BYTES, &pbar[MU]); \
+                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM_SUB, A.gauge + (((size_t)bslice + (size_t)slice_of(r + 1) * nsb) * 4 + MU) * TM_SUB, TM_SUB_BYTES, &pbar[MU]); \
                 }                                                                                                           \
             }
             TM_SPATIAL(0) TM_SPATIAL(1) TM_SPATIAL(2)
@@ -222,9 +294,14 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
             // ---- t forward: slice t+1 from the window, t links of slice t (requested after the backward hop) -------------------
             wait_w((r + 1) % 3);
             wait_p(3);
-            ld_spinor_s(p, up + (size_t)w * TM_REC + lane);
             ld_link_s(u, plane + ((size_t)3 * TM_W + w) * TM_SUB + lane);
-            hop_regs<3, 1, DAG>(acc, p, u, t == T - 1, A.bc[3]);
+            if (MULTI && g.part[3] && t == T - 1) halo_hop_regs<3, 1, DAG>(acc, A, face_index<3>(g, cx, cy, cz, t), u);
+            else {
+                ld_spinor_s(p, up + (size_t)w * TM_REC + lane);
+                hop_regs<3, 1, DAG>(acc, p, u, t == T - 1, A.bc[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = cadd(acc[k], acct[k]);
 
             // ---- epilogue: y = x - kappa * hops (+ fused shift / CG residual update / reductions), as wilson_kernel.cuh ----------
             const cplx *own = cur + (size_t)w * TM_REC + lane;
@@ -253,12 +330,21 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
     if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
 }
 
+// geometry / configuration test shared with comm.cu (which then feeds the halo slots with the separate pack kernel)
+bool wilson_tmarch_ok(const lqcd_ctx *ctx, const lqcd_op *op) {
+    static int family = -1;
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = e ? atoi(e) : 0; }
+    const Geom &g = ctx->g;
+    if (family != 4 || op->kind != LQCD_WILSON || op->csw != 0.0 || op->r != 1.0) return false;
+    return g.regular && g.s[3] == 1 && g.c[3] == 1 && g.c[0] * g.c[1] * g.c[2] == TM_W && g.T >= 2 && (!g.part[3] || g.T >= 3);
+}
+
 // LQCD_OK if launched; LQCD_ERR_STATE if the geometry / variant does not qualify (caller falls back to the register-resident kernel)
 int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s, bool halo, bool self_pack) {
     const Geom &g = ctx->g;
-    (void)self_pack;
-    if (halo || ctx->nranks != 1 || A.clover) return LQCD_ERR_STATE;
-    if (!g.regular || g.s[3] != 1 || g.c[3] != 1 || g.c[0] * g.c[1] * g.c[2] != TM_W || g.T < 2) return LQCD_ERR_STATE;
+    // multi-rank: the separate pack kernel on the priority stream feeds the halo slots (no self-packing / interior-only variants)
+    if (self_pack || A.clover || (ctx->nranks > 1 && !halo)) return LQCD_ERR_STATE;
+    if (!g.regular || g.s[3] != 1 || g.c[3] != 1 || g.c[0] * g.c[1] * g.c[2] != TM_W || g.T < 2 || (g.part[3] && g.T < 3)) return LQCD_ERR_STATE;
     const int npatch = g.nt[0] * g.nt[1] * g.nt[2];
     // chunks per patch: minimise rounds x (steps + ~1 step of pipeline fill per task) over the divisors of T
     int nchunk = 1;
@@ -276,14 +362,36 @@ int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStr
     K.A = A; K.Lc = g.T / nchunk; K.nchunk = nchunk; K.nsb = g.nb[0] * g.nb[1] * g.nb[2]; K.ntasks = npatch * nchunk;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
         attr_set = true;
     }
     const int grid = K.ntasks < ctx->num_sms ? K.ntasks : ctx->num_sms;
-    if (dagger) wilson_tmarch_kernel<1><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
-    else        wilson_tmarch_kernel<0><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+    if (halo) {
+        if (dagger) wilson_tmarch_kernel<1, 1><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+        else        wilson_tmarch_kernel<0, 1><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+    } else {
+        if (dagger) wilson_tmarch_kernel<1, 0><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+        else        wilson_tmarch_kernel<0, 0><<<grid, 128, TM_SMEM_BYTES, s>>>(K);
+    }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+#ifdef TM_DEBUG
+    {
+        cudaError_t e = cudaStreamSynchronize(s);
+        unsigned long long h[32];
+        cudaMemcpyFromSymbol(h, tm_dbg, sizeof h);
+        fprintf(stderr, "[tm_debug] grid %d Lc %d nchunk %d ntasks %d sync=%s timeouts=%llu", grid, K.Lc, K.nchunk, K.ntasks, cudaGetErrorString(e), h[0]);
+        if (h[0]) {
+            fprintf(stderr, " first: code %llu cta %llu thread %llu r %llu task %llu parity %llu bar %llu raw:", h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            for (int j = 0; j < 7; j++) fprintf(stderr, " %016llx", h[8 + j]);
+            unsigned long long z[32] = {0};
+            cudaMemcpyToSymbol(tm_dbg, z, sizeof z);
+        }
+        fprintf(stderr, "\n");
+    }
+#endif
     return LQCD_OK;
 }

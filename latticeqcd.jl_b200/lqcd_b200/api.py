@@ -375,15 +375,25 @@ class DiracOperator:
         self._bind(U)
 
     def _bind(self, U: Gaugefields):
+        """D(U): upload the links.  All operators of a context share ONE device link buffer, so the context counts bindings
+        (`binding_epoch`) and every use of an operator (`_ensure_bound`) re-uploads its own U when somebody else bound the
+        buffer in between (a second operator with another U, a rejected HMC trajectory).  Editing U.data on the host is not
+        noticed: call D(U) again, as the reference does before every measurement (measure_Pion_correlator.jl:338)."""
         self.U = U
         ptrs = (C.c_void_p * 4)(*[U.data[mu].ctypes.data for mu in range(4)])
         self.ctx.call("lqcd_gauge_upload", ptrs, 3, 0)
+        self.ctx.binding_epoch = getattr(self.ctx, "binding_epoch", 0) + 1
+        self._bound_epoch = self.ctx.binding_epoch
         if self.op.kind == L.WILSON and self.op.csw != 0.0:
             # the clover term depends on the links only: build it at the D(U) rebinding.  Its leaves reach one site into
             # the neighbouring ranks' links, so all ranks must have uploaded first and nobody may re-upload while a peer reads.
             self.ctx.barrier()
             self.ctx.call("lqcd_clover_term", C.byref(self.op), None)
             self.ctx.barrier()
+
+    def _ensure_bound(self):
+        if getattr(self, "_bound_epoch", None) != getattr(self.ctx, "binding_epoch", None):
+            self._bind(self.U)
 
     def clover_term(self) -> np.ndarray:
         """dense clover blocks [V_local, 2, 6(j), 6(i)] (oracle layout), for inspection / tests"""
@@ -421,6 +431,7 @@ def _base(A):
 def mul_(y: FermionField, A, x: FermionField):
     """LinearAlgebra.mul!(y, A, x)."""
     D, mode = _base(A)
+    D._ensure_bound()
     D.ctx.call("lqcd_dslash", C.byref(D.op), y.h, x.h, mode)
 
 
@@ -428,6 +439,7 @@ def mul_host_(y_host: np.ndarray, A, x_host: np.ndarray, y: FermionField = None,
     """mul!(y, A, x) for HOST arrays in the Julia layout (what the Julia shim does for the reference's CPU pseudofermion
     types): one pipelined upload + Dslash + download (lqcd_dslash_host).  y / x: optional device scratch fields."""
     D, mode = _base(A)
+    D._ensure_bound()
     x = x or FermionField(D.ctx, D.kind)
     y = y or FermionField(D.ctx, D.kind)
     assert x_host.dtype == np.complex128 and y_host.dtype == np.complex128 and x_host.flags.c_contiguous and y_host.flags.c_contiguous
@@ -443,6 +455,7 @@ def solve_DinvX_(y: FermionField, A, x: FermionField, history=False):
     """solve_DinvX!(y, A, x): A y = x, y is the initial guess.  A::Dirac_operator (or its adjoint) -> the
     routine upstream calls 'bicg' (CGNR) unless params["method_CG"] says otherwise; A::DdagD -> CG."""
     D, mode = _base(A)
+    D._ensure_bound()
     method = L.SOLVER_CG if mode == L.OP_DDAGD else _METHODS[D.method]
     it, rs = C.c_int(0), C.c_double(0.0)
     hist = np.full(D.maxsteps + 1, np.nan) if (history or D.verbose >= 3) else None
@@ -467,6 +480,7 @@ def _handles(fields):
 def mul_multi_(ys, A, xs):
     """mul!(ys[j], A, xs[j]) for all j in ONE pass over the links (lqcd_dslash_multi); bit-identical to the loop of mul_"""
     D, mode = _base(A)
+    D._ensure_bound()
     assert len(ys) == len(xs)
     D.ctx.call("lqcd_dslash_multi", C.byref(D.op), _handles(ys), _handles(xs), len(ys), mode)
     return ys
@@ -478,6 +492,7 @@ def solve_DinvX_multi_(ys, A, xs):
     (measure_chiral_condensate.jl:176-182) as one batched solve.  ys[j] is the initial guess.  Returns a list of per-source infos;
     raises NotConverged like solve_DinvX_ if any source did not converge."""
     D, mode = _base(A)
+    D._ensure_bound()
     assert len(ys) == len(xs)
     method = L.SOLVER_CG if mode == L.OP_DDAGD else _METHODS[D.method]
     n = len(ys)
@@ -489,10 +504,13 @@ def solve_DinvX_multi_(ys, A, xs):
     return [{"iters": its[j], "resid_sq": rs[j]} for j in range(n)]
 
 
-def calc_quark_propagators_point_source(D: DiracOperator, origin=(0, 0, 0, 0)):
+def calc_quark_propagators_point_source(D: DiracOperator, origin=(0, 0, 0, 0), U: Gaugefields = None):
     """D^-1 on the NC*Nspinor point sources at `origin` (measure_Pion_correlator.jl:333-409: source i has spin is = (i-1) % Nspinor,
     colour ic = (i-is) / Nspinor, value 1 at the origin; clear_fermion!(p); solve_DinvX!(p, D, b)), all sources in one batched
-    solve.  Returns (propagators, infos), propagators[i] a device field like the reference's deepcopy(p).  origin = (x, y, z, t)."""
+    solve.  Returns (propagators, infos), propagators[i] a device field like the reference's deepcopy(p).  origin = (x, y, z, t).
+    U: the configuration to measure on -- re-bound first, D = m.D(U) as measure_Pion_correlator.jl:338 does; None = D's own U."""
+    if U is not None:
+        D(U)
     nspin = 4 if D.kind == L.WILSON else 1
     n = 3 * nspin
     bs = [FermionField(D.ctx, D.kind) for _ in range(n)]
@@ -511,11 +529,13 @@ def calc_quark_propagators_point_source(D: DiracOperator, origin=(0, 0, 0, 0)):
     return ps, infos
 
 
-def measure_chiral_condensate(D: DiracOperator, Nr=10, factor=1.0, seed=114, batched=True):
+def measure_chiral_condensate(D: DiracOperator, Nr=10, factor=1.0, seed=114, batched=True, U: Gaugefields = None):
     """measure(m::Chiral_condensate_measurement, itrj, U) (measure_chiral_condensate.jl:164-204): for ir = 1:Nr { clear_fermion!(p);
     Z4_distribution_fermi!(r); solve_DinvX!(p, D, r); pbp += dot(r, p) }, pbp_value = real(pbp / Nr) / NV * factor.  batched: the Nr
     solves advance in lock step (lqcd_solve_multi); False: one solve_DinvX_ after the other like the reference.  Returns
-    (pbp_value, per-source values, noise fields)."""
+    (pbp_value, per-source values, noise fields).  U: configuration to measure on (D = m.D(U), measure_chiral_condensate.jl:170)."""
+    if U is not None:
+        D(U)
     rs = [FermionField(D.ctx, D.kind) for _ in range(Nr)]
     ps = [FermionField(D.ctx, D.kind) for _ in range(Nr)]
     for ir, (r, p) in enumerate(zip(rs, ps)):
@@ -534,6 +554,7 @@ def measure_chiral_condensate(D: DiracOperator, Nr=10, factor=1.0, seed=114, bat
 
 def shiftedcg_(ys, D: DiracOperator, x: FermionField, shifts, eps=None, maxsteps=None):
     """upstream shiftedcg: (DdagD + shifts[j]) ys[j] = x."""
+    D._ensure_bound()
     sh = np.ascontiguousarray(shifts, dtype=np.float64)
     hs = (C.c_void_p * len(ys))(*[y.h.value for y in ys])
     it, rs = C.c_int(0), C.c_double(0.0)
@@ -586,7 +607,8 @@ class RHMCFermiAction:
         m2 = float(D.op.mass) ** 2
         lo = parameters_action.get("rational_lambda_min", 0.9 * m2)
         hi = parameters_action.get("rational_lambda_max", 1.05 * (m2 + 16.0))
-        self.rhmc = rhmc.RHMCAction(rhmc.B200Backend(D), self.Nf, lo, hi, order=int(parameters_action.get("rational_order", 12)))
+        self.rhmc = rhmc.RHMCAction(rhmc.B200Backend(D), self.Nf, lo, hi, order=int(parameters_action.get("rational_order", 12)),
+                                    tolerance=float(parameters_action.get("rational_tolerance", 1e-6)))
         self.even_only = False
         self._temporary_fermionfields = [FermionField(D.ctx, D.kind) for _ in range(4)]
         self.last = {}
@@ -802,7 +824,12 @@ def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=
             mul_(eta, adjoint(D), xi)                                 # sample_pseudofermions! without re-uploading U
         if fa.even_only:
             mask_parity_(eta, 0)
-        S_old += dot(xi, xi).real                                     # standardHMC.jl:54
+        if is_rhmc:
+            # S_old with the SAME functional as S_new (eta^dag r_action(DdagD) eta): heat bath and action are two independent
+            # fits (each ~1e-7), so dot(xi, xi) would leave a systematic dH of ~1e-7 * S_f that grows with the volume
+            S_old += fa.rational_apply_(fa._temporary_fermionfields[0], fa.rhmc.r_action, eta, want_dot=True)[1]
+        else:
+            S_old += dot(xi, xi).real                                 # standardHMC.jl:54
     with _even_site_solves(fa):
         its = runMD_(ctx, beta, dtau, MDsteps, D, eta, SextonWeingargten, Nsw, rational=fa.rhmc.r_action if is_rhmc else None)
     S_new = kinetic_energy(ctx) + gauge_action(ctx, beta)
@@ -817,4 +844,11 @@ def hmc_update_(U: Gaugefields, beta, dtau, MDsteps, fa=None, SextonWeingargten=
     accept = bool(np.exp(min(0.0, S_old - S_new)) >= rng.random())    # exp(Sold - Snew) >= rand(), standardHMC.jl:79
     if accept:
         U.data[...] = get_links(ctx)
+    elif D is not None:
+        D(U)                                  # rejected: the device still holds the evolved links -- restore U (and the clover term)
+    else:
+        ctx.call("lqcd_gauge_upload", _link_ptrs(U.data), 3, 0)
+    ctx.binding_epoch = getattr(ctx, "binding_epoch", 0) + 1          # other operators of this context re-bind their own U on next use
+    if D is not None:
+        D._bound_epoch = ctx.binding_epoch                            # ... D itself is in sync with U (accepted: downloaded; rejected: restored)
     return accept, S_new - S_old, {"cg_iters": its, "S_old": S_old, "S_new": S_new}

@@ -149,21 +149,31 @@ class B200Backend:
 class RHMCAction:
     """Staggered pseudofermion action det(D^dag D)^{Nf/8} through rational approximations."""
 
-    def __init__(self, backend, Nf: int, lambda_min: float, lambda_max: float, order: int = 12):
+    def __init__(self, backend, Nf: int, lambda_min: float, lambda_max: float, order: int = 12, tolerance: float = 1e-6):
         if Nf in (4, 8):
             raise ValueError("Nf = 4, 8 use the plain HMC action (no rational approximation)")
         self.be, self.Nf = backend, Nf
         self._range = (order, float(lambda_min), float(lambda_max))
+        self.tolerance = float(tolerance)
+
+    def _checked(self, ra: RationalApprox) -> RationalApprox:
+        """a fit that missed its tolerance (too low an order for the spectral range, a least-squares run that did not converge)
+        would silently bias the action: refuse it"""
+        if not (ra.max_rel_err <= self.tolerance):
+            raise ValueError(f"rational approximation of x^{ra.power:+.4f} on [{ra.lo:.4g}, {ra.hi:.4g}] with {len(ra.beta)} poles has "
+                             f"max relative error {ra.max_rel_err:.3e} > tolerance {self.tolerance:.1e}: raise rational_order or "
+                             f"narrow rational_lambda_min / rational_lambda_max")
+        return ra
 
     # the fits are computed on first use and cached per (power, order, range): the positive-power (heat-bath) fit is the
     # slow one (tens of seconds) and is not needed by evaluate / force_terms
     @property
     def r_heatbath(self) -> RationalApprox:
-        return rational_approx(+self.Nf / 16.0, *self._range)
+        return self._checked(rational_approx(+self.Nf / 16.0, *self._range))
 
     @property
     def r_action(self) -> RationalApprox:
-        return rational_approx(-self.Nf / 8.0, *self._range)
+        return self._checked(rational_approx(-self.Nf / 8.0, *self._range))
 
     def _apply_rational(self, ra: RationalApprox, b):
         """alpha0 b + sum_j alpha_j (D^dag D + beta_j)^-1 b with ONE multi-shift solve."""

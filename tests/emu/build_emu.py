@@ -31,6 +31,7 @@ PTX = {
     "prefetch.global.L2": "(void)({i0});",
     "ld.global.nc.L1::evict_first.v2.f64": "{o0} = ({i0})->x; {o1} = ({i0})->y;",
     "fence.mbarrier_init.release.cluster": ";",
+    "mov.u64": "{o0} = (unsigned long long)__builtin_ia32_rdtsc();",
 }
 # helper functions whose bodies are PTX over 32-bit shared-window addresses: replaced wholesale by the mbarrier model
 FUNCS = {

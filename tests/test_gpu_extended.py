@@ -110,9 +110,10 @@ def test_evenodd_beats_full_solve_and_keeps_plain_path():
     assert np.abs(out[True][1] - out[False][1]).max() < 1e-8
 
 
-# ---- t-marching TMA Wilson kernel (csrc/wilson_tmarch.cu, default on regular geometries) vs the register-resident kernel ----------
-@pytest.mark.parametrize("env", [{}, {"LQCD_TM_CHUNKS": "1"}, {"LQCD_TM_CHUNKS": "2"}, {"LQCD_WILSON_KERNEL": "1"}],
-                         ids=["tmarch-auto", "tmarch-1chunk", "tmarch-2chunks", "register-kernel"])
+# ---- Wilson kernel families: register-resident kernel (default; two-row or full links) and the experimental t-marching TMA kernel ------
+@pytest.mark.parametrize("env", [{"LQCD_WILSON_KERNEL": "4"}, {"LQCD_WILSON_KERNEL": "4", "LQCD_TM_CHUNKS": "1"}, {"LQCD_WILSON_KERNEL": "4", "LQCD_TM_CHUNKS": "2"},
+                                 {}, {"LQCD_LINKS12": "0"}],
+                         ids=["tmarch-auto", "tmarch-1chunk", "tmarch-2chunks", "register-kernel-two-row-links", "register-kernel-full-links"])
 def test_wilson_kernel_families_match_oracle(env):
     import os
     import subprocess

@@ -284,3 +284,50 @@ def test_rhmc_trajectory_matches_oracle(golden_dir):
     if acc:
         assert np.abs(U.data - U0).max() > 1e-3
         assert np.abs(np.einsum("...ij,...kj->...ik", U.data, U.data.conj()) - np.eye(3)).max() < 1e-9
+
+
+class _AlwaysReject:
+    """Metropolis draw of 2.0: exp(min(0, -dH)) <= 1 is never >= it -> every trajectory is rejected (seeds stay random)"""
+
+    def __init__(self, seed):
+        self._r = np.random.default_rng(seed)
+
+    def integers(self, *a, **k):
+        return self._r.integers(*a, **k)
+
+    def random(self):
+        return 2.0
+
+
+@pytest.mark.gpu
+def test_rejected_trajectory_and_second_operator_leave_each_operator_on_its_own_links(golden_dir):
+    """All operators of a context share one device link buffer.  After a REJECTED trajectory the device holds the evolved links
+    (hmc_update_ must restore U), and building a second operator with another U re-binds the buffer (the first operator must
+    re-upload its own U on next use): mul! through D has to give the same bits before and after both events."""
+    import lqcd_b200 as q
+    Uh = np.load(golden_dir / "wilson_4444.npy")
+    U = q.gaugefields_from_array(Uh.copy())
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    params = {"Dirac_operator": "Wilson", "κ": 0.12, "eps_CG": 1e-20, "MaxCGstep": 3000, "boundarycondition": [1, 1, 1, -1]}
+    D = q.Dirac_operator(U, x, params)
+    fa = q.FermiAction(D, {})
+    x.from_host(orc.gaussian_field((4, 4, 4, 4), orc.WILSON, seed=77))
+    y = q.similar(x)
+    q.mul_(y, D, x)
+    before = y.to_host()
+    acc, dH, info = q.hmc_update_(U, BETA, 0.05, 4, fa=fa, rng=_AlwaysReject(5))
+    assert not acc and np.array_equal(U.data, Uh)
+    assert np.array_equal(q.get_links(D.ctx), Uh)                 # device restored to the host configuration
+    q.mul_(y, D, x)
+    assert np.array_equal(y.to_host(), before)
+    # a second operator on the same lattice with other links
+    U2 = q.Initialize_Gaugefields(3, 0, 4, 4, 4, 4, condition="cold")
+    D2 = q.Dirac_operator(U2, x, params)
+    y2 = q.similar(x)
+    q.mul_(y2, D2, x)
+    assert not np.array_equal(y2.to_host(), before)
+    q.mul_(y, D, x)                                               # D finds the buffer re-bound and uploads its own U again
+    assert np.array_equal(y.to_host(), before)
+    props, infos = q.calc_quark_propagators_point_source(D2, U=U)  # measurement mirrors re-bind like the reference: D = m.D(U)
+    ref = orc.cgnr(orc.make_op((4, 4, 4, 4), kappa=0.12), orc.WILSON, Uh, orc.point_source((4, 4, 4, 4), orc.WILSON, 0, 0), eps=1e-20)
+    assert infos[0]["iters"] == ref["iters"]

@@ -1,4 +1,5 @@
-"""Correctness worker for the t-marching TMA Wilson kernel (csrc/wilson_tmarch.cu, the default Wilson path on regular geometries):
+"""Correctness worker for the Wilson kernel families (LQCD_WILSON_KERNEL=4: t-marching TMA kernel csrc/wilson_tmarch.cu; unset: the
+register-resident default with two-row links, LQCD_LINKS12=0 full links):
 operator applications and a CG solve (fused |Dp|^2 / residual-update epilogues) against the oracle on lattices whose tiling
 qualifies for the kernel, with several chunkings (LQCD_TM_CHUNKS).  The library caches its knobs per process, hence a worker
 (tests/test_emu_preflight.py under emulation with both bulk-copy completion schedules, tests/test_gpu_extended.py on the B200)."""
