@@ -576,9 +576,10 @@ EXPERIMENTS_MULTI = {       # most informative first: the leg stops starting new
     "default": ({}, "defaults: Wilson Dslash + CG (reference for the knob rows), BASELINE configs[3] (32^4 Wilson-clover CG) and, on 8 ranks, "
                     "configs[4] (32^3 x 64 staggered Nf = 2 RHMC trajectory, 12 poles)"),
     "timeline": ({"LQCD_COMM_TIMING": "1"}, "in-kernel phase stamps of the Wilson Dslash (pack / interior / face tiles / flag waits)"),
+    "self_pack_spt4": ({"LQCD_SELF_PACK": "1", "LQCD_PACK_SPT": "4"}, "pack CTAs lead the Dslash kernel, 4 face sites per pack thread (4x fewer pack CTAs)"),
     "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel"),
-    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream"),
     "tmarch_kernel": ({"LQCD_WILSON_KERNEL": "4"}, "t-marching TMA Wilson kernel (cyclic march: the two halo slices come last)"),
+    "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream"),
     "links_full": ({"LQCD_LINKS12": "0"}, "full 3x3 links instead of the two-row copy"),
     "pack_fence_sys": ({"LQCD_PACK_FENCE": "sys"}, "system-scope fence per pack CTA (round-1 default)"),
 }

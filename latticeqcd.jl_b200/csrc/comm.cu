@@ -313,10 +313,13 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
     const int slot = (int)(seq & 1);
     // measured on 2 / 8 B200 (profiles/r1g_*, round-1 experiments leg): a gpu-scope fence per pack CTA with ONE cumulative system
     // fence by the last pack CTA is faster than a system fence per CTA at every N (N = 2: 0.115 vs 0.125 ms, N = 8: 0.042 vs 0.045 ms)
-    static int sys_fence = -1, timing = -1, self_pack_env = -2;
+    static int sys_fence = -1, timing = -1, self_pack_env = -2, spt_env = -1, tune = -1;
+    if (tune < 0) { const char *e = getenv("LQCD_COMM_TUNE"); tune = (e && atoi(e) == 1) ? 1 : 0; }
+    if (tune) { timing = -1; self_pack_env = -2; spt_env = -1; }      // tools/comm_tune.py changes the knobs between timed runs of one process
     if (sys_fence < 0) { const char *e = getenv("LQCD_PACK_FENCE"); sys_fence = (e && e[0] == 's') ? 1 : 0; }
     if (timing < 0) { const char *e = getenv("LQCD_COMM_TIMING"); timing = (e && atoi(e) >= 1) ? 1 : 0; }
     if (self_pack_env == -2) { const char *e = getenv("LQCD_SELF_PACK"); self_pack_env = e ? (atoi(e) != 0) : -1; }
+    if (spt_env < 0) { const char *e = getenv("LQCD_PACK_SPT"); spt_env = (e && atoi(e) >= 1 && atoi(e) <= 64) ? atoi(e) : 0; }
     unsigned long long *tm = nullptr;
     if (timing) {
         if (!c->timing) {
@@ -329,14 +332,24 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         if (seq - c->timing_first < LQCD_TIMING_SLOTS) tm = c->timing + (seq - c->timing_first) * 8;
     }
     const bool tmarch = op->kind == LQCD_WILSON && wilson_tmarch_ok(ctx, op);     // consumes the slots itself, fed by the separate pack kernel
-    const int npart = g.part[0] + g.part[1] + g.part[2] + g.part[3];
-    const int self_pack = tmarch ? 0 : (self_pack_env >= 0 ? self_pack_env : (g.V <= (1 << 18) && (npart == 1 || g.V < (1 << 15))));
+    // Pack placement, measured on one 8 x B200 box at 32^4 (round 2, profiles/r2d_comm_tune_sweep.txt, us per Wilson application):
+    //   local volume 2^17 (8 GPUs): separate pack kernel 40.6 | pack CTAs leading the Dslash kernel, 1 / 2 / 4 / 8 / 16 face sites per
+    //                               pack thread 38-58 / 36.8 / 33.4 / 35.3 / 44.6
+    //   local volume 2^18 (4 GPUs): separate 66.3 (4 sites per thread 62.8) | leading 70.2 / 66.0 / 64.8 / 63.9 / 65.2
+    //   local volume 2^19 (2 GPUs): separate 108.4 (4 sites per thread 111.7) | leading 120.7 / 115.6 / 114.5 / 115.2 / 115.4
+    // (staggered: leading with 2-4 sites per thread wins up to 2^18, separate with 4 at 2^19).  The in-kernel timeline shows why: a
+    // separate pack kernel only gets SM slots as first-wave Dslash CTAs retire (its CTAs start 6-10 us late), which is hidden behind
+    // a long interior phase but not behind the 15-19 us of the 8-GPU local volume; leading pack CTAs start at once, and fewer, longer
+    // ones leave the rest of the first wave to the interior tiles.
+    const int self_limit = op->kind == LQCD_WILSON ? (1 << 17) : (1 << 18);
+    const int self_pack = tmarch ? 0 : (self_pack_env >= 0 ? self_pack_env : (g.V <= self_limit));
     const int pbs = self_pack ? 32 * g.wpc : 128;                                   // threads per pack CTA
+    const int spt = spt_env ? spt_env : (self_pack ? 4 : (g.V <= (1 << 18) || op->kind == LQCD_STAGGERED ? 4 : 1));   // face sites per pack thread
     HaloOut O;
     HaloIn H;
     memset(&O, 0, sizeof O);
     memset(&H, 0, sizeof H);
-    O.seq = seq; O.gpu_fence = !sys_fence; O.ticket = (unsigned int *)(c->base + c->off_ticket); O.timing = tm;
+    O.seq = seq; O.gpu_fence = !sys_fence; O.ticket = (unsigned int *)(c->base + c->off_ticket); O.timing = tm; O.spt = spt;
     H.seq = seq; H.err = (int *)(c->base + c->off_err); H.cta_order = c->cta_order; H.n_interior = c->n_interior;
     H.timeout_cycles = ctx->red.cr.timeout_cycles; H.timing = tm;
     int ncta = 0;
@@ -344,7 +357,7 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         H.pfirst[mu] = ctx->pcoord[mu] == 0; H.plast[mu] = ctx->pcoord[mu] == ctx->procgrid[mu] - 1;
         O.cta0[mu] = ncta;           // number of pack CTAs of partitioned directions < mu (non-partitioned ones own zero CTAs)
         if (!g.part[mu]) continue;
-        ncta += (2 * c->face[mu] + pbs - 1) / pbs;
+        ncta += (2 * c->face[mu] + pbs * spt - 1) / (pbs * spt);
         const int lo = c->nbr[mu][0], hi = c->nbr[mu][1];
         // my low face feeds the LOWER neighbour's "from upper" (side 1) slot; my high face the UPPER neighbour's side 0
         O.send[mu][0] = (cplx *)(c->peer[lo] + c->halo_off[mu][1][slot]);
@@ -357,9 +370,6 @@ int comm_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *x, int da
         }
     }
     O.cta0[4] = ncta;
-    // Self-packing (one launch, no second stream) for small local volumes with ONE partitioned direction, the separate pack kernel
-    // otherwise -- measured on 2 / 8 B200 in round 1: local volume 32.32.16.8 with one partitioned direction 39.0 us self-packing vs
-    // 41.7 us separate; 32.32.32.16: 122.5-126.5 vs 119.9 us; 8 GPUs, two partitioned directions: 52.0 vs 51.1 us.  LQCD_SELF_PACK=0/1 forces.
     if (self_pack) {
         if (op->kind == LQCD_WILSON) return launch_wilson_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);
         return launch_staggered_dslash(ctx, op, y, x, dagger, fuse, ctx->stream, &H, &O);

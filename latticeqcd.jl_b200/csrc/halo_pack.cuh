@@ -97,8 +97,10 @@ __device__ __forceinline__ void halo_pack_cta(const Geom &g, int kind, int dagge
     while (mu < 3 && pcta >= H.cta0[mu + 1]) mu++;
     const int d[4] = {g.X, g.Y, g.Z, g.T};
     const int F = g.V / d[mu];
-    const int i = (pcta - H.cta0[mu]) * blockDim.x + threadIdx.x;
-    if (i < 2 * F) {
+    // H.spt face sites per thread: fewer, longer pack CTAs leave the remaining CTA slots of the first wave to the interior tiles
+    for (int k = 0; k < H.spt; k++) {
+        const int i = ((pcta - H.cta0[mu]) * H.spt + k) * blockDim.x + threadIdx.x;
+        if (i >= 2 * F) break;
         const int side = i / F, f = i % F;
         const int s = face_site(g, mu, f, side ? d[mu] - 1 : 0);
         cplx *send = H.send[mu][side];

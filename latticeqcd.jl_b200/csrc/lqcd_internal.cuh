@@ -269,6 +269,7 @@ struct HaloOut {
     unsigned long long seq;              // application number published in the flags
     int gpu_fence;                       // 1: pack CTAs fence at gpu scope only; the LAST pack CTA's system fence (cumulative) covers them
     unsigned long long *timing;          // LQCD_COMM_TIMING=1: phase stamps of this application, else null
+    int spt;                             // face sites per pack thread (>= 1)
 };
 
 struct WilsonArgs {

@@ -128,7 +128,7 @@ __device__ __forceinline__ void clover_apply(cplx (&ax)[12], const cplx *__restr
 // alternatives (B200, round 2, profiles/r2a_kernel_sweep.txt): 144 registers / 14 warps 206 us, 128 registers / 16 warps 211 us
 // against 202 us at 32^4 (29.5 / 31.5 / 31.3 us on the 8-GPU local volume): occupancy is not the lever, bytes are.
 #ifndef LQCD_WILSON_MINB
-#define LQCD_WILSON_MINB 3          // experiment builds: LQCD_BUILD_DEFS=-DLQCD_WILSON_MINB=4 (128 registers, 16 warps per SM)
+#define LQCD_WILSON_MINB 4          // 128 registers, 16 warps per SM (experiment builds: LQCD_BUILD_DEFS=-DLQCD_WILSON_MINB=3 -> 168 registers, 12 warps)
 #endif
 template <int DAG, int MULTI, int LH, int CLOVER, int G12>
 __global__ void __launch_bounds__(128, LQCD_WILSON_MINB) wilson_dslash_kernel(const WilsonArgs A) {
