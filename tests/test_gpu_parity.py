@@ -365,3 +365,17 @@ def test_mask_parity(Us):
     ref = orc.cg(orc.make_op(dims, mass=0.5), orc.STAGGERED, Us, np.ascontiguousarray(src * even))
     assert info["iters"] == ref["iters"]
     assert np.abs(sol.to_host() * (~even)).max() == 0.0
+
+
+def test_verbose_level_3_prints_the_residual_history(Uw, capsys):
+    """universe.jl:133 passes verbose_level to the operator; at level 3 upstream prints '<i>-th eps: <r.r>' every CG step"""
+    U = q.gaugefields_from_array(Uw)
+    x = q.Initialize_pseudofermion_fields(U[0], "Wilson")
+    D = q.Dirac_operator(U, x, wparams(0.12, verbose_level=3))
+    x.from_host(orc.gaussian_field((4, 4, 4, 4), orc.WILSON, seed=9))
+    sol = q.similar(x)
+    q.clear_fermion_(sol)
+    info = q.solve_DinvX_(sol, q.DdagD(D), x)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if "-th eps:" in ln]
+    assert len(lines) == info["iters"] + 1 and lines[0].startswith("0-th eps:")
+    assert float(lines[-1].split(":")[1]) < 1e-19
