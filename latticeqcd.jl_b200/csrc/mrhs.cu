@@ -4,27 +4,25 @@
 // of the quark propagator (src/measurements/unusedfiles/measure_Pion_correlator.jl:333-349 maps
 // calc_quark_propagators_point_source_each over 1:NC*Nspinor, each ending in solve_DinvX!(p, D, b), :399) and the Nr Z4 noise
 // vectors of the chiral condensate (measure_chiral_condensate.jl:176-182).  On the CPU they run one after the other; here they
-// run in lock step so that every link matrix fetched from HBM is used for R right-hand sides:
+// run in lock step so that every link matrix fetched from HBM is used for R right-hand sides.  That pays for
+// the STAGGERED operator, where links are 576 of the 672 B/site (two-row links: 384 of 480): 576/R + 96 B per site and right-hand
+// side.  For Wilson the neighbour spinors dominate the L2 -> SM traffic and sharing links bought nothing (measured, see
+// staggered_group below), so Wilson right-hand sides take the single-RHS path inside the same entry points.
 //
-//     Wilson     960 B/site/RHS  ->  576/R + 384      (R = 3: 576 B, R = 4: 528 B)
-//     staggered  672 B/site/RHS  ->  576/R +  96      (R = 4: 240 B, R = 12: 144 B)
-//
-// Kernel: same site <-> thread, warp <-> AoSoA-32 block and CTA-tile mapping as the single-RHS kernels; per hop the 3x3 link is
-// loaded ONCE into registers (9 x 128-bit coalesced loads) and applied to the R neighbour spinors, each RHS keeping its own
-// accumulator.  grid.y runs over groups of R right-hand sides.  The per-RHS arithmetic (projection, SU(3) multiply,
-// reconstruction, xpay, |y|^2) is the single-RHS kernel's, operation for operation, and the per-RHS reductions use the same CTA
-// partial order, so one application reproduces lqcd_dslash bit for bit and every right-hand side of a CGNR solve reproduces
-// lqcd_solve bit for bit -- iteration counts included (the batched CG on DdagD keeps q = D^dag D p in memory instead of fusing the
-// residual update into the second Dslash, so it agrees with the single-RHS CG to rounding).
+// Kernel: same site <-> thread, warp <-> AoSoA-32 block and CTA-tile mapping as the single-RHS kernel; per hop the link is loaded
+// ONCE into registers and applied to the R neighbour vectors, each RHS keeping its own accumulator.  grid.y runs over groups of R
+// right-hand sides.  The per-RHS arithmetic is the single-RHS kernel's, operation for operation, and the per-RHS reductions use the
+// same CTA partial order, so one application reproduces lqcd_dslash bit for bit and every right-hand side of a CGNR solve
+// reproduces lqcd_solve bit for bit -- iteration counts included (the batched CG on DdagD keeps q = D^dag D p in memory instead
+// of fusing the residual update into the second Dslash, so it agrees with the single-RHS CG to rounding).
 //
 // Solver: CGNR (upstream "bicg", what solve_DinvX!(p, D, b) runs) and CG on DdagD, all right-hand sides advancing together; each
 // has its OWN SolverState / reduction workspace in device memory, converged systems drop out of the kernels (mask), the host
-// polls all states one batch behind the GPU.  Single rank (Wilson-clover included); anything else takes the single-RHS path inside the same
-// entry points, one right-hand side after the other.
+// polls all states one batch behind the GPU.  Single rank; anything else takes the single-RHS path, one right-hand side after the other.
 #include "lqcd_internal.cuh"
 #include "reduce.cuh"
 #include "site_map.cuh"
-#include "wilson_kernel.cuh"      // clover_apply (site-local clover term of the single-RHS kernel)
+#include "link_load.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -39,7 +37,6 @@ struct MrhsArgs {
     MrhsRed red[LQCD_MAX_RHS];
     const cplx *gauge;
     const cplx *links12; // two-row links (links12.cu) when the links are SU(3), else null: same choice as the single-RHS kernels
-    const cplx *clover;  // Wilson-clover: packed clover blocks (wilson_kernel.cuh), else null
     Geom g;
     double kappa, mass, sign;
     double bc[4];
@@ -67,108 +64,6 @@ __device__ __forceinline__ unsigned live_mask(const MrhsArgs &A, int rhs0) {
     }
     return mask;
 }
-
-// ---- Wilson ----------------------------------------------------------------------------------------------------------------
-template <int MU, int FWD, int DAG, int R>
-__device__ __forceinline__ void hop_m(cplx (&acc)[R][12], const MrhsArgs &A, int rhs0, unsigned mask, int ns, int ls, bool wrapped, double phase) {
-    constexpr int S = (FWD ^ DAG) ? -1 : +1;
-    cplx u[9];
-    if (A.links12) load_link<MU, 1, 0>(u, A.links12, ls); else load_link<MU, 0, 0>(u, A.gauge, ls);      // grid-uniform
-    const size_t so = (size_t)(ns >> 5) * (12 * 32) + (ns & 31);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        if (!((mask >> r) & 1u)) continue;
-        const cplx *sp = A.in[rhs0 + r] + so;
-        cplx h0[3], h1[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            cplx p0 = __ldg(sp + (0 + c) * 32), p1 = __ldg(sp + (3 + c) * 32);
-            cplx p2 = __ldg(sp + (6 + c) * 32), p3 = __ldg(sp + (9 + c) * 32);
-            project<MU, S>(h0[c], h1[c], p0, p1, p2, p3);
-        }
-        if (wrapped) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                if (FWD) { cfma(g0, u[a * 3 + b], h0[b]); cfma(g1, u[a * 3 + b], h1[b]); }
-                else     { cfmac(g0, u[b * 3 + a], h0[b]); cfmac(g1, u[b * 3 + a], h1[b]); }
-            }
-            reconstruct<MU, S>(acc[r], a, g0, g1);
-        }
-    }
-}
-
-template <int MU, int DAG, int R>
-__device__ __forceinline__ void hop_pair_m(cplx (&acc)[R][12], const MrhsArgs &A, int rhs0, unsigned mask, int s, int coord, int dim, int stride) {
-    {
-        const bool w = (coord == dim - 1);
-        const int ns = w ? s - (dim - 1) * stride : s + stride;
-        hop_m<MU, 1, DAG, R>(acc, A, rhs0, mask, ns, s, w, A.bc[MU]);
-    }
-    {
-        const bool w = (coord == 0);
-        const int ns = w ? s + (dim - 1) * stride : s - stride;
-        hop_m<MU, 0, DAG, R>(acc, A, rhs0, mask, ns, ns, w, A.bc[MU]);
-    }
-}
-
-template <int DAG, int R, int MINB, int CLOVER>
-__global__ void __launch_bounds__(128, MINB) wilson_mrhs_kernel(const MrhsArgs A) {
-    const int rhs0 = blockIdx.y * R;
-    const unsigned mask = live_mask<R>(A, rhs0);
-    if (!mask) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int blk = block_of_warp(A.g, blockIdx.x, warp);
-    const bool active = blk < A.g.nblk;
-    cplx acc[R][12];
-#pragma unroll
-    for (int r = 0; r < R; r++)
-#pragma unroll
-        for (int k = 0; k < 12; k++) acc[r][k] = cmake(0.0, 0.0);
-    if (active) {
-        const int s = blk * 32 + lane;
-        int x, y, z, t;
-        site_coords(A.g, s, x, y, z, t);
-        hop_pair_m<0, DAG, R>(acc, A, rhs0, mask, s, x, A.g.X, 1);
-        hop_pair_m<1, DAG, R>(acc, A, rhs0, mask, s, y, A.g.Y, A.g.X);
-        hop_pair_m<2, DAG, R>(acc, A, rhs0, mask, s, z, A.g.Z, A.g.X * A.g.Y);
-        hop_pair_m<3, DAG, R>(acc, A, rhs0, mask, s, t, A.g.T, A.g.X * A.g.Y * A.g.Z);
-    }
-    const size_t base = (size_t)blk * (12 * 32) + lane;
-    const double mk = -A.kappa;
-    bool reduced = false;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        if (!((mask >> r) & 1u)) continue;
-        const int j = rhs0 + r;
-        double red[3] = {0.0, 0.0, 0.0};
-        if (active) {
-            const cplx *xin = A.in[j];
-            cplx *dst = A.out[j];
-            cplx ax[12];                    // CLOVER only (dead otherwise): A(n) x(n), as in the single-RHS kernel
-            if constexpr (CLOVER != 0) clover_apply(ax, A.clover + (size_t)blk * (36 * 32) + lane, xin + base);
-#pragma unroll
-            for (int k = 0; k < 12; k++) {
-                cplx xi;
-                if constexpr (CLOVER != 0) xi = ax[k]; else xi = __ldg(xin + base + k * 32);
-                const cplx yk = cmake(fma(mk, acc[r][k].x, xi.x), fma(mk, acc[r][k].y, xi.y));
-                red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
-                dst[base + k * 32] = yk;
-            }
-        }
-        if (A.want_norm) {
-            if (reduced) __syncthreads();          // the shared scratch of the previous right-hand side's reduction is free again
-            grid_reduce_finish<3>(red, reduce_of(A.red[j]), A.finish);
-            reduced = true;
-        }
-    }
-}
-
 
 // ---- staggered -------------------------------------------------------------------------------------------------------------
 template <int MU, int FWD, int R>
@@ -394,17 +289,12 @@ static void fill_red(const MrhsWork *w, MrhsRed *red) {
     }
 }
 
-// right-hand sides per thread.  Wilson 2 / 3 (LQCD_MRHS_R): R = 2 fits the single-RHS kernel's 168-register budget, R = 3 needs
-// __launch_bounds__(128, 2) (255 registers, no spills).  Measured on B200 at 32^4, 12 right-hand sides, full links (round 2,
-// profiles/r2a_experiments_n1.json): R = 2 0.99x, R = 3 1.04x per right-hand side against the single-RHS kernel; R = 4 (528 B of
-// spills) 0.56x and a variant with the links staged in shared memory by bulk copies (one CTA per SM) 0.71x -- both removed.
-// Staggered 2 / 3 / 4 / 6 / 8 / 12 (LQCD_MRHS_R_STAGGERED, no spills); default 4.
-static int wilson_group(int nrhs) {
-    static int env = -1;
-    if (env < 0) { const char *e = getenv("LQCD_MRHS_R"); env = e ? atoi(e) : 0; }
-    if (env == 2 || env == 3) return env;
-    return (nrhs == 2 || nrhs == 4) ? 2 : 3;
-}
+// Right-hand sides per thread of the staggered kernel: 2 / 3 / 4 / 6 / 8 / 12 (LQCD_MRHS_R_STAGGERED), default 4.  Measured on B200 at
+// 32^4 with 12 right-hand sides and two-row links (round 2, profiles/r2e_experiments_n1.json), per right-hand side against the
+// single-RHS kernel: R = 2 1.08x, 3 1.23x, 4 1.34x, 6 1.08x, 12 0.81x (230 registers).
+// A Wilson multi-RHS kernel (links in registers shared by R = 2 / 3 / 4 right-hand sides, and a variant with the links staged in
+// shared memory by bulk copies) was measured in rounds 1 and 2: 0.56-1.04x -- the Wilson kernel is bound by spinor traffic over the
+// L2 -> SM fabric, which sharing links does not reduce -- and removed; Wilson right-hand sides go through the single-RHS path.
 static int staggered_group(int nrhs) {
     static int env = -1;
     if (env < 0) { const char *e = getenv("LQCD_MRHS_R_STAGGERED"); env = e ? atoi(e) : 0; }
@@ -432,17 +322,8 @@ static int launch_mrhs(lqcd_ctx *ctx, const lqcd_op *op, cplx *const *out, const
     A.nrhs = nrhs; A.want_norm = want_norm; A.finish = finish; A.use_state = use_state;
     const int bs = 32 * ctx->g.wpc;
     const int gx = (ctx->g.nblk + ctx->g.wpc - 1) / ctx->g.wpc;
-    if (op->kind == LQCD_WILSON) {
-        if (op->r != 1.0) return lqcd_fail(ctx, LQCD_ERR_ARG, "Wilson kernel implements r = 1 only (got r = %g)", op->r);
-        if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "multi-RHS Wilson kernel: LQCD_WPC > 4 is not supported");
-        if (op->csw != 0.0) { LQCD_TRY(ensure_clover(ctx, op)); A.clover = ctx->clover; }
-        int R = wilson_group(nrhs);
-        const dim3 grid(gx, (nrhs + R - 1) / R);
-#define WM(R_, MB_, CL_) do { if (dagger) wilson_mrhs_kernel<1, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); else wilson_mrhs_kernel<0, R_, MB_, CL_><<<grid, bs, 0, ctx->stream>>>(A); } while (0)
-        if (A.clover) { if (R == 2) WM(2, 2, 1); else WM(3, 2, 1); }          // Wilson-clover: 2 or 3 right-hand sides per thread
-        else if (R == 2) WM(2, 3, 0); else WM(3, 2, 0);
-#undef WM
-    } else {
+    if (op->kind != LQCD_STAGGERED) return lqcd_fail(ctx, LQCD_ERR_STATE, "multi-RHS kernel: staggered only");
+    {
         const int R = staggered_group(nrhs);
         const dim3 grid(gx, (nrhs + R - 1) / R);
         if (R == 2) staggered_mrhs_kernel<2><<<grid, bs, 0, ctx->stream>>>(A);
@@ -486,10 +367,9 @@ static int check_fields(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys
     return LQCD_OK;
 }
 
-// the batched kernels cover: one rank, Wilson (r = 1, with or without the clover term) / staggered, full (not even-odd) fields,
-// regular or irregular tiling
+// the batched kernels cover: one rank, staggered, full (not even-odd) fields, regular or irregular tiling
 static bool batched_ok(const lqcd_ctx *ctx, const lqcd_op *op) {
-    return ctx->nranks == 1 && !(op->kind == LQCD_WILSON && op->r != 1.0) && !ctx->eo_active && 32 * ctx->g.wpc <= (op->kind == LQCD_WILSON ? 128 : 256);
+    return ctx->nranks == 1 && op->kind == LQCD_STAGGERED && !ctx->eo_active && 32 * ctx->g.wpc <= 256;
 }
 
 extern "C" int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const xs[], int nrhs, int mode) {
@@ -573,16 +453,18 @@ extern "C" int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *
     if (method != LQCD_SOLVER_CG && target != LQCD_OP_D && target != LQCD_OP_DDAG) return lqcd_fail(ctx, LQCD_ERR_ARG, "CGNR/BiCGStab solve D or D^dag");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (!batched_ok(ctx, op) || method == LQCD_SOLVER_BICGSTAB) {       // one right-hand side after the other through the single-RHS path
-        int rc_all = LQCD_OK;
+        int first_bad = -1;
+        std::string first_msg;
         for (int j = 0; j < nrhs; j++) {
             int it = 0; double rs = 0.0;
             const int rc = lqcd_solve(ctx, op, ys[j], bs[j], method, target, eps, maxsteps, &it, &rs, nullptr);
             if (iters) iters[j] = it;
             if (resid_sq) resid_sq[j] = rs;
             if (rc != LQCD_OK && rc != LQCD_ERR_NOCONV) return rc;
-            if (rc != LQCD_OK) rc_all = rc;
+            if (rc != LQCD_OK && first_bad < 0) { first_bad = j; first_msg = ctx->err; }      // keep solving the others, like the batched path
         }
-        return rc_all;
+        if (first_bad >= 0) return lqcd_fail(ctx, LQCD_ERR_NOCONV, "right-hand side %d: %s", first_bad, first_msg.c_str());
+        return LQCD_OK;
     }
     MrhsWork *w = nullptr;
     LQCD_TRY(mrhs_work(ctx, &w));

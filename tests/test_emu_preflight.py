@@ -141,7 +141,7 @@ def test_bench_experiments_leg_under_emulation(emu_lib, monkeypatch):
     assert set(res) == set(bench.EXPERIMENTS)
     bad = {k: v for k, v in res.items() if not v.get("ok")}
     assert not bad, bad
-    assert res["mrhs_r3"]["bit_identical_to_single_rhs"] and res["staggered_mrhs"]["bit_identical_to_single_rhs"]
+    assert res["staggered_mrhs"]["bit_identical_to_single_rhs"] and res["staggered_mrhs_r3"]["bit_identical_to_single_rhs"]
     assert res["tmarch_kernel"]["max_rel_dev_vs_default"] < 1e-13 and res["links_full"]["max_rel_dev_vs_default"] < 1e-13
 
 
