@@ -100,11 +100,13 @@ extern "C" int lqcd_ctx_create(const int gd[4], const int pg[4], int rank, int d
     ctx->gauge_epoch = 0; ctx->clover = nullptr; ctx->clover_k = nullptr; ctx->clover_epoch = ~0ull; ctx->clover_coef = 0.0;
     ctx->hist_dev = nullptr; ctx->hist_cap = 0;
     ctx->links12 = nullptr; ctx->links12_epoch = ~0ull; ctx->links12_ok = false; ctx->links12_dev = 0.0; ctx->links12_scratch = nullptr;
-#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); delete ctx; return rc; } } while (0)
+    // a failure half way through creation goes through the normal destructor (null-safe frees), so streams / events / allocations
+    // made so far are released
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { int rc = lqcd_fail(nullptr, LQCD_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)); lqcd_ctx_destroy(ctx); return rc; } } while (0)
     CT(cudaSetDevice(device));
     cudaDeviceProp prop;
     CT(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) { delete ctx; return lqcd_fail(nullptr, LQCD_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
+    if (prop.major != 10) { lqcd_ctx_destroy(ctx); return lqcd_fail(nullptr, LQCD_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
     ctx->num_sms = prop.multiProcessorCount;
     CT(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {   // stream2 carries the halo pack kernels: highest priority so that its CTAs are dispatched before the
@@ -156,8 +158,11 @@ extern "C" int lqcd_ctx_destroy(lqcd_ctx *ctx) {
     cudaFree(ctx->gauge); cudaFree(ctx->stage); cudaFree(ctx->flush); cudaFree(ctx->hist_dev); cudaFree(ctx->force_buf); cudaFree(ctx->mom); cudaFree(ctx->clover); cudaFree(ctx->clover_k);
     cudaFree(ctx->queue); cudaFree(ctx->red.partials); cudaFree(ctx->red.ticket); cudaFree(ctx->red.st);
     cudaFreeHost(ctx->st_host);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_int); cudaEventDestroy(ctx->ev_poll[0]); cudaEventDestroy(ctx->ev_poll[1]);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
+    cudaEvent_t evs[6] = {ctx->ev0, ctx->ev1, ctx->ev_pack, ctx->ev_int, ctx->ev_poll[0], ctx->ev_poll[1]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);                    // (null after a creation that failed half way)
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    cudaGetLastError();
     delete ctx;
     return LQCD_OK;
 }

@@ -206,7 +206,10 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[NR], const Reduce
                     if (clock64() - t0 > c.timeout_cycles) { ok = false; break; }
                 }
             }
-            if (!ok) { *c.err = 2000000 + (int)(seq % 1000000); R.st->done = 1; R.st->failed = 2; }
+            if (!ok) {       // a lost peer: report LQCD_ERR_COMM (failed = 2) and stop here -- the partial sums must not reach the finish op
+                *c.err = 2000000 + (int)(seq % 1000000); R.st->done = 1; R.st->failed = 2; R.st->iters = R.st->it;
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < NR; j++) {
                 double s = 0.0;
