@@ -47,7 +47,7 @@ STAG_BYTES_PER_SITE = 672     # 576 links + 48 in + 48 out
 STAG_FLOP_PER_SITE = 582
 # N-independent fingerprints of the bench workload (hot links seed 111, Gaussian sources seed 112, kappa 0.12 / mass 0.5): measured
 # at N = 1 where the same run compares y = D x with the oracle; every N must reproduce them to 1e-12 (deterministic reductions).
-EXPECTED = {"32x32x32x32": {"norm_Dx_sq": 15490456.52178676, "staggered_norm_Dx_sq": 7083744.73603815, "cg_converged_iters_eps1e-10": None}}
+EXPECTED = {"32x32x32x32": {"norm_Dx_sq": 15490456.52178676, "staggered_norm_Dx_sq": 7083744.73603815, "cg_converged_iters_eps1e-10": 140}}
 KAPPA = 0.12
 BC = [1, 1, 1, -1]
 
