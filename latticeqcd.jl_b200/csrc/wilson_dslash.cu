@@ -52,10 +52,10 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
     if (lh_env == -2) { const char *e = getenv("LQCD_LINK_HINT"); lh_env = e ? (atoi(e) != 0) : -1; }
     const int lh = lh_env >= 0 ? lh_env : (ctx->g.V <= (1 << 18));
     if (bs > 128) return lqcd_fail(ctx, LQCD_ERR_ARG, "LQCD_WPC > 4 is not supported by the Wilson kernel");
-    // kernel family: 1 = one lane per site, register-resident hops (this file); 4 = t-marching kernel with TMA-staged spinor
-    // window and link stages (wilson_tmarch.cu), which falls through to family 1 when the geometry does not qualify.
-    // (Rounds 1 / 2 also measured a two-lanes-per-site kernel, 222-355 us at 32^4, and a first t-marching kernel with LDG links,
-    // 335-490 us: both removed.)
+    // kernel family: default = one thread per site, register-resident hops (wilson_kernel.cuh); LQCD_WILSON_KERNEL=4 = t-marching
+    // kernel with TMA-staged spinor window and link planes (wilson_tmarch.cu, experimental: 300 vs 173 us at 32^4), which falls
+    // through to the default when the geometry does not qualify.  (Rounds 1 / 2 also measured a two-lanes-per-site kernel,
+    // 222-355 us, a first t-marching kernel with LDG links, 335-490 us, and a persistent tile-queue variant: all removed.)
     static int family = -1;
     if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = e ? atoi(e) : 0; }
     if (A.clover) {                    // Wilson-clover: CLOVER = 1 instantiations live in wilson_clover.cu

@@ -124,9 +124,10 @@ __device__ __forceinline__ void clover_apply(cplx (&ax)[12], const cplx *__restr
 
 // MULTI: 0 single GPU | 1 fused halo (separate pack kernel on the priority stream) | 2 self-packing (the leading CTAs of this
 // kernel ship the halo).  (A persistent-CTA tile-queue variant was measured in rounds 1 / 2: slower at every N, removed.)
-// G12: links read from the two-row copy (links12.cu).  __launch_bounds__(128, 3): <= 168 registers, 12 warps per SM.  Measured
-// alternatives (B200, round 2, profiles/r2a_kernel_sweep.txt): 144 registers / 14 warps 206 us, 128 registers / 16 warps 211 us
-// against 202 us at 32^4 (29.5 / 31.5 / 31.3 us on the 8-GPU local volume): occupancy is not the lever, bytes are.
+// G12: links read from the two-row copy (links12.cu).  __launch_bounds__(128, 4): 128 registers, 16 warps per SM.  Measured on
+// B200 at 32^4 (round 2): with FULL links 12 / 14 / 16 warps per SM ran 202 / 206 / 211 us (profiles/r2a_kernel_sweep.txt) -- the
+// kernel sat at the L2 -> SM fabric limit and more warps only lowered the L1 hit rate; with two-row links 12 warps take 182 us and
+// 16 warps 173 us (26.6 vs 28.8 us on the 8-GPU local volume; profiles/r2c_occupancy_with_links12.txt).
 #ifndef LQCD_WILSON_MINB
 #define LQCD_WILSON_MINB 4          // 128 registers, 16 warps per SM (experiment builds: LQCD_BUILD_DEFS=-DLQCD_WILSON_MINB=3 -> 168 registers, 12 warps)
 #endif

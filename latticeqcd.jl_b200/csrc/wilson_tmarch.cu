@@ -1,7 +1,8 @@
 // wilson_tmarch.cu -- Wilson Dslash, fp64, sm_100a: t-marching kernel with ALL compulsory traffic staged through shared memory by
-// TMA bulk copies (cp.async.bulk + mbarrier).  Default Wilson path for regular geometries (x-line blocks, 4-warp (y,z) patches);
-// launch_wilson_tmarch returns LQCD_ERR_STATE for anything else and the caller falls back to the register-resident kernel
-// (wilson_kernel.cuh).
+// TMA bulk copies (cp.async.bulk + mbarrier).  EXPERIMENTAL (LQCD_WILSON_KERNEL=4), not the default: correct on hardware (parity
+// tests on 1 / 2 / 8 GPUs) and it moves the bytes it was designed to move, but at 300 us per 32^4 application it loses to the
+// register-resident kernel (173 us) -- see "Measured" below.  Regular geometries only (x-line blocks, 4-warp (y,z) patches);
+// launch_wilson_tmarch returns LQCD_ERR_STATE for anything else and the caller takes the register-resident kernel.
 //
 // Why (measured, profiles/r2a_*): the register-resident kernel moves 2.29 GB per 32^4 application from L2 to the SMs (2.2 KB/site,
 // L1 hit rate 22 %) at 11 TB/s -- that is the L2->SM fabric limit (probe: 10.8 TB/s), so it sits at 0.76 of the HBM roofline and no
@@ -18,6 +19,11 @@
 //   * only the out-of-patch y / z neighbours (2 of 8 hops per site for a 2x2 patch) and their backward links use LDG.
 // L2 -> SM traffic: 24 KB (compulsory) + ~16.5 KB per block-step = 1.27 KB/site instead of 2.2 KB; bytes in flight per SM are
 // set by the copy schedule (~90 KB), not by registers or occupancy.
+//
+// Measured (B200, 32^4, profiles/r2b_wilson_tmarch_ncu_full.csv): 298-300 us; L2 -> SM traffic 1.43 GB (register kernel: 2.29 GB
+// with full links, 2.03 GB with two-row links), DRAM 1.10 GB; but 144 KB of staging per CTA leaves ONE 4-warp CTA per SM = one warp
+// per scheduler, and the issue slots are 20 % busy: stall samples 33 % fixed-latency (FP64 dependency chains), 22 % LDG of the
+// out-of-patch neighbours, 14 % LDS latency, 7 % the four CTA barriers per step.  What it would take to win is in DESIGN.md section 8.
 //
 // Reference semantics: LinearAlgebra.mul!(y, D, x) / mul!(y, D', x) of LatticeDiracOperators.jl (upstream Wx!/Wdagx!, SURVEY.md
 // App. C.1); call sites src/md/AbstractMD.jl:129, src/updates/standardHMC.jl:69-71, measure_Pion_correlator.jl:379,399.
