@@ -125,6 +125,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return r;
 }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
 static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 static inline void sincospi(double x, double *s, double *c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }

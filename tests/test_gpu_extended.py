@@ -167,7 +167,7 @@ def _mrhs_setup(kind, dims, seed=3):
     return q, Uh, U, x, D, orc.make_op(dims, kappa=0.12, mass=0.5)
 
 
-@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (6, 8, 4, 4), (32, 4, 4, 4)])
+@pytest.mark.parametrize("dims", [(4, 4, 4, 4), (6, 8, 4, 4), (32, 4, 4, 4), (16, 8, 4, 6)])
 @pytest.mark.parametrize("kind,nrhs", [(orc.WILSON, 2), (orc.WILSON, 5), (orc.WILSON, 12), (orc.WILSON, 16),
                                        (orc.STAGGERED, 3), (orc.STAGGERED, 7), (orc.STAGGERED, 16)])
 def test_multi_rhs_dslash_is_bit_identical_to_single(dims, kind, nrhs):
@@ -189,13 +189,14 @@ def test_multi_rhs_dslash_is_bit_identical_to_single(dims, kind, nrhs):
             assert np.array_equal(xs[j].to_host(), srcs[j])             # inputs untouched
 
 
+# (8, 4, 4, 8): irregular patch shape -> register multi-RHS kernel; (8, 8, 4, 8): 2x2 (y,z) patches -> t-marching TMA multi-RHS kernel
+@pytest.mark.parametrize("dims", [(8, 4, 4, 8), (8, 8, 4, 8)])
 @pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
 @pytest.mark.parametrize("dagger", [False, True])
-def test_multi_rhs_cgnr_matches_single_solves(kind, dagger):
+def test_multi_rhs_cgnr_matches_single_solves(kind, dagger, dims):
     """solve_DinvX_multi_ (CGNR = upstream "bicg"): right-hand sides of very different difficulty (point sources, Gaussian noise, a
     source that is already solved by its initial guess) advance in lock step; each one's iteration count, residual and solution
     are those of its own single solve, bit for bit; iteration counts equal the oracle's"""
-    dims = (8, 4, 4, 8)
     q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
     A = q.adjoint(D) if dagger else D
     srcs = []
@@ -227,9 +228,9 @@ def test_multi_rhs_cgnr_matches_single_solves(kind, dagger):
     assert infos[-1]["iters"] == 0
 
 
+@pytest.mark.parametrize("dims", [(8, 4, 4, 8), (8, 8, 4, 8)])
 @pytest.mark.parametrize("kind", [orc.WILSON, orc.STAGGERED])
-def test_multi_rhs_cg_on_DdagD(kind):
-    dims = (8, 4, 4, 8)
+def test_multi_rhs_cg_on_DdagD(kind, dims):
     q, Uh, U, x, D, op = _mrhs_setup(kind, dims)
     srcs = [orc.gaussian_field(dims, kind, seed=60 + j) for j in range(5)]
     bs = [q.similar(x).from_host(s) for s in srcs]
