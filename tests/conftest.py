@@ -24,6 +24,7 @@ def pytest_cmdline_main(config):
         opt.numprocesses = 4
         opt.dist = "load"
         opt.tx = ["popen"] * 4
+        sys.stderr.write("[conftest] -m \"not gpu\": running on 4 xdist workers with OMP_NUM_THREADS=2 (LQCD_TEST_SERIAL=1 or an explicit -n / --dist keeps your settings)\n")
 
 
 def pytest_configure(config):
