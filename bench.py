@@ -1047,7 +1047,7 @@ def run_b200(args, dims):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     want = os.environ.get("LQCD_BENCH_EXPERIMENTS", "1") != "0"
-    budget = float(os.environ.get("LQCD_BENCH_EXPERIMENTS_S", "300"))
+    budget = float(os.environ.get("LQCD_BENCH_EXPERIMENTS_S", "150"))
     watchdog = None
     if want:
         # (every rank arms it: a rank that is stuck behind a lost peer must not keep the launcher waiting either)
