@@ -826,12 +826,16 @@ def run_b200(args, dims):
     # The bracket must not depend on how small --steps is: lqcd_time_dslash first runs two untimed applications (they align the
     # ranks through the halo flags, so no launch skew from the host barrier is measured), and at least MIN_TIMED applications are
     # timed; ms_per_step = bracket / applications, `steps` is reported as given.
-    MIN_TIMED = 200
+    MIN_TIMED = 200 * world               # N = 8: 1600 applications of ~35 us, so the bracket is tens of ms at every N
     reps = max(args.steps, MIN_TIMED)
     mean, mn = C.c_double(), C.c_double()
+    # the clock sampler (nvidia-smi polling GPU `local_rank` of rank 0 every 100 ms) starts BEFORE the warm-up: its start-up (fork,
+    # NVML initialisation) must not fall into a bracket that is only a few ms long at N = 8
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.5)
     ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, max(args.warmup, 3), 0, C.byref(mean), C.byref(mn))
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = ctx.launch_count()
     t_wall0 = time.perf_counter()
     ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
@@ -1010,7 +1014,7 @@ def run_b200(args, dims):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_string(args.lattice),
                        "procgrid": list(pg), "l2": f"not flushed: per-GPU inputs {806 // world} MB vs 126 MB L2 (N=8: L2-resident by strong scaling); ms_flushed = per-application time with a 512 MB memset between applications (N=1 only)",
-                       "timing": f"one CUDA-event bracket around max(steps, {MIN_TIMED}) back-to-back applications on the library stream after two untimed aligning applications, / applications, max over ranks",
+                       "timing": f"one CUDA-event bracket around max(steps, {MIN_TIMED} = 200 x GPUs) back-to-back applications on the library stream after two untimed aligning applications, / applications, max over ranks",
                        "applications_timed": reps, "ms_flushed": ms_flushed, "wall_s_timed_region": t_wall,
                        # the CG half of the metric, where the driver keeps it
                        "cg_iters_per_s": cg_ips, "cg_iters_timed": n_it,
