@@ -190,16 +190,16 @@ int lqcd_gauge_save(lqcd_ctx *ctx, const char *path, int format);
 /* ---- several right-hand sides in lock step ----------------------------------------------------------
  *      The reference's measurement solves are loops of independent solves against the same links: the NC*Nspinor point sources
  *      of calc_quark_propagators_point_source (src/measurements/unusedfiles/measure_Pion_correlator.jl:333-349, solve_DinvX! at
- *      :399) and the Nr noise vectors of the chiral condensate (measure_chiral_condensate.jl:176-182).  Here every link fetched
- *      from HBM serves a group of right-hand sides (csrc/mrhs.cu); each right-hand side keeps its own Krylov scalars, stopping
- *      test (reference rule, eps absolute and squared) and iteration count.
+ *      :399) and the Nr noise vectors of the chiral condensate (measure_chiral_condensate.jl:176-182).  For the staggered
+ *      operator every link fetched from HBM serves a group of right-hand sides that advance in lock step (csrc/mrhs.cu); each
+ *      right-hand side keeps its own Krylov scalars, stopping test (reference rule, eps absolute and squared) and iteration count.
  *      lqcd_dslash_multi   ys[j] = op(mode) xs[j], j < nrhs <= 16: bit-identical to nrhs calls of lqcd_dslash
  *      lqcd_solve_multi    op(target) ys[j] = bs[j], ys[j] is the initial guess; method CGNR (upstream "bicg", target D / D^dag:
  *                          per right-hand side bit-identical to lqcd_solve) or CG (target DdagD); BICGSTAB runs the right-hand
  *                          sides one after the other.  iters / resid_sq: arrays of nrhs (nullable).  LQCD_ERR_NOCONV if any
  *                          right-hand side did not converge (the arrays are filled for all of them).
- *      Wilson-clover is covered (clover term in the epilogue).  Several ranks, r != 1: the same entry points take the single-RHS
- *      path, one right-hand side after the other. */
+ *      Wilson (any variant: a Wilson multi-RHS kernel measured slower than the single-RHS kernel and was removed), several ranks:
+ *      the same entry points take the single-RHS path, one right-hand side after the other, with the same results. */
 int lqcd_dslash_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const xs[], int nrhs, int mode);
 int lqcd_solve_multi(lqcd_ctx *ctx, const lqcd_op *op, lqcd_fermion *const ys[], const lqcd_fermion *const bs[], int nrhs,
                      int method, int target, double eps, int maxsteps, int *iters, double *resid_sq);
