@@ -33,3 +33,16 @@ def test_reference_arm_json_line():
 def test_reference_arm_other_ranks_are_silent():
     r = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_honours_steps_and_shares_the_workload_string():
+    """the driver compares steps / warmup / config.workload of the two arms: the CPU arm runs exactly the requested steps and prints
+    the same workload string as the B200 arm; the live-reference probe (julia, baseline/_ref) is recorded in the line"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    r = run()
+    d = json.loads(r.stdout.strip())
+    assert d["steps"] == 2 and d["warmup"] == 1
+    assert d["config"]["workload"] == bench.workload_string("8x8x8x8")
+    assert "live reference probe" in d["config"]["arm"] and '"julia"' in d["config"]["arm"]
+    assert d["cpu_baseline"]["sample"].startswith("2 full-lattice applications")
