@@ -171,3 +171,14 @@ def test_fermi_action_nf_dispatch_on_b200(golden_dir):
         Fr += a * orc.force(op, orc.STAGGERED, Uh, X, Y)
     q.calc_UdSfdU_(F, fa2, U, eta)
     assert np.abs(F - Fr).max() < 1e-8 * np.abs(Fr).max()
+
+
+def test_rational_fit_that_misses_its_tolerance_is_refused():
+    """a user-supplied order / spectral range the fit cannot cover must raise instead of silently biasing the action (the
+    tolerance is parameters_action["rational_tolerance"], default 1e-6)"""
+    from lqcd_b200 import rhmc
+    bad = rhmc.RHMCAction(None, 2, 1e-3, 20.0, order=3)
+    with pytest.raises(ValueError, match="max relative error"):
+        bad.r_action
+    good = rhmc.RHMCAction(None, 2, 0.22, 17.0, order=12)
+    assert good.r_action.max_rel_err < 1e-7
