@@ -290,6 +290,7 @@ EXPERIMENTS = {
     # name: (environment of the child, what it measures)
     "default": ({}, "default Wilson kernel: register-resident, one thread per site, two-row links (reference for the rows below; writes the 16^4 comparison vector)"),
     "tmarch_kernel": ({"LQCD_WILSON_KERNEL": "4"}, "t-marching kernel with TMA-staged spinor window and link planes (wilson_tmarch.cu, experimental)"),
+    "tmarch2_kernel": ({"LQCD_WILSON_KERNEL": "5"}, "second-generation t-marching TMA kernel: two CTAs per SM, two-row link planes, carried t-backward hop (wilson_tmarch.cu, experimental)"),
     "staggered_mrhs": ({}, "staggered: single-RHS kernel vs 12 right-hand sides, default grouping (4 per thread)"),
     "staggered_mrhs_r2": ({"LQCD_MRHS_R_STAGGERED": "2"}, "staggered, 2 right-hand sides per thread"),
     "staggered_mrhs_r3": ({"LQCD_MRHS_R_STAGGERED": "3"}, "staggered, 3 right-hand sides per thread"),
@@ -351,7 +352,7 @@ def _experiment_body(name, dims, out):
         ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
         return mean.value
 
-    if name in ("default", "register_kernel", "links_full", "tmarch_kernel"):
+    if name in ("default", "register_kernel", "links_full", "tmarch_kernel", "tmarch2_kernel"):
         ctx, op, x, y = setup(small)
         ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
         got = y.to_host()
@@ -361,6 +362,7 @@ def _experiment_body(name, dims, out):
         else:
             ref = np.load(ref_file)
             out["max_rel_dev_vs_default"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+            out["bit_identical_to_default"] = bool(np.array_equal(got, ref))
         out["ok"] = out["max_rel_dev_vs_default"] < 1e-13
         out["ms_16^4"] = dslash_ms(ctx, op, y, x, 50)
         ctx2, op2, x2, y2 = setup(dims)
@@ -578,6 +580,7 @@ EXPERIMENTS_MULTI = {       # most informative first: the leg stops starting new
     "self_pack_spt4": ({"LQCD_SELF_PACK": "1", "LQCD_PACK_SPT": "4"}, "pack CTAs lead the Dslash kernel, 4 face sites per pack thread (4x fewer pack CTAs)"),
     "self_pack": ({"LQCD_SELF_PACK": "1"}, "pack CTAs lead the Dslash kernel"),
     "tmarch_kernel": ({"LQCD_WILSON_KERNEL": "4"}, "t-marching TMA Wilson kernel (cyclic march: the two halo slices come last)"),
+    "tmarch2_kernel": ({"LQCD_WILSON_KERNEL": "5"}, "second-generation t-marching TMA Wilson kernel (two CTAs per SM)"),
     "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream"),
     "links_full": ({"LQCD_LINKS12": "0"}, "full 3x3 links instead of the two-row copy"),
     "pack_fence_sys": ({"LQCD_PACK_FENCE": "sys"}, "system-scope fence per pack CTA (round-1 default)"),

@@ -63,7 +63,7 @@ int launch_wilson_dslash(lqcd_ctx *ctx, const lqcd_op *op, cplx *y, const cplx *
         ctx->launches++;
         return LQCD_OK;
     }
-    if (family == 4 && !sub) {                 // t-marching TMA kernel; LQCD_ERR_STATE = geometry does not qualify -> family 1
+    if ((family == 4 || family == 5) && !sub) {                 // t-marching TMA kernel; LQCD_ERR_STATE = geometry does not qualify -> family 1
         const int rc = launch_wilson_tmarch(ctx, A, dagger, s, halo != nullptr, hout != nullptr);
         if (rc != LQCD_ERR_STATE) return rc;
     }

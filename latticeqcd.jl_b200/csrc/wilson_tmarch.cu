@@ -1,8 +1,11 @@
-// wilson_tmarch.cu -- Wilson Dslash, fp64, sm_100a: t-marching kernel with ALL compulsory traffic staged through shared memory by
-// TMA bulk copies (cp.async.bulk + mbarrier).  EXPERIMENTAL (LQCD_WILSON_KERNEL=4), not the default: correct on hardware (parity
-// tests on 1 / 2 / 8 GPUs) and it moves the bytes it was designed to move, but at 300 us per 32^4 application it loses to the
-// register-resident kernel (173 us) -- see "Measured" below.  Regular geometries only (x-line blocks, 4-warp (y,z) patches);
-// launch_wilson_tmarch returns LQCD_ERR_STATE for anything else and the caller takes the register-resident kernel.
+// wilson_tmarch.cu -- Wilson Dslash, fp64, sm_100a: t-marching kernels with ALL compulsory traffic staged through shared memory by
+// TMA bulk copies (cp.async.bulk + mbarrier).  EXPERIMENTAL, not the default: correct on hardware and they move the bytes they were
+// designed to move, but both lose to the register-resident kernel (173 us per 32^4 application):
+//   LQCD_WILSON_KERNEL=4  first generation, one CTA per SM, 144 KB of staging: 300 us (parity tests on 1 / 2 / 8 GPUs);
+//   LQCD_WILSON_KERNEL=5  second generation (further down), two CTAs per SM, 96 KB of staging each: 182-184 us, bit-identical to
+//                         the default kernel (single GPU on hardware; multi-rank under tests/emu only).
+// Regular geometries only (x-line blocks, 4-warp (y,z) patches); launch_wilson_tmarch returns LQCD_ERR_STATE for anything else and
+// the caller takes the register-resident kernel.
 //
 // Why (measured, profiles/r2a_*): the register-resident kernel moves 2.29 GB per 32^4 application from L2 to the SMs (2.2 KB/site,
 // L1 hit rate 22 %) at 11 TB/s -- that is the L2->SM fabric limit (probe: 10.8 TB/s), so it sits at 0.76 of the HBM roofline and no
@@ -32,6 +35,7 @@
 #include "wilson_spin.cuh"
 #include "bulk_copy.cuh"
 #include "site_map.cuh"
+#include "link_load.cuh"
 #ifdef TM_DEBUG
 #include "../../tools/debug/tm_debug.cuh"
 #endif
@@ -48,6 +52,7 @@
 struct TMArgs {
     WilsonArgs A;
     int Lc, nchunk, nsb, ntasks;            // t-steps per task, chunks per patch, blocks per t-slice, tasks = patches * chunks
+    int prefetch;                           // second generation: pull the next task's first records into L2 during the last step
 };
 
 // hop arithmetic on operands already in registers: p = neighbour spinor, u = link (row-major 3x3)
@@ -336,18 +341,298 @@ __global__ void __launch_bounds__(128, 1) wilson_tmarch_kernel(const TMArgs K) {
     if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Second generation (LQCD_WILSON_KERNEL=5): the same march with HALF the staging, so that TWO CTAs (8 warps, two per scheduler) share
+// an SM -- the first kernel's one warp per scheduler is what left its issue slots 80 % idle.
+//   * link planes hold two-row records (links12.cu: 3 KB instead of 4.5 KB per block and direction; the third row is rebuilt in
+//     registers by the same link_row3() as the register-resident kernel, so the two stay bit-identical);
+//   * the window has TWO slots (t, t+1): the t-backward hop of slice t+1, U_t(t)^dag P psi(t), needs only operands the step of
+//     slice t already holds (own spinor, own t link), so it is computed there and CARRIED to the next step in 24 registers; the
+//     first step of a task computes its carry from 18 global loads;
+//   * three CTA barriers per step (one per spatial direction, after which the direction's plane is refilled); the window slot and
+//     the t plane are private to a warp once the z phase is over and are refilled after a warp-level sync.
+// 96 KB of staging per CTA.  Needs SU(3) links (two-row copy valid); otherwise the caller takes the register-resident kernel.
+//
+// Measured (B200, 32^4, profiles/r2j_wilson_tmarch2.txt): 184.1 us with the automatic chunking (8 chunks of 4 slices: 2048 tasks on
+// 296 resident CTAs = 6.9 rounds), 191 / 196 / 199 / 197 us with 1 / 2 / 4 / 16 chunks.  A fit of those five numbers gives 5.8 us
+// per step and ~0.5 step of pipeline fill per task, i.e. ~161 us if the 256 patches could be spread evenly over 296 CTA slots with
+// long chunks -- they cannot (256 x nchunk tasks), and splitting the (patch, t) sequence evenly would give up the common t wavefront
+// that keeps the out-of-patch neighbours L2 hits.  Pulling the next task's first records into L2 during the last step
+// (LQCD_TM_PREFETCH=1) did not help: 187.9 us.  So: 1.63x faster than the first generation, 6 % slower than the default kernel.
+#define TM2_SUB (6 * 32)
+#define TM2_SUB_BYTES (TM2_SUB * 16)
+#define TM2_SMEM_BYTES ((2 * TM_W * TM_REC + 4 * TM_W * TM2_SUB) * 16 + 64)
+
+__device__ __forceinline__ void ld_link12_s(cplx (&u)[9], const cplx *s) {
+#pragma unroll
+    for (int e = 0; e < 6; e++) u[e] = s[e * 32];
+    link_row3(u);
+}
+__device__ __forceinline__ void ld_link12_g(cplx (&u)[9], const cplx *__restrict__ gp) {
+#pragma unroll
+    for (int e = 0; e < 6; e++) u[e] = __ldg(gp + e * 32);
+    link_row3(u);
+}
+// the t-backward hop of the NEXT slice from this site's spinor and t link: g = U_t(n)^dag P psi(n) (times the boundary phase when
+// the next slice is t = 0); reconstruct<3, S>(acc, a, g0[a], g1[a]) there completes hop_regs<3, 0, DAG> bit for bit
+template <int DAG>
+__device__ __forceinline__ void carry_make(cplx (&c0)[3], cplx (&c1)[3], const cplx (&p)[12], const cplx (&u)[9], bool wrapped, double phase) {
+    constexpr int S = DAG ? -1 : +1;
+    cplx h0[3], h1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) project<3, S>(h0[c], h1[c], p[c], p[3 + c], p[6 + c], p[9 + c]);
+    if (wrapped) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { h0[c] = cscale(phase, h0[c]); h1[c] = cscale(phase, h1[c]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        cplx g0 = cmake(0.0, 0.0), g1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < 3; b++) { cfmac(g0, u[b * 3 + a], h0[b]); cfmac(g1, u[b * 3 + a], h1[b]); }
+        c0[a] = g0; c1[a] = g1;
+    }
+}
+
+template <int DAG, int MULTI>
+__global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) {
+    const WilsonArgs &A = K.A;
+    if (A.fuse.use_state && A.red.st->done) return;
+    extern __shared__ __align__(128) unsigned char tm_smem[];
+    cplx *const win = reinterpret_cast<cplx *>(tm_smem);                     // [2][W][12][32]
+    cplx *const plane = win + 2 * TM_W * TM_REC;                             // [4 (mu)][W][6][32]
+    uint64_t *const wbar = reinterpret_cast<uint64_t *>(plane + 4 * TM_W * TM2_SUB);  // [2] window slots
+    uint64_t *const pbar = wbar + 2;                                         // [4] link planes
+    const Geom &g = A.g;
+    const cplx *const links = A.links12;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nsb = K.nsb, T = g.T, Lc = K.Lc;
+    const int npatch = g.nt[0] * g.nt[1] * g.nt[2];
+
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 2; j++) mbar_init(&wbar[j], TM_W);
+        for (int j = 0; j < 4; j++) mbar_init(&pbar[j], TM_W);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t wph = 0, pph = 0;
+    auto wait_w = [&](int j) { mbar_wait(&wbar[j], (wph >> j) & 1u); wph ^= 1u << j; };
+    auto wait_p = [&](int j) { mbar_wait(&pbar[j], (pph >> j) & 1u); pph ^= 1u << j; };
+
+    const int w0 = w % g.c[0], w1 = (w / g.c[0]) % g.c[1], w2 = w / (g.c[0] * g.c[1]);
+    const int tshift = (MULTI && g.part[3]) ? 1 : 0;
+    bool halo_ready = false;
+    double red[3] = {0.0, 0.0, 0.0};
+    const double mk = -A.kappa;
+    const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
+    cplx *const dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
+
+    for (int task = blockIdx.x; task < K.ntasks; task += gridDim.x) {
+        const int patch = task % npatch, chunk = task / npatch;
+        const int p0 = patch % g.nt[0], p1 = (patch / g.nt[0]) % g.nt[1], p2 = patch / (g.nt[0] * g.nt[1]);
+        const int bslice = (p0 * g.c[0] + w0) + g.nb[0] * ((p1 * g.c[1] + w1) + g.nb[1] * (p2 * g.c[2] + w2));
+        const int t0 = chunk * Lc + tshift;
+        auto slice_of = [&](int rel) { return (t0 - 1 + rel + T) % T; };
+
+        const int ssl = bslice * 32 + lane;
+        const int cx = ssl % g.X, cy = (ssl / g.X) % g.Y, cz = ssl / (g.X * g.Y);
+        int nbl[6], nl[6], nw[6];
+        bool wr[6];
+        {
+            const int coord[3] = {cx, cy, cz}, dim[3] = {g.X, g.Y, g.Z}, stride[3] = {1, g.X, g.X * g.Y};
+#pragma unroll
+            for (int mu = 0; mu < 3; mu++) {
+#pragma unroll
+                for (int f = 0; f < 2; f++) {
+                    const int d = mu * 2 + f;
+                    const bool wrapd = f == 0 ? (coord[mu] == dim[mu] - 1) : (coord[mu] == 0);
+                    const int nssl = f == 0 ? (wrapd ? ssl - (dim[mu] - 1) * stride[mu] : ssl + stride[mu])
+                                            : (wrapd ? ssl + (dim[mu] - 1) * stride[mu] : ssl - stride[mu]);
+                    wr[d] = wrapd;
+                    nbl[d] = nssl >> 5; nl[d] = nssl & 31;
+                    const int q0 = nbl[d] % g.nb[0], q1 = (nbl[d] / g.nb[0]) % g.nb[1], q2 = nbl[d] / (g.nb[0] * g.nb[1]);
+                    const bool inp = q0 >= p0 * g.c[0] && q0 < (p0 + 1) * g.c[0] && q1 >= p1 * g.c[1] && q1 < (p1 + 1) * g.c[1] &&
+                                     q2 >= p2 * g.c[2] && q2 < (p2 + 1) * g.c[2];
+                    nw[d] = inp ? (q0 - p0 * g.c[0]) + g.c[0] * ((q1 - p1 * g.c[1]) + g.c[1] * (q2 - p2 * g.c[2])) : -1;
+                }
+            }
+        }
+
+        __syncthreads();                  // everybody is done reading the previous task's window and planes
+        if (MULTI && !halo_ready) {
+            bool need = false;
+            const int pc[3] = {p0, p1, p2};
+            for (int mu = 0; mu < 3; mu++) need = need || (g.part[mu] && (pc[mu] == 0 || pc[mu] == g.nt[mu] - 1));
+            if (need) { wait_halo_flags(g, A.halo); halo_ready = true; }
+        }
+        if (lane == 0) {
+            for (int rel = 1; rel <= 2; rel++) {                                 // slices of step 1 and step 2 -> slots 1, 0
+                mbar_arrive_expect_tx(&wbar[rel & 1], TM_REC_BYTES);
+                bulk_g2s(win + ((size_t)(rel & 1) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)slice_of(rel) * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel & 1]);
+            }
+            const size_t b0 = (size_t)bslice + (size_t)slice_of(1) * nsb;
+            for (int mu = 0; mu < 4; mu++) {                                     // forward links of the first slice
+                mbar_arrive_expect_tx(&pbar[mu], TM2_SUB_BYTES);
+                bulk_g2s(plane + ((size_t)mu * TM_W + w) * TM2_SUB, links + (b0 * 4 + mu) * TM2_SUB, TM2_SUB_BYTES, &pbar[mu]);
+            }
+        }
+        cplx c0[3], c1[3];                // carried t-backward hop
+        {
+            const int tf = slice_of(1);
+            if (!(MULTI && g.part[3] && tf == 0)) {
+                const size_t bm = (size_t)bslice + (size_t)slice_of(0) * nsb;
+                cplx p[12], u[9];
+                ld_spinor_g(p, A.in + bm * TM_REC + lane);
+                ld_link12_g(u, links + (bm * 4 + 3) * TM2_SUB + lane);
+                carry_make<DAG>(c0, c1, p, u, tf == 0, A.bc[3]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { c0[a] = cmake(0.0, 0.0); c1[a] = cmake(0.0, 0.0); }
+            }
+        }
+
+        for (int r = 1; r <= Lc; r++) {
+            const int t = slice_of(r);
+            const size_t blk = (size_t)bslice + (size_t)t * nsb;
+            if (MULTI && !halo_ready && g.part[3] && (t == T - 1 || t == 0)) { wait_halo_flags(g, A.halo); halo_ready = true; }
+            const cplx *cur = win + (size_t)(r & 1) * TM_W * TM_REC;
+            const cplx *up = win + (size_t)((r + 1) & 1) * TM_W * TM_REC;
+            const size_t base = blk * TM_REC + lane;
+            if (A.fuse.axpy_r || A.fuse.dot_with || A.fuse.shift_src) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    if (A.fuse.axpy_r) prefetch_l2(A.fuse.axpy_r + base + k * 32);
+                    if (A.fuse.dot_with) prefetch_l2(A.fuse.dot_with + base + k * 32);
+                    if (A.fuse.shift_src) prefetch_l2(A.fuse.shift_src + base + k * 32);
+                }
+            }
+            if (K.prefetch && r == Lc && task + (int)gridDim.x < K.ntasks) {
+                // the next task starts cold (a new chunk of another patch): its window records, link planes and carry operands are
+                // on their way to L2 while this task's last step runs, so its priming copies and loads are L2 hits
+                const int ntask = task + (int)gridDim.x, np = ntask % npatch;
+                const int n0 = np % g.nt[0], n1 = (np / g.nt[0]) % g.nt[1], n2 = np / (g.nt[0] * g.nt[1]);
+                const size_t nbs = (size_t)((n0 * g.c[0] + w0) + g.nb[0] * ((n1 * g.c[1] + w1) + g.nb[1] * (n2 * g.c[2] + w2)));
+                const int nt0 = (ntask / npatch) * Lc + tshift;
+                for (int rel = 0; rel < 3; rel++) {
+                    const size_t nb = nbs + (size_t)((nt0 - 1 + rel + T) % T) * nsb;
+                    const char *rec = reinterpret_cast<const char *>(A.in + nb * TM_REC);
+                    prefetch_l2(rec + lane * 128);
+                    if (lane < 16) prefetch_l2(rec + (32 + lane) * 128);
+                    if (lane < 24) {
+                        if (rel == 0) prefetch_l2(reinterpret_cast<const char *>(links + (nb * 4 + 3) * TM2_SUB) + lane * 128);
+                        if (rel == 1) {
+                            for (int mu = 0; mu < 4; mu++) prefetch_l2(reinterpret_cast<const char *>(links + (nb * 4 + mu) * TM2_SUB) + lane * 128);
+                        }
+                    }
+                }
+            }
+            cplx acc[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) acc[k] = cmake(0.0, 0.0);
+            cplx p[12], u[9];
+            if (r == 1) wait_w(1);        // later steps: the slot was waited for as `up` by the previous step
+
+#define TM2_SPATIAL(MU)                                                                                                     \
+            {                                                                                                               \
+                wait_p(MU);                                                                                                 \
+                const int df = MU * 2, db = MU * 2 + 1;                                                                     \
+                const cplx *pl = plane + (size_t)MU * TM_W * TM2_SUB;                                                       \
+                ld_link12_s(u, pl + (size_t)w * TM2_SUB + lane);                                                            \
+                if (MULTI && wr[df] && g.part[MU]) halo_hop_regs<MU, 1, DAG>(acc, A, face_index<MU>(g, cx, cy, cz, t), u);  \
+                else {                                                                                                      \
+                    if (nw[df] >= 0) ld_spinor_s(p, cur + (size_t)nw[df] * TM_REC + nl[df]);                                \
+                    else             ld_spinor_g(p, A.in + ((size_t)nbl[df] + (size_t)t * nsb) * TM_REC + nl[df]);          \
+                    hop_regs<MU, 1, DAG>(acc, p, u, wr[df], A.bc[MU]);                                                      \
+                }                                                                                                           \
+                if (MULTI && wr[db] && g.part[MU]) halo_hop_regs<MU, 0, DAG>(acc, A, face_index<MU>(g, cx, cy, cz, t), u);  \
+                else if (nw[db] >= 0) { ld_spinor_s(p, cur + (size_t)nw[db] * TM_REC + nl[db]); ld_link12_s(u, pl + (size_t)nw[db] * TM2_SUB + nl[db]); } \
+                else {                                                                                                      \
+                    ld_spinor_g(p, A.in + ((size_t)nbl[db] + (size_t)t * nsb) * TM_REC + nl[db]);                           \
+                    ld_link12_g(u, links + (((size_t)nbl[db] + (size_t)t * nsb) * 4 + MU) * TM2_SUB + nl[db]);              \
+                }                                                                                                           \
+                if (!(MULTI && wr[db] && g.part[MU])) hop_regs<MU, 0, DAG>(acc, p, u, wr[db], A.bc[MU]);                    \
+                __syncthreads();                                                                                            \
+                if (lane == 0 && r < Lc) {                                       /* forward links of the next slice */      \
+                    mbar_arrive_expect_tx(&pbar[MU], TM2_SUB_BYTES);                                                        \
+                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM2_SUB, links + (((size_t)bslice + (size_t)slice_of(r + 1) * nsb) * 4 + MU) * TM2_SUB, TM2_SUB_BYTES, &pbar[MU]); \
+                }                                                                                                           \
+            }
+            TM2_SPATIAL(0) TM2_SPATIAL(1) TM2_SPATIAL(2)
+#undef TM2_SPATIAL
+            // from here on the warp touches only its own records (cur[w], up[w], plane 3 [w])
+
+            // ---- t forward ---------------------------------------------------------------------------------------------------------
+            wait_w((r + 1) & 1);
+            wait_p(3);
+            ld_link12_s(u, plane + ((size_t)3 * TM_W + w) * TM2_SUB + lane);
+            if (MULTI && g.part[3] && t == T - 1) halo_hop_regs<3, 1, DAG>(acc, A, face_index<3>(g, cx, cy, cz, t), u);
+            else {
+                ld_spinor_s(p, up + (size_t)w * TM_REC + lane);
+                hop_regs<3, 1, DAG>(acc, p, u, t == T - 1, A.bc[3]);
+            }
+            // ---- t backward: the carry of the previous step (or the halo) ---------------------------------------------------------
+            if (MULTI && g.part[3] && t == 0) halo_hop_regs<3, 0, DAG>(acc, A, face_index<3>(g, cx, cy, cz, t), u);
+            else {
+#pragma unroll
+                for (int a = 0; a < 3; a++) reconstruct<3, (DAG ? -1 : +1)>(acc, a, c0[a], c1[a]);
+            }
+            ld_spinor_s(p, cur + (size_t)w * TM_REC + lane);                     // own spinor: next carry and the epilogue
+            if (r < Lc && !(MULTI && g.part[3] && t == T - 1)) carry_make<DAG>(c0, c1, p, u, t == T - 1, A.bc[3]);
+
+            // ---- epilogue -----------------------------------------------------------------------------------------------------------
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const cplx xi = p[k];
+                cplx yk = cmake(fma(mk, acc[k].x, xi.x), fma(mk, acc[k].y, xi.y));
+                if (A.fuse.shift_src) {
+                    const cplx sv = ldg128(A.fuse.shift_src + base + k * 32);
+                    yk.x = fma(A.fuse.shift, sv.x, yk.x); yk.y = fma(A.fuse.shift, sv.y, yk.y);
+                }
+                if (A.fuse.axpy_r) {
+                    const cplx rv = A.fuse.axpy_r[base + k * 32];
+                    yk = cmake(fma(malpha, yk.x, rv.x), fma(malpha, yk.y, rv.y));
+                }
+                if (A.fuse.dot_with) {
+                    const cplx wv = ldg128(A.fuse.dot_with + base + k * 32);
+                    red[0] = fma(wv.x, yk.x, red[0]); red[0] = fma(wv.y, yk.y, red[0]);
+                    red[1] = fma(wv.x, yk.y, red[1]); red[1] = fma(-wv.y, yk.x, red[1]);
+                }
+                red[2] = fma(yk.x, yk.x, red[2]); red[2] = fma(yk.y, yk.y, red[2]);
+                dst[base + k * 32] = yk;
+            }
+            __syncwarp();                 // every lane has consumed its own spinor and t link: the warp's records may be overwritten
+            if (lane == 0) {
+                if (r < Lc) {                                                    // t links of the next slice
+                    mbar_arrive_expect_tx(&pbar[3], TM2_SUB_BYTES);
+                    bulk_g2s(plane + ((size_t)3 * TM_W + w) * TM2_SUB, links + (((size_t)bslice + (size_t)slice_of(r + 1) * nsb) * 4 + 3) * TM2_SUB, TM2_SUB_BYTES, &pbar[3]);
+                }
+                if (r + 2 <= Lc + 1) {                                           // slice of step r+2 into the slot this step leaves
+                    mbar_arrive_expect_tx(&wbar[r & 1], TM_REC_BYTES);
+                    bulk_g2s(win + ((size_t)(r & 1) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)slice_of(r + 2) * nsb) * TM_REC, TM_REC_BYTES, &wbar[r & 1]);
+                }
+            }
+        }
+    }
+    if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
+}
+
 // geometry / configuration test shared with comm.cu (which then feeds the halo slots with the separate pack kernel)
 bool wilson_tmarch_ok(const lqcd_ctx *ctx, const lqcd_op *op) {
     static int family = -1;
     if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = e ? atoi(e) : 0; }
     const Geom &g = ctx->g;
-    if (family != 4 || op->kind != LQCD_WILSON || op->csw != 0.0 || op->r != 1.0) return false;
+    if ((family != 4 && family != 5) || op->kind != LQCD_WILSON || op->csw != 0.0 || op->r != 1.0) return false;
     return g.regular && g.s[3] == 1 && g.c[3] == 1 && g.c[0] * g.c[1] * g.c[2] == TM_W && g.T >= 2 && (!g.part[3] || g.T >= 3);
 }
 
 // LQCD_OK if launched; LQCD_ERR_STATE if the geometry / variant does not qualify (caller falls back to the register-resident kernel)
+int ensure_links12(lqcd_ctx *ctx, int *use);       // links12.cu
+
 int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStream_t s, bool halo, bool self_pack) {
     const Geom &g = ctx->g;
+    static int family = -1;
+    if (family < 0) { const char *e = getenv("LQCD_WILSON_KERNEL"); family = e ? atoi(e) : 0; }
+    const bool gen2 = family == 5;
     // multi-rank: the separate pack kernel on the priority stream feeds the halo slots (no self-packing / interior-only variants)
     if (self_pack || A.clover || (ctx->nranks > 1 && !halo)) return LQCD_ERR_STATE;
     if (!g.regular || g.s[3] != 1 || g.c[3] != 1 || g.c[0] * g.c[1] * g.c[2] != TM_W || g.T < 2 || (g.part[3] && g.T < 3)) return LQCD_ERR_STATE;
@@ -358,14 +643,44 @@ int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStr
         double best = 1e300;
         for (int c = 1; c <= g.T / 2; c++) {
             if (g.T % c) continue;
-            const int tasks = npatch * c, grid = tasks < ctx->num_sms ? tasks : ctx->num_sms;
-            const double cost = (double)((tasks + grid - 1) / grid) * (g.T / c + 1.0);
+            const int slots = gen2 ? 2 * ctx->num_sms : ctx->num_sms;
+            const int tasks = npatch * c, grid = tasks < slots ? tasks : slots;
+            const double cost = (double)((tasks + grid - 1) / grid) * (g.T / c + (gen2 ? 0.5 : 1.0));
             if (cost < best) { best = cost; nchunk = c; }
         }
         if (const char *e = getenv("LQCD_TM_CHUNKS")) { int v = atoi(e); if (v >= 1 && g.T % v == 0) nchunk = v; }
     }
     TMArgs K;
+    K.prefetch = 0;
     K.A = A; K.Lc = g.T / nchunk; K.nchunk = nchunk; K.nsb = g.nb[0] * g.nb[1] * g.nb[2]; K.ntasks = npatch * nchunk;
+    if (gen2) {
+        int g12 = 0;
+        LQCD_TRY(ensure_links12(ctx, &g12));
+        if (!g12) return LQCD_ERR_STATE;          // links are not SU(3): the register-resident kernel reads the full matrices
+        K.A.links12 = ctx->links12;
+        static int pf = -1;
+        if (pf < 0) { const char *e = getenv("LQCD_TM_PREFETCH"); pf = (e && atoi(e) == 1) ? 1 : 0; }   // measured: 187.9 us with, 182.4 us without
+        K.prefetch = pf;
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
+            attr2_set = true;
+        }
+        const int slots = 2 * ctx->num_sms, grid2 = K.ntasks < slots ? K.ntasks : slots;
+        if (halo) {
+            if (dagger) wilson_tmarch2_kernel<1, 1><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+            else        wilson_tmarch2_kernel<0, 1><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+        } else {
+            if (dagger) wilson_tmarch2_kernel<1, 0><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+            else        wilson_tmarch2_kernel<0, 0><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+        }
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return LQCD_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));

@@ -112,8 +112,9 @@ def test_evenodd_beats_full_solve_and_keeps_plain_path():
 
 # ---- Wilson kernel families: register-resident kernel (default; two-row or full links) and the experimental t-marching TMA kernel ------
 @pytest.mark.parametrize("env", [{"LQCD_WILSON_KERNEL": "4"}, {"LQCD_WILSON_KERNEL": "4", "LQCD_TM_CHUNKS": "1"}, {"LQCD_WILSON_KERNEL": "4", "LQCD_TM_CHUNKS": "2"},
-                                 {}, {"LQCD_LINKS12": "0"}],
-                         ids=["tmarch-auto", "tmarch-1chunk", "tmarch-2chunks", "register-kernel-two-row-links", "register-kernel-full-links"])
+                                 {"LQCD_WILSON_KERNEL": "5"}, {"LQCD_WILSON_KERNEL": "5", "LQCD_TM_CHUNKS": "2"}, {}, {"LQCD_LINKS12": "0"}],
+                         ids=["tmarch-auto", "tmarch-1chunk", "tmarch-2chunks", "tmarch2-auto", "tmarch2-2chunks", "register-kernel-two-row-links",
+                              "register-kernel-full-links"])
 def test_wilson_kernel_families_match_oracle(env):
     import os
     import subprocess
