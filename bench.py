@@ -303,6 +303,8 @@ EXPERIMENTS = {
     "md": ({}, "device-resident Sexton-Weingarten trajectory with Wilson pseudofermions, 16^4"),
     "force": ({}, "fermion-force outer-product kernels (Wilson, staggered) alone, 32^4"),
     "rhmc_md": ({}, "device-resident RHMC trajectory (staggered Nf = 2: multi-shift CG + rational force per step), 16^4"),
+    # last: verified under tests/emu only (a hang here costs the leg's remaining budget, nothing else)
+    "tmarch2_pipelined": ({"LQCD_WILSON_KERNEL": "5", "LQCD_TM_PIPE": "1"}, "second-generation t-marching kernel with pipelined tasks: the next task's copies are requested during the last step of the current one, x phase without a CTA barrier"),
 }
 
 
@@ -352,7 +354,7 @@ def _experiment_body(name, dims, out):
         ctx.call("lqcd_time_dslash", C.byref(op), y.h, x.h, L.OP_D, reps, 0, C.byref(mean), C.byref(mn))
         return mean.value
 
-    if name in ("default", "register_kernel", "links_full", "tmarch_kernel", "tmarch2_kernel"):
+    if name in ("default", "register_kernel", "links_full", "tmarch_kernel", "tmarch2_kernel", "tmarch2_pipelined"):
         ctx, op, x, y = setup(small)
         ctx.call("lqcd_dslash", C.byref(op), y.h, x.h, L.OP_D)
         got = y.to_host()
@@ -584,6 +586,7 @@ EXPERIMENTS_MULTI = {       # most informative first: the leg stops starting new
     "separate_pack": ({"LQCD_SELF_PACK": "0"}, "pack kernel on the priority stream"),
     "links_full": ({"LQCD_LINKS12": "0"}, "full 3x3 links instead of the two-row copy"),
     "pack_fence_sys": ({"LQCD_PACK_FENCE": "sys"}, "system-scope fence per pack CTA (round-1 default)"),
+    "tmarch2_pipelined": ({"LQCD_WILSON_KERNEL": "5", "LQCD_TM_PIPE": "1"}, "second-generation t-marching kernel with pipelined tasks (tests/emu only so far)"),
 }
 
 

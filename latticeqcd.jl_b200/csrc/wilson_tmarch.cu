@@ -394,7 +394,12 @@ __device__ __forceinline__ void carry_make(cplx (&c0)[3], cplx (&c1)[3], const c
     }
 }
 
-template <int DAG, int MULTI>
+// PIPE = 1 (LQCD_TM_PIPE=1, not yet on hardware): tasks are pipelined -- during the LAST step of a task every plane is refilled with
+// the NEXT task's first slice as soon as its direction is done, and every warp requests its own window records and t plane of the
+// next task right after its epilogue, so a task starts with its copies a step old instead of just issued (no CTA barrier between
+// tasks: the mbarriers order the cross-warp reads); and when a block spans the whole x extent the x plane is private to a warp,
+// so the x phase ends with a warp-level sync (two CTA barriers per step).
+template <int DAG, int MULTI, int PIPE>
 __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) {
     const WilsonArgs &A = K.A;
     if (A.fuse.use_state && A.red.st->done) return;
@@ -426,6 +431,8 @@ __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) 
     const double mk = -A.kappa;
     const double malpha = A.fuse.axpy_r ? -A.red.st->alpha : 0.0;
     cplx *const dst = A.fuse.axpy_r ? A.fuse.axpy_r : A.out;
+    const bool xpriv = PIPE && g.nb[0] == 1;          // both x neighbours of a site live in the site's own block
+    bool primed = false;                              // PIPE: the previous task's last step requested this task's first copies
 
     for (int task = blockIdx.x; task < K.ntasks; task += gridDim.x) {
         const int patch = task % npatch, chunk = task / npatch;
@@ -458,14 +465,14 @@ __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) 
             }
         }
 
-        __syncthreads();                  // everybody is done reading the previous task's window and planes
+        if (!(PIPE && primed)) __syncthreads();      // everybody is done reading the previous task's window and planes
         if (MULTI && !halo_ready) {
             bool need = false;
             const int pc[3] = {p0, p1, p2};
             for (int mu = 0; mu < 3; mu++) need = need || (g.part[mu] && (pc[mu] == 0 || pc[mu] == g.nt[mu] - 1));
             if (need) { wait_halo_flags(g, A.halo); halo_ready = true; }
         }
-        if (lane == 0) {
+        if (lane == 0 && !(PIPE && primed)) {
             for (int rel = 1; rel <= 2; rel++) {                                 // slices of step 1 and step 2 -> slots 1, 0
                 mbar_arrive_expect_tx(&wbar[rel & 1], TM_REC_BYTES);
                 bulk_g2s(win + ((size_t)(rel & 1) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)slice_of(rel) * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel & 1]);
@@ -490,6 +497,18 @@ __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) 
                 for (int a = 0; a < 3; a++) { c0[a] = cmake(0.0, 0.0); c1[a] = cmake(0.0, 0.0); }
             }
         }
+
+        // PIPE: this warp's block and first slices of the CTA's next task
+        const bool nxt = PIPE && task + (int)gridDim.x < K.ntasks;
+        size_t nbs = 0;
+        int nt0 = 0;
+        if (nxt) {
+            const int ntask = task + (int)gridDim.x, np = ntask % npatch;
+            const int n0 = np % g.nt[0], n1 = (np / g.nt[0]) % g.nt[1], n2 = np / (g.nt[0] * g.nt[1]);
+            nbs = (size_t)((n0 * g.c[0] + w0) + g.nb[0] * ((n1 * g.c[1] + w1) + g.nb[1] * (n2 * g.c[2] + w2)));
+            nt0 = (ntask / npatch) * Lc + tshift;
+        }
+        auto nslice = [&](int rel) { return (nt0 - 1 + rel + T) % T; };
 
         for (int r = 1; r <= Lc; r++) {
             const int t = slice_of(r);
@@ -551,10 +570,11 @@ __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) 
                     ld_link12_g(u, links + (((size_t)nbl[db] + (size_t)t * nsb) * 4 + MU) * TM2_SUB + nl[db]);              \
                 }                                                                                                           \
                 if (!(MULTI && wr[db] && g.part[MU])) hop_regs<MU, 0, DAG>(acc, p, u, wr[db], A.bc[MU]);                    \
-                __syncthreads();                                                                                            \
-                if (lane == 0 && r < Lc) {                                       /* forward links of the next slice */      \
+                if (MU == 0 && xpriv) __syncwarp(); else __syncthreads();                                                   \
+                if (lane == 0 && (r < Lc || nxt)) {                              /* forward links of the next slice (PIPE, last step: of the next task's first slice) */ \
+                    const size_t nb_ = r < Lc ? (size_t)bslice + (size_t)slice_of(r + 1) * nsb : nbs + (size_t)nslice(1) * nsb;   \
                     mbar_arrive_expect_tx(&pbar[MU], TM2_SUB_BYTES);                                                        \
-                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM2_SUB, links + (((size_t)bslice + (size_t)slice_of(r + 1) * nsb) * 4 + MU) * TM2_SUB, TM2_SUB_BYTES, &pbar[MU]); \
+                    bulk_g2s(plane + ((size_t)MU * TM_W + w) * TM2_SUB, links + (nb_ * 4 + MU) * TM2_SUB, TM2_SUB_BYTES, &pbar[MU]); \
                 }                                                                                                           \
             }
             TM2_SPATIAL(0) TM2_SPATIAL(1) TM2_SPATIAL(2)
@@ -610,8 +630,18 @@ __global__ void __launch_bounds__(128, 2) wilson_tmarch2_kernel(const TMArgs K) 
                     mbar_arrive_expect_tx(&wbar[r & 1], TM_REC_BYTES);
                     bulk_g2s(win + ((size_t)(r & 1) * TM_W + w) * TM_REC, A.in + ((size_t)bslice + (size_t)slice_of(r + 2) * nsb) * TM_REC, TM_REC_BYTES, &wbar[r & 1]);
                 }
+                if (r == Lc && nxt) {                                            // PIPE: the next task's t plane and both window records of this warp
+                    const size_t nb1 = nbs + (size_t)nslice(1) * nsb;
+                    mbar_arrive_expect_tx(&pbar[3], TM2_SUB_BYTES);
+                    bulk_g2s(plane + ((size_t)3 * TM_W + w) * TM2_SUB, links + (nb1 * 4 + 3) * TM2_SUB, TM2_SUB_BYTES, &pbar[3]);
+                    for (int rel = 1; rel <= 2; rel++) {
+                        mbar_arrive_expect_tx(&wbar[rel & 1], TM_REC_BYTES);
+                        bulk_g2s(win + ((size_t)(rel & 1) * TM_W + w) * TM_REC, A.in + (nbs + (size_t)nslice(rel) * nsb) * TM_REC, TM_REC_BYTES, &wbar[rel & 1]);
+                    }
+                }
             }
         }
+        primed = nxt;
     }
     if (A.fuse.dot_with || A.fuse.want_norm) grid_reduce_finish<3>(red, A.red, A.fuse.finish);
 }
@@ -661,22 +691,26 @@ int launch_wilson_tmarch(lqcd_ctx *ctx, const WilsonArgs &A, int dagger, cudaStr
         static int pf = -1;
         if (pf < 0) { const char *e = getenv("LQCD_TM_PREFETCH"); pf = (e && atoi(e) == 1) ? 1 : 0; }   // measured: 187.9 us with, 182.4 us without
         K.prefetch = pf;
+        static int pipe = -1;
+        if (pipe < 0) { const char *e = getenv("LQCD_TM_PIPE"); pipe = (e && atoi(e) == 1) ? 1 : 0; }
         static bool attr2_set = false;
         if (!attr2_set) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
-            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
-            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
-            CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES));
+#define TM2_ATTR(D, M, P) CUDA_TRY(ctx, cudaFuncSetAttribute(wilson_tmarch2_kernel<D, M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM2_SMEM_BYTES))
+            TM2_ATTR(0, 0, 0); TM2_ATTR(1, 0, 0); TM2_ATTR(0, 1, 0); TM2_ATTR(1, 1, 0);
+            TM2_ATTR(0, 0, 1); TM2_ATTR(1, 0, 1); TM2_ATTR(0, 1, 1); TM2_ATTR(1, 1, 1);
+#undef TM2_ATTR
             attr2_set = true;
         }
         const int slots = 2 * ctx->num_sms, grid2 = K.ntasks < slots ? K.ntasks : slots;
-        if (halo) {
-            if (dagger) wilson_tmarch2_kernel<1, 1><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
-            else        wilson_tmarch2_kernel<0, 1><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+#define TM2_GO(D, M, P) wilson_tmarch2_kernel<D, M, P><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K)
+        if (pipe) {
+            if (halo) { if (dagger) TM2_GO(1, 1, 1); else TM2_GO(0, 1, 1); }
+            else      { if (dagger) TM2_GO(1, 0, 1); else TM2_GO(0, 0, 1); }
         } else {
-            if (dagger) wilson_tmarch2_kernel<1, 0><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
-            else        wilson_tmarch2_kernel<0, 0><<<grid2, 128, TM2_SMEM_BYTES, s>>>(K);
+            if (halo) { if (dagger) TM2_GO(1, 1, 0); else TM2_GO(0, 1, 0); }
+            else      { if (dagger) TM2_GO(1, 0, 0); else TM2_GO(0, 0, 0); }
         }
+#undef TM2_GO
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
         return LQCD_OK;

@@ -374,6 +374,9 @@ cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof *p);
     p->major = 10; p->minor = 0; p->multiProcessorCount = 148; p->clockRate = 1965000; p->sharedMemPerBlockOptin = 227 << 10;
+    // LQCD_EMU_SMS: pretend to have fewer SMs, so that persistent kernels (grid = a multiple of the SM count) loop over several
+    // tasks per CTA on the small lattices the emulation can afford
+    if (const char *e = getenv("LQCD_EMU_SMS")) { const int v = atoi(e); if (v >= 1 && v <= 148) p->multiProcessorCount = v; }
     snprintf(p->name, sizeof p->name, "emulated sm_100 (tests/emu)");
     return cudaSuccess;
 }

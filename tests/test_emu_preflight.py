@@ -88,18 +88,22 @@ def test_multirank_under_emulation(emu_lib, dims, pg, kind):
 
 @pytest.mark.parametrize("bulk", ["early", "late"])
 @pytest.mark.parametrize("chunks", ["auto", "1", "2"])
-@pytest.mark.parametrize("family", ["4", "5"])
+@pytest.mark.parametrize("family", ["4", "5", "5-pipelined"])
 def test_tmarch_kernel_under_emulation(emu_lib, bulk, chunks, family):
     """t-marching TMA kernel (cp.async.bulk window + link planes on mbarriers, modelled by tests/emu): bulk copies completing at
     issue (earliest) and only when somebody waits on their mbarrier (latest) -- a missing wait or a premature slot refill
     shows up as NaNs / mismatches in one of the two; chunks = tasks per patch (window re-priming, persistent task loop)"""
-    extra = {"LQCD_WILSON_KERNEL": family}     # 4: one CTA per SM, 3-slot window; 5: two CTAs per SM, two-row planes, carried t- hop
+    # 4: one CTA per SM, 3-slot window; 5: two CTAs per SM, two-row planes, carried t- hop; pipelined: LQCD_TM_PIPE=1 (the next task's
+    # copies requested during the last step).  LQCD_EMU_SMS=1: one emulated SM, so that every CTA loops over several tasks.
+    extra = {"LQCD_WILSON_KERNEL": family[0], "LQCD_EMU_SMS": "1"}
+    if family.endswith("pipelined"):
+        extra["LQCD_TM_PIPE"] = "1"
     if chunks != "auto":
         extra["LQCD_TM_CHUNKS"] = chunks
     r = subprocess.run([sys.executable, "tests/tmarch_worker.py"], cwd=ROOT, capture_output=True, text=True, timeout=900,
                        env=_env(emu_lib, LQCD_EMU_BULK=bulk, LQCD_EMU_TRACE="1", **extra))
     assert r.returncode == 0 and "TMARCH OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
-    m = re.search(r"launches wilson_tmarch%s_kernel\s+(\d+)" % ("2" if family == "5" else ""), r.stderr)
+    m = re.search(r"launches wilson_tmarch%s_kernel\s+(\d+)" % ("2" if family[0] == "5" else ""), r.stderr)
     assert m and int(m.group(1)) > 500 and "launches wilson_dslash_kernel" not in r.stderr, r.stderr[-2000:]
 
 
@@ -144,7 +148,7 @@ def test_bench_experiments_leg_under_emulation(emu_lib, monkeypatch):
     assert not bad, bad
     assert res["staggered_mrhs"]["bit_identical_to_single_rhs"] and res["staggered_mrhs_r3"]["bit_identical_to_single_rhs"]
     assert res["tmarch_kernel"]["max_rel_dev_vs_default"] < 1e-13 and res["links_full"]["max_rel_dev_vs_default"] < 1e-13
-    assert res["tmarch2_kernel"]["bit_identical_to_default"]
+    assert res["tmarch2_kernel"]["bit_identical_to_default"] and res["tmarch2_pipelined"]["bit_identical_to_default"]
 
 
 def test_bench_multirank_experiments_leg_under_emulation(emu_lib):
